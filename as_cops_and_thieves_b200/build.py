@@ -1,0 +1,57 @@
+"""In-tree build of the CUDA extension: ``nvcc`` -> ``as_cops_and_thieves_b200/libcat_b200.so``.
+
+sm_100a only (``-gencode arch=compute_100a,code=sm_100a``), ``-lineinfo`` so ncu's source page maps
+to ``csrc/cat_b200.cu``.  The shared library has a plain C ABI (``include/cat_b200.h``) and links
+only the CUDA runtime; Python binds it with ctypes (``_lib.py``).  nvcc cross-compiles without a
+GPU, so this runs on the CPU-only build box too.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+SRC = PKG / "csrc" / "cat_b200.cu"
+LIB = PKG / "libcat_b200.so"
+DEPS = [SRC, ROOT / "include" / "cat_b200.h", ROOT / "include" / "cat_philox.h"]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found (needed to build libcat_b200.so)")
+
+
+def nvcc_cmd(out: Path = LIB, extra=()) -> list:
+    cmd = [
+        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-o", str(out), str(SRC),
+    ]
+    if Path("/usr/bin/g++").exists():
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    return cmd + list(extra)
+
+
+def up_to_date() -> bool:
+    return LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if up_to_date() and not force:
+        return LIB
+    proc = subprocess.run(nvcc_cmd(), capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed building libcat_b200.so")
+    (PKG / "build_ptxas.log").write_text(proc.stdout + proc.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

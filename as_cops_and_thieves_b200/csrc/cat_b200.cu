@@ -1,0 +1,1244 @@
+// cat_b200.cu — hand-written sm_100a kernels + C ABI for the batched cops-and-thieves step.
+//
+// One warp owns one world for one lockstep transition (persistent CTAs loop over worlds):
+//   state record (coalesced) -> termination test -> action impulses -> 90-ray sensor sweep per
+//   agent (one lane per ray, uniform-grid walk over the wall hulls staged in shared memory by one
+//   TMA bulk copy per CTA) -> float16 observation chain -> rewards -> team-shared merge ->
+//   rigid-body step (position integrate, circle-hull / circle-circle contacts, warm start,
+//   10 sequential-impulse iterations) -> auto-reset (Philox) -> outputs + state record (coalesced).
+//
+// Restates /root/reference/src/environments/base_env.py:354-413,521-554,286-352,
+// /root/reference/src/agents/entity.py:126-241, cop.py:49-75, thief.py:48-69,
+// /root/reference/src/environments/observation_spaces.py:67-131 and the Chipmunk2D 7.0.3
+// routines they call (cpSpaceStep, cpArbiterPreStep/ApplyImpulse, CircleToPoly, CircleToCircle,
+// cpShapeSegmentQuery, cpPolyShapeSegmentQuery, CircleSegmentQuery, cpBBSegmentQuery) in fp32,
+// origin-relative so that ray distances keep ~1e-5 absolute accuracy at coordinates ~1e3.
+//
+// No CPU fallback, no Triton, no tensor cores (the path is ALU/latency bound).
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cat_b200.h"
+#include "../../include/cat_philox.h"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kSlots = CAT_WALL_SLOTS;
+constexpr int kNear = 4;            // hulls an origin can be "inside" (alpha = 0 rule) per agent
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+
+enum { TYPE_WALL = 0, TYPE_COP = 1, TYPE_THIEF = 2, TYPE_EMPTY = 4 };
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2, MODE_INIT = 3 };
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(CAT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+  } while (0)
+
+// ------------------------------------------------------------------ shared-memory map blob
+struct BlobHeader {
+  int32_t n_hulls, n_edges, nx, ny;
+  float gx0, gy0, cell, inv_cell;
+  int32_t off_edge, off_len, off_hbb, off_heo;
+  int32_t off_rayoff, off_raylist, off_conoff, off_conlist;
+  int32_t off_dir, off_regoff, off_regions, off_initpos;
+  int32_t pad[4];
+};
+static_assert(sizeof(BlobHeader) == 96, "header must stay 16-byte sized");
+
+struct MapView {
+  const float4* edge;      // vx, vy, nx, ny  (vertex ending the edge, outward normal)
+  const float* edge_len;
+  const float4* hull_bb;   // l,b,r,t grown by the wall radius (the shape's bb)
+  const uint32_t* hull_eo; // edge offset | count << 16
+  const uint16_t* ray_off;
+  const uint16_t* ray_list;
+  const uint16_t* con_off;
+  const uint16_t* con_list;
+  const float2* dir;       // unit ray directions
+  const int32_t* reg_off;
+  const float4* regions;
+  const float2* init_pos;
+  int H, nx, ny;
+  float gx0, gy0, cell, inv_cell;
+};
+
+struct KParams {
+  const unsigned char* blob;
+  int blob_bytes;
+  float* state;
+  int rec_words;
+  int n_worlds;
+  long long gid0;
+  int A, nc, R, P, nrays, nrays_pad, maxc;
+  int mode;
+  // record offsets (words)
+  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep;
+  // per-warp scratch offsets (bytes) and size
+  int s_rdist, s_rtype, s_min, s_near, s_nearcnt, s_con, s_ccount, s_order, scratch_bytes;
+  int state_dim;
+  // constants
+  float dt, inv_dt, impulse, inv_mass, agent_r, max_speed, term_r, ray_len, ray_r, wall_r;
+  float slop, bias_coef;
+  int iterations, persistence, max_steps, stale, auto_reset;
+  unsigned long long seed;
+  // I/O
+  const void* actions[CAT_MAX_AGENTS];
+  int actions_kind;
+  const uint8_t* reset_mask;
+  uint16_t* obs_dist;
+  uint8_t* obs_type;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  int8_t* winner;
+  uint16_t* shared_dist;
+  uint8_t* shared_type;
+  uint16_t* team_pos;
+  float* obs_f32;
+  float* state_f32;
+  float* hit_point;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ MapView make_view(const unsigned char* blob) {
+  const BlobHeader* h = reinterpret_cast<const BlobHeader*>(blob);
+  MapView m;
+  m.edge = reinterpret_cast<const float4*>(blob + h->off_edge);
+  m.edge_len = reinterpret_cast<const float*>(blob + h->off_len);
+  m.hull_bb = reinterpret_cast<const float4*>(blob + h->off_hbb);
+  m.hull_eo = reinterpret_cast<const uint32_t*>(blob + h->off_heo);
+  m.ray_off = reinterpret_cast<const uint16_t*>(blob + h->off_rayoff);
+  m.ray_list = reinterpret_cast<const uint16_t*>(blob + h->off_raylist);
+  m.con_off = reinterpret_cast<const uint16_t*>(blob + h->off_conoff);
+  m.con_list = reinterpret_cast<const uint16_t*>(blob + h->off_conlist);
+  m.dir = reinterpret_cast<const float2*>(blob + h->off_dir);
+  m.reg_off = reinterpret_cast<const int32_t*>(blob + h->off_regoff);
+  m.regions = reinterpret_cast<const float4*>(blob + h->off_regions);
+  m.init_pos = reinterpret_cast<const float2*>(blob + h->off_initpos);
+  m.H = h->n_hulls; m.nx = h->nx; m.ny = h->ny;
+  m.gx0 = h->gx0; m.gy0 = h->gy0; m.cell = h->cell; m.inv_cell = h->inv_cell;
+  return m;
+}
+
+// ------------------------------------------------------------------ geometry (device)
+
+// Closest feature of the raw hull to point p (CircleToPoly's GJK/EPA result for a point):
+// d = signed distance (negative inside: least-penetration edge), n = unit vector from p towards
+// the hull surface.  Same quantity cpPolyShapePointQuery reports as +-minDist.
+__device__ __forceinline__ void hull_closest(const MapView& m, int h, float px, float py, float& d, float& nx,
+                                             float& ny) {
+  const uint32_t eo = m.hull_eo[h];
+  const int o = eo & 0xFFFF, n = eo >> 16;
+  bool inside = true, binterior = false;
+  float maxpd = -CUDART_INF_F, mnx = 0.f, mny = 0.f;
+  float bestd2 = CUDART_INF_F, bqx = px, bqy = py, benx = 0.f, beny = 0.f;
+  float4 pv = m.edge[o + n - 1];
+  float v0x = pv.x, v0y = pv.y;
+  for (int i = 0; i < n; ++i) {
+    const float4 e = m.edge[o + i];
+    const float rx = px - e.x, ry = py - e.y;
+    const float pd = rx * e.z + ry * e.w;
+    if (pd > 0.f) inside = false;
+    if (pd > maxpd) { maxpd = pd; mnx = e.z; mny = e.w; }
+    const float edx = e.x - v0x, edy = e.y - v0y;
+    float t = ((px - v0x) * edx + (py - v0y) * edy) / (edx * edx + edy * edy);
+    const bool interior = (t > 0.f) && (t < 1.f);
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    const float qx = v0x + edx * t, qy = v0y + edy * t;
+    const float ddx = px - qx, ddy = py - qy;
+    const float d2 = ddx * ddx + ddy * ddy;
+    if (d2 < bestd2) { bestd2 = d2; bqx = qx; bqy = qy; benx = e.z; beny = e.w; binterior = interior; }
+    v0x = e.x; v0y = e.y;
+  }
+  if (inside) { d = maxpd; nx = -mnx; ny = -mny; return; }
+  d = sqrtf(bestd2);
+  if (binterior) { nx = -benx; ny = -beny; }
+  else { const float inv = 1.f / (d + 1.17549435e-38f); nx = (bqx - px) * inv; ny = (bqy - py) * inv; }
+}
+
+// cpBBSegmentQuery(bb, a, b) < 1: the BB-tree visits a leaf only if the THIN segment enters its bb.
+__device__ __forceinline__ bool thin_bb_hit(const float4 bb, float ox, float oy, float dx, float dy) {
+  float tmin = -CUDART_INF_F, tmax = CUDART_INF_F;
+  if (dx == 0.f) {
+    if (ox < bb.x || bb.z < ox) return false;
+  } else {
+    const float inv = 1.f / dx;
+    const float t1 = (bb.x - ox) * inv, t2 = (bb.z - ox) * inv;
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  }
+  if (dy == 0.f) {
+    if (oy < bb.y || bb.w < oy) return false;
+  } else {
+    const float inv = 1.f / dy;
+    const float t1 = (bb.y - oy) * inv, t2 = (bb.w - oy) * inv;
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  }
+  return (tmin <= tmax) && (0.f <= tmax) && (tmin < 1.f);
+}
+
+struct Hit {
+  float s;        // distance along the ray of the fat-ray centre at first touch (alpha * L)
+  float nx, ny;   // surface normal at the hit (hit point = centre - n * ray_radius)
+  int id;         // -1 none, < H hull, H + j agent j
+};
+
+// cpPolyShapeSegmentQuery for hull h against the ray o + s*u, s in [0, L): planes offset by
+// rsum = wall_r + ray_r, then the bevelled vertexes as circles of radius rsum.
+// The alpha = 0 "start inside" rule of cpShapeSegmentQuery is handled by the caller.
+__device__ __forceinline__ void ray_hull(const MapView& m, int h, float ox, float oy, float ux, float uy, float L,
+                                         float rsum, Hit& best) {
+  const float4 bb = m.hull_bb[h];
+  if (!thin_bb_hit(bb, ox, oy, ux * L, uy * L)) return;
+  const uint32_t eo = m.hull_eo[h];
+  const int o = eo & 0xFFFF, n = eo >> 16;
+  const float rs2 = rsum * rsum, inv_rs = 1.f / rsum;
+  for (int i = 0; i < n; ++i) {
+    const float4 e = m.edge[o + i];
+    const float len = m.edge_len[o + i];
+    const float rx = ox - e.x, ry = oy - e.y;
+    // plane i: d = a.n - v0.n - rsum ; t = d / (a.n - b.n)
+    const float d = rx * e.z + ry * e.w - rsum;
+    const float un = ux * e.z + uy * e.w;
+    if (d >= 0.f && un < 0.f) {
+      const float s = d / (-un);
+      if (s < L && s <= best.s) {
+        const float c = e.z * (ry + s * uy) - e.w * (rx + s * ux);  // cross(n, P - v_i) in [-len, 0]
+        if (c >= -len && c <= 0.f) { best.s = s; best.nx = e.z; best.ny = e.w; best.id = h; }
+      }
+    }
+    // bevel circle at v_i (CircleSegmentQuery), perpendicular-offset form of the discriminant
+    const float b = rx * ux + ry * uy;
+    const float cp = rx * uy - ry * ux;
+    const float disc = rs2 - cp * cp;
+    if (disc >= 0.f) {
+      const float s = -b - sqrtf(disc);
+      if (s >= 0.f && s < L && s <= best.s) {
+        best.s = s; best.nx = (rx + s * ux) * inv_rs; best.ny = (ry + s * uy) * inv_rs; best.id = h;
+      }
+    }
+  }
+}
+
+// CircleSegmentQuery against an agent circle (cached centre c, radius r1) with ray radius r2.
+__device__ __forceinline__ void ray_circle(float cx, float cy, float rs, float ox, float oy, float ux, float uy,
+                                           float L, int id, Hit& best) {
+  const float rx = ox - cx, ry = oy - cy;
+  const float b = rx * ux + ry * uy;
+  const float cp = rx * uy - ry * ux;
+  const float disc = rs * rs - cp * cp;
+  if (disc >= 0.f) {
+    const float s = -b - sqrtf(disc);
+    if (s >= 0.f && s < L && s < best.s) {
+      const float inv = 1.f / rs;
+      best.s = s; best.nx = (rx + s * ux) * inv; best.ny = (ry + s * uy) * inv; best.id = id;
+    }
+  }
+}
+
+// Thin segment a -> b against hull h with query radius 0 (capture line of sight,
+// base_env.py:536-544): true if the hull blocks (alpha < 1), including the alpha = 0 rule.
+__device__ __forceinline__ bool los_hull_blocks(const MapView& m, int h, float ax, float ay, float bx, float by,
+                                                float wall_r) {
+  const float4 bb = m.hull_bb[h];
+  const float dx = bx - ax, dy = by - ay;
+  if (!thin_bb_hit(bb, ax, ay, dx, dy)) return false;
+  float d, nx, ny;
+  hull_closest(m, h, ax, ay, d, nx, ny);
+  if (d - wall_r <= 0.f) return true;  // start point inside the rounded hull
+  const float L = sqrtf(dx * dx + dy * dy);
+  if (!(L > 0.f)) return false;
+  Hit best; best.s = L; best.id = -1; best.nx = best.ny = 0.f;
+  const float inv = 1.f / L;
+  ray_hull(m, h, ax, ay, dx * inv, dy * inv, L, wall_r, best);
+  return best.id >= 0;
+}
+
+__device__ __forceinline__ int grid_cell(const MapView& m, float x, float y) {
+  const float gx = (x - m.gx0) * m.inv_cell, gy = (y - m.gy0) * m.inv_cell;
+  if (!(gx >= 0.f && gy >= 0.f && gx < (float)m.nx && gy < (float)m.ny)) return -1;
+  return (int)gy * m.nx + (int)gx;
+}
+
+// ------------------------------------------------------------------ per-warp world context
+struct Warp {
+  float* rec;
+  uint16_t* rdist;
+  uint8_t* rtype;
+  uint32_t* minbits;
+  uint16_t* near;
+  uint32_t* nearcnt;
+  float* con;       // contact entries, 8 words each
+  uint32_t* ccount; // wall contacts per agent
+  uint8_t* order;   // compact solver order
+  int lane;
+};
+
+// Sensor sweep of every agent of one world (entity.py:159-220) into shared memory.
+__device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
+  const int A = k.A, R = k.R, lane = w.lane;
+  const float* pos = w.rec;
+  const float* tc = w.rec + k.o_tc;
+  const float L = k.ray_len, rsum = k.wall_r + k.ray_r;
+  // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates
+  if (lane < A) {
+    const float px = pos[2 * lane], py = pos[2 * lane + 1];
+    uint32_t cnt = 0;
+    const int cell = grid_cell(m, px, py);
+    if (cell >= 0) {
+      for (int q = m.ray_off[cell]; q < m.ray_off[cell + 1]; ++q) {
+        const int h = m.ray_list[q];
+        float d, nx, ny;
+        hull_closest(m, h, px, py, d, nx, ny);
+        if (d - k.wall_r <= k.ray_r && cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
+      }
+    }
+    w.nearcnt[lane] = cnt;
+    w.minbits[lane] = kEmpty;
+  }
+  __syncwarp();
+
+  for (int r0 = 0; r0 < k.nrays_pad; r0 += 32) {
+    const int r = r0 + lane;
+    if (r < k.nrays) {
+      const int a = r / R, i = r - a * R;
+      const float ox = pos[2 * a], oy = pos[2 * a + 1];
+      const float2 u = m.dir[i];
+      Hit best; best.s = L; best.id = -1; best.nx = 0.f; best.ny = 0.f;
+      bool zero_hit = false;   // alpha = 0: point stays at the ray end (cpShapeSegmentQuery)
+      // dynamic shapes: the other agents' cached centres
+      for (int j = 0; j < A; ++j) {
+        if (j == a) continue;
+        const float cx = tc[2 * j], cy = tc[2 * j + 1];
+        const float ddx = ox - cx, ddy = oy - cy;
+        if (sqrtf(ddx * ddx + ddy * ddy) - k.agent_r <= k.ray_r) {
+          if (!zero_hit) { zero_hit = true; best.s = 0.f; best.id = m.H + j; }
+        } else if (!zero_hit) {
+          ray_circle(cx, cy, k.agent_r + k.ray_r, ox, oy, u.x, u.y, L, m.H + j, best);
+        }
+      }
+      // static shapes with the origin inside their reach: visited only if the thin ray enters the bb
+      const uint32_t ncnt = w.nearcnt[a];
+      bool wall_zero = false;
+      for (uint32_t q = 0; q < ncnt; ++q) {
+        const int h = w.near[a * kNear + q];
+        if (!wall_zero && thin_bb_hit(m.hull_bb[h], ox, oy, u.x * L, u.y * L)) {
+          wall_zero = true; zero_hit = true; best.s = 0.f; best.id = h;  // static index is queried first
+        }
+      }
+      if (!zero_hit) {
+        // walk the uniform grid along the ray; stop once the next cell starts beyond the best hit
+        const float gx = (ox - m.gx0) * m.inv_cell, gy = (oy - m.gy0) * m.inv_cell;
+        const float dgx = u.x * m.inv_cell, dgy = u.y * m.inv_cell;  // grid units per unit distance
+        float t0 = 0.f, t1 = best.s;
+        bool ok = true;
+        if (dgx != 0.f) {
+          const float ta = (0.f - gx) / dgx, tb = ((float)m.nx - gx) / dgx;
+          t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+        } else if (gx < 0.f || gx >= (float)m.nx) ok = false;
+        if (dgy != 0.f) {
+          const float ta = (0.f - gy) / dgy, tb = ((float)m.ny - gy) / dgy;
+          t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+        } else if (gy < 0.f || gy >= (float)m.ny) ok = false;
+        if (ok && t0 <= t1) {
+          const float sx = gx + dgx * t0, sy = gy + dgy * t0;
+          int ix = min(max((int)floorf(sx), 0), m.nx - 1);
+          int iy = min(max((int)floorf(sy), 0), m.ny - 1);
+          const int stepx = dgx > 0.f ? 1 : -1, stepy = dgy > 0.f ? 1 : -1;
+          const float tdx = dgx != 0.f ? fabsf(1.f / dgx) : CUDART_INF_F;
+          const float tdy = dgy != 0.f ? fabsf(1.f / dgy) : CUDART_INF_F;
+          float tmx = dgx != 0.f ? ((float)(ix + (stepx > 0 ? 1 : 0)) - gx) / dgx : CUDART_INF_F;
+          float tmy = dgy != 0.f ? ((float)(iy + (stepy > 0 ? 1 : 0)) - gy) / dgy : CUDART_INF_F;
+          int last1 = -1, last2 = -1;
+          for (int guard = 0; guard < 4096; ++guard) {
+            const int cell = iy * m.nx + ix;
+            const int qb = m.ray_off[cell], qe = m.ray_off[cell + 1];
+            for (int q = qb; q < qe; ++q) {
+              const int h = m.ray_list[q];
+              if (h == last1 || h == last2) continue;
+              last2 = last1; last1 = h;
+              ray_hull(m, h, ox, oy, u.x, u.y, L, rsum, best);
+            }
+            const float tn = fminf(tmx, tmy);
+            if (!(tn < best.s)) break;
+            if (tmx < tmy) { ix += stepx; tmx += tdx; } else { iy += stepy; tmy += tdy; }
+            if (ix < 0 || iy < 0 || ix >= m.nx || iy >= m.ny) break;
+          }
+        }
+      }
+      // entity.py:200-215 — float16 chain, reproduced at each of its rounding points
+      uint16_t dbits;
+      uint8_t type;
+      float hx, hy;
+      if (best.id < 0) {
+        dbits = __half_as_ushort(__float2half_rn(L));
+        type = TYPE_EMPTY;
+        hx = ox + L * u.x; hy = oy + L * u.y;
+      } else {
+        if (zero_hit) { hx = ox + L * u.x; hy = oy + L * u.y; }
+        else { hx = ox + best.s * u.x - best.nx * k.ray_r; hy = oy + best.s * u.y - best.ny * k.ray_r; }
+        const float pxh = __half2float(__float2half_rn(hx)), pyh = __half2float(__float2half_rn(hy));
+        const float oxh = __half2float(__float2half_rn(ox)), oyh = __half2float(__float2half_rn(oy));
+        const float dxh = __half2float(__float2half_rn(pxh - oxh));
+        const float dyh = __half2float(__float2half_rn(pyh - oyh));
+        const float hyp = (float)sqrt((double)dxh * (double)dxh + (double)dyh * (double)dyh);
+        dbits = __half_as_ushort(__float2half_rn(hyp));
+        type = best.id < m.H ? TYPE_WALL : ((best.id - m.H) >= k.nc ? TYPE_THIEF : TYPE_COP);
+        // rewards need the nearest opponent seen by this agent (cop.py:66-70, thief.py:60-63)
+        const int want = (a < k.nc) ? TYPE_THIEF : TYPE_COP;
+        if (type == want) atomicMin(&w.minbits[a], (uint32_t)dbits);
+      }
+      w.rdist[r] = dbits;
+      w.rtype[r] = type;
+      if (k.hit_point) {
+        float2* hp = reinterpret_cast<float2*>(k.hit_point) + (size_t)world * k.nrays + r;
+        *hp = make_float2(hx, hy);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Write the observation-side outputs of one world from shared memory (coalesced).
+__device__ __forceinline__ void write_observation(const KParams& k, const Warp& w, long long world) {
+  const int A = k.A, R = k.R, lane = w.lane, nrays = k.nrays;
+  const float* pos = w.rec;
+  if (k.obs_dist) {
+    if ((nrays & 1) == 0) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(k.obs_dist + (size_t)world * nrays);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(w.rdist);
+      for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
+    } else {
+      for (int i = lane; i < nrays; i += 32) k.obs_dist[(size_t)world * nrays + i] = w.rdist[i];
+    }
+  }
+  if (k.obs_type) {
+    if ((nrays & 1) == 0) {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(k.obs_type + (size_t)world * nrays);
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(w.rtype);
+      for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
+    } else {
+      for (int i = lane; i < nrays; i += 32) k.obs_type[(size_t)world * nrays + i] = w.rtype[i];
+    }
+  }
+  if (k.team_pos) {  // observation_spaces.py:92-95
+    for (int i = lane; i < 2 * A; i += 32)
+      k.team_pos[(size_t)world * 2 * A + i] = __half_as_ushort(__float2half_rn(pos[i]));
+  }
+  // observation_spaces.py:97-121 net effect: first non-EMPTY (type, distance) in team order
+  if (k.shared_dist || k.shared_type) {
+    for (int q = lane; q < 2 * R; q += 32) {
+      const int team = q / R, i = q - team * R;
+      const int a0 = team == 0 ? 0 : k.nc, a1 = team == 0 ? k.nc : A;
+      uint8_t t = TYPE_EMPTY;
+      uint16_t d = 0;
+      for (int a = a0; a < a1; ++a)
+        if (t == TYPE_EMPTY) { t = w.rtype[a * R + i]; d = w.rdist[a * R + i]; }
+      if (k.shared_dist) k.shared_dist[(size_t)world * 2 * R + q] = d;
+      if (k.shared_type) k.shared_type[(size_t)world * 2 * R + q] = t;
+    }
+  }
+  if (k.obs_f32) {  // [A][N][2R]: [distance | object_type] as skrl flattens the Dict (keys sorted)
+    for (int a = 0; a < A; ++a) {
+      float* dst = k.obs_f32 + ((size_t)a * k.n_worlds + world) * (2 * R);
+      for (int i = lane; i < 2 * R; i += 32)
+        dst[i] = i < R ? __half2float(__ushort_as_half(w.rdist[a * R + i])) : (float)w.rtype[a * R + i - R];
+    }
+  }
+  if (k.state_f32) {
+    // env.state(): per agent [distance_shared | object_type_shared | own_distances | own_obj_types | team_positions]
+    float* dst = k.state_f32 + (size_t)world * k.state_dim;
+    int base = 0;
+    for (int a = 0; a < A; ++a) {
+      const int team = a < k.nc ? 0 : 1;
+      const int a0 = team == 0 ? 0 : k.nc, a1 = team == 0 ? k.nc : A;
+      const int blk = 4 * R + 2 * (a1 - a0);
+      for (int i = lane; i < blk; i += 32) {
+        float v;
+        if (i < 2 * R) {
+          const int ri = i < R ? i : i - R;
+          uint8_t t = TYPE_EMPTY;
+          uint16_t d = 0;
+          for (int b = a0; b < a1; ++b)
+            if (t == TYPE_EMPTY) { t = w.rtype[b * R + ri]; d = w.rdist[b * R + ri]; }
+          v = i < R ? __half2float(__ushort_as_half(d)) : (float)t;
+        } else if (i < 3 * R) v = __half2float(__ushort_as_half(w.rdist[a * R + i - 2 * R]));
+        else if (i < 4 * R) v = (float)w.rtype[a * R + i - 3 * R];
+        else v = __half2float(__float2half_rn(pos[2 * a0 + (i - 4 * R)]));
+        dst[base + i] = v;
+      }
+      base += blk;
+    }
+  }
+}
+
+// cop.py:49-75 / thief.py:48-69 in fp32 from the f16 distance.
+__device__ __forceinline__ float agent_reward(const KParams& k, int a, uint32_t minbits, bool captured, bool timeout) {
+  const bool is_cop = a < k.nc;
+  if (captured) return is_cop ? 1.f : -1.f;
+  if (timeout) return is_cop ? -1.f : 1.f;
+  const bool seen = minbits != kEmpty;
+  const float d = seen ? __half2float(__ushort_as_half((uint16_t)minbits)) : 0.f;
+  if (is_cop) return seen ? (-0.02f + 1.5f * expf(-d / 50.f)) : -0.04f;
+  return seen ? tanhf((d - 100.f) / 50.f) / 10.f : 0.15f;
+}
+
+// cpSpaceStep(dt) for one world, state in shared memory.
+__device__ __forceinline__ void physics_world(const KParams& k, const MapView& m, const Warp& w) {
+  const int A = k.A, P = k.P, lane = w.lane;
+  float* pos = w.rec;
+  float* vel = w.rec + k.o_vel;
+  float* vb = w.rec + k.o_vb;
+  float* tc = w.rec + k.o_tc;
+  uint32_t* wkey = reinterpret_cast<uint32_t*>(w.rec + k.o_wkey);
+  float* wjn = w.rec + k.o_wjn;
+  uint32_t* page = reinterpret_cast<uint32_t*>(w.rec + k.o_page);
+  float* pjn = w.rec + k.o_pjn;
+  const float rsum_w = k.agent_r + k.wall_r;
+
+  // (1) cpBodyUpdatePosition, (2) shape caches
+  if (lane < 2 * A) {
+    const float p = pos[lane] + (vel[lane] + vb[lane]) * k.dt;
+    pos[lane] = p; tc[lane] = p; vb[lane] = 0.f;
+  }
+  __syncwarp();
+
+  // (3) narrow phase.  Entry: {nx, ny, bias, jn, jBias, nMass, meta, slot}
+  if (lane < A) {
+    const float px = pos[2 * lane], py = pos[2 * lane + 1];
+    uint32_t cnt = 0, used = 0;
+    const int cell = grid_cell(m, px, py);
+    if (cell >= 0) {
+      for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && cnt < (uint32_t)kSlots; ++q) {
+        const int h = m.con_list[q];
+        float d, nx, ny;
+        hull_closest(m, h, px, py, d, nx, ny);
+        if (d <= rsum_w) {  // CircleToPoly: d <= r_circle + r_poly
+          // cpArbiterUpdate: reuse the cached arbiter of this (agent, hull) pair if any
+          int slot = -1;
+          for (int s = 0; s < kSlots; ++s)
+            if (wkey[lane * kSlots + s] != kEmpty && (wkey[lane * kSlots + s] & 0xFFFF) == (uint32_t)h) slot = s;
+          float jn0 = 0.f;
+          bool first = true;
+          if (slot >= 0) {
+            jn0 = wjn[lane * kSlots + slot];
+            first = (wkey[lane * kSlots + slot] >> 16) != 0;  // used in the previous step -> not first
+          } else {
+            // free slot, else the oldest slot not used this step
+            uint32_t oldest = 0;
+            for (int s = 0; s < kSlots; ++s) {
+              if (used & (1u << s)) continue;
+              const uint32_t key = wkey[lane * kSlots + s];
+              const uint32_t age = key == kEmpty ? 0x10000u : (key >> 16) + 1u;
+              if (age > oldest) { oldest = age; slot = s; }
+            }
+          }
+          if (slot >= 0) {
+            used |= 1u << slot;
+            wkey[lane * kSlots + slot] = (uint32_t)h;  // age 0 = used this step
+            float* c = w.con + (lane * kSlots + cnt) * 8;
+            c[0] = nx; c[1] = ny;
+            c[2] = -k.bias_coef * fminf(0.f, (d - rsum_w) + k.slop) * k.inv_dt;  // cpArbiterPreStep
+            c[3] = jn0; c[4] = 0.f; c[5] = 1.f / k.inv_mass;
+            reinterpret_cast<uint32_t*>(c)[6] = (uint32_t)lane | (0xFFu << 8) | (first ? 1u << 16 : 0u);
+            reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)(lane * kSlots + slot);
+            ++cnt;
+          }
+        }
+      }
+    }
+    // cpSpaceArbiterSetFilter: arbiters not used this step age; dropped at collision_persistence
+    for (int s = 0; s < kSlots; ++s) {
+      if (used & (1u << s)) continue;
+      const uint32_t key = wkey[lane * kSlots + s];
+      if (key == kEmpty) continue;
+      const uint32_t age = (key >> 16) + 1u;
+      if ((int)age >= k.persistence) { wkey[lane * kSlots + s] = kEmpty; wjn[lane * kSlots + s] = 0.f; }
+      else wkey[lane * kSlots + s] = (key & 0xFFFF) | (age << 16);
+    }
+    w.ccount[lane] = cnt;
+  }
+  uint32_t pair_hit = 0;
+  if (lane < P) {
+    // pair index -> (i, j), i-major
+    int i = 0, rem = lane;
+    while (rem >= A - 1 - i) { rem -= A - 1 - i; ++i; }
+    const int j = i + 1 + rem;
+    const float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1];
+    const float mind = 2.f * k.agent_r, dsq = dx * dx + dy * dy;
+    const uint32_t age = page[lane];
+    if (dsq < mind * mind) {  // CircleToCircle (strict)
+      const float dist = sqrtf(dsq);
+      float* c = w.con + (A * kSlots + lane) * 8;
+      c[0] = dist > 0.f ? dx / dist : 1.f;
+      c[1] = dist > 0.f ? dy / dist : 0.f;
+      c[2] = -k.bias_coef * fminf(0.f, (dist - mind) + k.slop) * k.inv_dt;
+      c[3] = age != kEmpty ? pjn[lane] : 0.f;
+      c[4] = 0.f; c[5] = 1.f / (2.f * k.inv_mass);
+      reinterpret_cast<uint32_t*>(c)[6] = (uint32_t)i | ((uint32_t)j << 8) | (age != 0 ? 1u << 16 : 0u);
+      reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)lane;
+      page[lane] = 0;
+      pair_hit = 1;
+    } else if (age != kEmpty) {
+      const uint32_t na = age + 1u;
+      if ((int)na >= k.persistence) { page[lane] = kEmpty; pjn[lane] = 0.f; } else page[lane] = na;
+    }
+  }
+  const uint32_t pair_mask = __ballot_sync(0xFFFFFFFFu, pair_hit != 0);
+  __syncwarp();
+
+  // (7) warm start + (8) sequential impulses: serial by construction, lane 0
+  if (lane == 0) {
+    int n = 0;
+    for (int a = 0; a < A; ++a)
+      for (uint32_t q = 0; q < w.ccount[a]; ++q) w.order[n++] = (uint8_t)(a * kSlots + q);
+    for (int p = 0; p < P; ++p)
+      if (pair_mask & (1u << p)) w.order[n++] = (uint8_t)(A * kSlots + p);
+    if (n > 0) {
+      const float minv = k.inv_mass;
+      for (int q = 0; q < n; ++q) {  // cpArbiterApplyCachedImpulse (dt_coef = 1)
+        float* c = w.con + w.order[q] * 8;
+        const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
+        if (meta & (1u << 16)) continue;  // first contact: nothing applied
+        const int a = meta & 0xFF, b = (meta >> 8) & 0xFF;
+        const float jx = c[0] * c[3] * minv, jy = c[1] * c[3] * minv;
+        vel[2 * a] -= jx; vel[2 * a + 1] -= jy;
+        if (b != 0xFF) { vel[2 * b] += jx; vel[2 * b + 1] += jy; }
+      }
+      for (int it = 0; it < k.iterations; ++it) {
+        for (int q = 0; q < n; ++q) {  // cpArbiterApplyImpulse, e = 0, u = 0
+          float* c = w.con + w.order[q] * 8;
+          const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
+          const int a = meta & 0xFF, b = (meta >> 8) & 0xFF;
+          const float nx = c[0], ny = c[1], nMass = c[5];
+          float vbx = -vb[2 * a], vby = -vb[2 * a + 1], vrx = -vel[2 * a], vry = -vel[2 * a + 1];
+          if (b != 0xFF) { vbx += vb[2 * b]; vby += vb[2 * b + 1]; vrx += vel[2 * b]; vry += vel[2 * b + 1]; }
+          const float vbn = vbx * nx + vby * ny;
+          const float vrn = vrx * nx + vry * ny;
+          const float jbnOld = c[4];
+          const float jBias = fmaxf(jbnOld + (c[2] - vbn) * nMass, 0.f);
+          const float jnOld = c[3];
+          const float jnAcc = fmaxf(jnOld - vrn * nMass, 0.f);
+          c[4] = jBias; c[3] = jnAcc;
+          const float jb = (jBias - jbnOld) * minv, j = (jnAcc - jnOld) * minv;
+          vb[2 * a] -= nx * jb; vb[2 * a + 1] -= ny * jb;
+          vel[2 * a] -= nx * j; vel[2 * a + 1] -= ny * j;
+          if (b != 0xFF) {
+            vb[2 * b] += nx * jb; vb[2 * b + 1] += ny * jb;
+            vel[2 * b] += nx * j; vel[2 * b + 1] += ny * j;
+          }
+        }
+      }
+      for (int q = 0; q < n; ++q) {  // persist jnAcc in the arbiter cache
+        const float* c = w.con + w.order[q] * 8;
+        const uint32_t meta = reinterpret_cast<const uint32_t*>(c)[6];
+        const uint32_t slot = reinterpret_cast<const uint32_t*>(c)[7];
+        if (((meta >> 8) & 0xFF) == 0xFF) wjn[slot] = c[3]; else pjn[slot] = c[3];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// BaseEnv.reset for one world (base_env.py:313-350, _get_non_colliding_position :123-166).
+__device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
+  const int A = k.A, lane = w.lane;
+  float* pos = w.rec;
+  float* vel = w.rec + k.o_vel;
+  float* tc = w.rec + k.o_tc;
+  uint32_t* ep = reinterpret_cast<uint32_t*>(w.rec + k.o_ep);
+  const uint32_t episode = *ep + 1u;
+  float nx_ = 0.f, ny_ = 0.f;
+  if (lane < A) {
+    const int r0 = m.reg_off[lane], nr = m.reg_off[lane + 1] - r0;
+    if (nr > 0) {
+      const unsigned long long gid = (unsigned long long)(k.gid0 + world);
+      const uint32_t idx = cat_spawn_region_index(k.seed, gid, episode, (uint32_t)lane, (uint32_t)nr);
+      const float4 reg = m.regions[r0 + (int)idx];
+      nx_ = reg.x + reg.z / 2.f; ny_ = reg.y + reg.w / 2.f;  // base_env.py:163-166 fallback
+      for (uint32_t t = 0; t < 20; ++t) {
+        float ux, uy;
+        cat_spawn_uniforms(k.seed, gid, episode, (uint32_t)lane, t, &ux, &uy);
+        const float px = fmaf(reg.z, ux, reg.x), py = fmaf(reg.w, uy, reg.y);
+        // point_query_nearest(pos, 5, ray_filter): any shape with distance < 5
+        bool blocked = false;
+        const int cell = grid_cell(m, px, py);
+        if (cell >= 0) {
+          for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && !blocked; ++q) {
+            float d, ax, ay;
+            hull_closest(m, m.con_list[q], px, py, d, ax, ay);
+            if (d - k.wall_r < k.agent_r) blocked = true;
+          }
+        }
+        for (int j = 0; j < A && !blocked; ++j) {
+          if (j == lane) continue;
+          const float dx = px - tc[2 * j], dy = py - tc[2 * j + 1];
+          if (sqrtf(dx * dx + dy * dy) - k.agent_r < k.agent_r) blocked = true;
+        }
+        if (!blocked) { nx_ = px; ny_ = py; break; }
+      }
+    } else {
+      const float2 ip = m.init_pos[lane];  // base_env.py:328-332 -> Entity.reset() default
+      nx_ = ip.x; ny_ = ip.y;
+    }
+  }
+  __syncwarp();  // every lane has finished reading the stale centres
+  if (lane < A) {
+    pos[2 * lane] = nx_; pos[2 * lane + 1] = ny_;       // entity.py:154-156
+    vel[2 * lane] = 0.f; vel[2 * lane + 1] = 0.f;        // entity.py:157
+    if (!k.stale) { tc[2 * lane] = nx_; tc[2 * lane + 1] = ny_; }
+  }
+  if (lane == 0) {
+    *ep = episode;
+    reinterpret_cast<int32_t*>(w.rec)[k.o_sc] = 0;  // base_env.py:350
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads) cat_world_kernel(const __grid_constant__ KParams k) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // Stage the map once per CTA: one elected thread issues a TMA bulk copy (cp.async.bulk ->
+  // UBLKCP) that completes on an mbarrier; everyone else waits on the barrier's phase.
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(k.blob_bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+        "l"(k.blob), "r"(k.blob_bytes), "r"(smem_u32(&mbar))
+        : "memory");
+  }
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(&mbar)), "r"(0)
+          : "memory");
+    }
+  }
+  const MapView m = make_view(smem);
+
+  unsigned char* scratch = smem + ((k.blob_bytes + 127) & ~127) + (size_t)warp * k.scratch_bytes;
+  Warp w;
+  w.rec = reinterpret_cast<float*>(scratch);
+  w.rdist = reinterpret_cast<uint16_t*>(scratch + k.s_rdist);
+  w.rtype = reinterpret_cast<uint8_t*>(scratch + k.s_rtype);
+  w.minbits = reinterpret_cast<uint32_t*>(scratch + k.s_min);
+  w.near = reinterpret_cast<uint16_t*>(scratch + k.s_near);
+  w.nearcnt = reinterpret_cast<uint32_t*>(scratch + k.s_nearcnt);
+  w.con = reinterpret_cast<float*>(scratch + k.s_con);
+  w.ccount = reinterpret_cast<uint32_t*>(scratch + k.s_ccount);
+  w.order = reinterpret_cast<uint8_t*>(scratch + k.s_order);
+  w.lane = lane;
+
+  const int A = k.A;
+  const long long stride = (long long)gridDim.x * kWarpsPerCta;
+  for (long long world = (long long)blockIdx.x * kWarpsPerCta + warp; world < k.n_worlds; world += stride) {
+    float* grec = k.state + (size_t)world * k.rec_words;
+    int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
+
+    if (k.mode == MODE_INIT) {  // fresh environment (entity.py:115,124): agents at map positions
+      for (int i = lane; i < k.rec_words; i += 32) {
+        float v = 0.f;
+        if (i < 2 * A) v = (i & 1) ? m.init_pos[i >> 1].y : m.init_pos[i >> 1].x;
+        else if (i >= k.o_tc && i < k.o_tc + 2 * A) { const int q = i - k.o_tc; v = (q & 1) ? m.init_pos[q >> 1].y : m.init_pos[q >> 1].x; }
+        else if ((i >= k.o_wkey && i < k.o_wkey + A * kSlots) || (i >= k.o_page && i < k.o_page + k.P)) v = __uint_as_float(kEmpty);
+        grec[i] = v;
+      }
+      continue;
+    }
+    if (k.mode == MODE_RESET && k.reset_mask && !k.reset_mask[world]) continue;
+
+    for (int i = lane; i < k.rec_words; i += 32) w.rec[i] = grec[i];
+    __syncwarp();
+
+    if (k.mode == MODE_OBSERVE) {
+      observe_world(k, m, w, world);
+      write_observation(k, w, world);
+      __syncwarp();
+      continue;
+    }
+    if (k.mode == MODE_RESET) {
+      reset_world(k, m, w, world);
+      observe_world(k, m, w, world);
+      write_observation(k, w, world);
+      __syncwarp();
+      for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
+      __syncwarp();
+      continue;
+    }
+
+    // ---------------- MODE_STEP: base_env.py:354-413 ----------------
+    const float* pos = w.rec;
+    float* vel = w.rec + k.o_vel;
+    const int step_count = reci[k.o_sc] + 1;  // :372
+    __syncwarp();
+    if (lane == 0) reci[k.o_sc] = step_count;
+
+    // _termination_criterion (:521-554): thief-major; LOS blocked by walls only; dist < radius (strict)
+    bool captured = false;
+    for (int t = k.nc; t < A && !captured; ++t)
+      for (int c = 0; c < k.nc && !captured; ++c) {
+        const float tx = pos[2 * t], ty = pos[2 * t + 1], cx = pos[2 * c], cy = pos[2 * c + 1];
+        const float dx = tx - cx, dy = ty - cy;
+        if (sqrtf(dx * dx + dy * dy) < k.term_r) {
+          bool blocked = false;
+          for (int h = lane; h < m.H; h += 32) blocked = blocked || los_hull_blocks(m, h, tx, ty, cx, cy, k.wall_r);
+          if (!__any_sync(0xFFFFFFFFu, blocked)) captured = true;
+        }
+      }
+    const bool timeout = !captured && step_count >= k.max_steps;
+
+    // Entity._perform_action (entity.py:126-134)
+    if (lane < A) {
+      int act;
+      const size_t ai = (size_t)world * A + lane;
+      if (k.actions_kind == 0) act = reinterpret_cast<const uint8_t*>(k.actions[0])[ai];
+      else if (k.actions_kind == 1) act = reinterpret_cast<const int32_t*>(k.actions[0])[ai];
+      else if (k.actions_kind == 2) act = (int)reinterpret_cast<const long long*>(k.actions[0])[ai];
+      else act = (int)reinterpret_cast<const long long*>(k.actions[lane])[world];
+      float fx = 0.f, fy = 0.f;
+      if (act == 0) fx = -k.impulse; else if (act == 1) fy = k.impulse;
+      else if (act == 2) fx = k.impulse; else if (act == 3) fy = -k.impulse;
+      float vx = vel[2 * lane] + fx * k.inv_mass, vy = vel[2 * lane + 1] + fy * k.inv_mass;
+      const float sp = sqrtf(vx * vx + vy * vy);
+      if (sp > k.max_speed) { vx = vx / sp * k.max_speed; vy = vy / sp * k.max_speed; }
+      vel[2 * lane] = vx; vel[2 * lane + 1] = vy;
+    }
+    __syncwarp();
+
+    observe_world(k, m, w, world);  // entity.py:143, pre-physics state
+    if (lane < A && k.reward)
+      k.reward[(size_t)world * A + lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
+    const bool done = captured || timeout;
+    const bool will_reset = done && k.auto_reset;
+    if (!will_reset) write_observation(k, w, world);
+    if (lane == 0) {
+      if (k.terminated) k.terminated[world] = done ? 1 : 0;  // entity.py:146
+      if (k.truncated) k.truncated[world] = timeout ? 1 : 0;   // base_env.py:397
+      if (k.winner) k.winner[world] = done ? (captured ? 0 : 1) : -1;
+    }
+    __syncwarp();
+
+    physics_world(k, m, w);  // base_env.py:392
+
+    if (will_reset) {  // emit the observation of the re-spawned state
+      reset_world(k, m, w, world);
+      observe_world(k, m, w, world);
+      write_observation(k, w, world);
+      __syncwarp();
+    }
+    for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ state pack / unpack
+struct ViewParams {
+  float* state;
+  int rec_words, n_worlds, A, P;
+  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep;
+  CatStateView v;
+  int set;
+};
+
+__global__ void cat_state_view_kernel(const ViewParams p) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= p.n_worlds) return;
+  float* rec = p.state + (size_t)w * p.rec_words;
+  uint32_t* recu = reinterpret_cast<uint32_t*>(rec);
+  const int A = p.A, P = p.P;
+  auto xfer = [&](float* ext, int off, int n) {
+    if (!ext) return;
+    for (int i = 0; i < n; ++i) { if (p.set) rec[off + i] = ext[(size_t)w * n + i]; else ext[(size_t)w * n + i] = rec[off + i]; }
+  };
+  xfer(p.v.pos, 0, 2 * A);
+  xfer(p.v.vel, p.o_vel, 2 * A);
+  xfer(p.v.vbias, p.o_vb, 2 * A);
+  xfer(p.v.tc, p.o_tc, 2 * A);
+  xfer(p.v.wall_jn, p.o_wjn, A * kSlots);
+  xfer(p.v.pair_jn, p.o_pjn, P);
+  if (p.v.step_count) { if (p.set) recu[p.o_sc] = (uint32_t)p.v.step_count[w]; else p.v.step_count[w] = (int32_t)recu[p.o_sc]; }
+  if (p.v.episode) { if (p.set) recu[p.o_ep] = p.v.episode[w]; else p.v.episode[w] = recu[p.o_ep]; }
+  if (p.v.wall_hull && p.v.wall_age) {
+    for (int i = 0; i < A * kSlots; ++i) {
+      const size_t e = (size_t)w * A * kSlots + i;
+      if (p.set) {
+        recu[p.o_wkey + i] = p.v.wall_hull[e] < 0 ? kEmpty : ((uint32_t)p.v.wall_hull[e] & 0xFFFF) | ((uint32_t)p.v.wall_age[e] << 16);
+      } else {
+        const uint32_t key = recu[p.o_wkey + i];
+        p.v.wall_hull[e] = key == kEmpty ? -1 : (int32_t)(key & 0xFFFF);
+        p.v.wall_age[e] = key == kEmpty ? -1 : (int32_t)(key >> 16);
+      }
+    }
+  }
+  if (p.v.pair_age) {
+    for (int i = 0; i < P; ++i) {
+      const size_t e = (size_t)w * P + i;
+      if (p.set) recu[p.o_page + i] = p.v.pair_age[e] < 0 ? kEmpty : (uint32_t)p.v.pair_age[e];
+      else p.v.pair_age[e] = recu[p.o_page + i] == kEmpty ? -1 : (int32_t)recu[p.o_page + i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ GAE
+// One thread per (world, agent) column scans T backwards; loads of step t-1 are independent of
+// the recurrence so the compiler keeps several in flight.  Block partials of sum / sum^2 in fp64.
+__global__ void __launch_bounds__(256) cat_gae_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
+                                                      const float* __restrict__ values,
+                                                      const float* __restrict__ last_values, float* __restrict__ returns,
+                                                      float* __restrict__ advantages, double* __restrict__ stats, int T,
+                                                      int M, float gamma, float lam) {
+  const int mcol = blockIdx.x * blockDim.x + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (mcol < M) {
+    float adv = 0.f;
+    float next_v = last_values[mcol];
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t i = (size_t)t * M + mcol;
+      const float r = rewards[i], v = values[i];
+      const float nd = dones[i] ? 0.f : 1.f;
+      adv = r - v + gamma * nd * (next_v + lam * adv);
+      advantages[i] = adv;
+      returns[i] = adv + v;
+      next_v = v;
+      s1 += (double)adv;
+      s2 += (double)adv * (double)adv;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+    s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+  }
+  __shared__ double sh1[8], sh2[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh1[warp] = s1; sh2[warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh1[i]; b += sh2[i]; }
+    atomicAdd(&stats[0], a);
+    atomicAdd(&stats[1], b);
+  }
+}
+
+__global__ void __launch_bounds__(256) cat_adv_normalize_kernel(float* __restrict__ adv, long long n,
+                                                                const double* __restrict__ stats, long long count) {
+  const double mean = stats[0] / (double)count;
+  double var = count > 1 ? (stats[1] - (double)count * mean * mean) / (double)(count - 1) : 0.0;
+  if (var < 0.0) var = 0.0;
+  const float fm = (float)mean, inv = (float)(1.0 / (sqrt(var) + 1e-8));
+  const long long n4 = n >> 2;
+  float4* a4 = reinterpret_cast<float4*>(adv);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = a4[i];
+    v.x = (v.x - fm) * inv; v.y = (v.y - fm) * inv; v.z = (v.z - fm) * inv; v.w = (v.w - fm) * inv;
+    a4[i] = v;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adv[i] = (adv[i] - fm) * inv;
+}
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side / C ABI
+struct CatEnv {
+  int device = 0;
+  int n_worlds = 0;
+  unsigned char* blob_dev = nullptr;
+  KParams kp{};
+  CatEnvInfo info{};
+  int smem_bytes = 0;
+  int grid = 0;
+};
+
+extern "C" {
+
+int cat_abi_version(void) { return CAT_ABI_VERSION; }
+const char* cat_last_error(void) { return g_last_error.c_str(); }
+
+int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds, int64_t gid0, int32_t device,
+                   CatEnv** out) {
+  if (!map || !pr || !out) return fail(CAT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const int A = map->n_cops + map->n_thieves, R = pr->n_rays, H = map->n_hulls, E = map->n_edges;
+  if (n_worlds < 1) return fail(CAT_ERR_INVALID, "n_worlds must be >= 1");
+  if (map->n_cops < 1 || map->n_thieves < 1) return fail(CAT_ERR_INVALID, "need at least one cop and one thief");
+  if (A > CAT_MAX_AGENTS) return fail(CAT_ERR_LIMIT, "too many agents (CAT_MAX_AGENTS)");
+  if (R < 1 || R > CAT_MAX_RAYS) return fail(CAT_ERR_LIMIT, "n_rays out of range (CAT_MAX_RAYS)");
+  if (H < 1 || H > 65535 || E > 65535) return fail(CAT_ERR_LIMIT, "hull/edge count out of range");
+  const int ncell = map->nx * map->ny;
+  if (ncell < 1 || map->ray_cell_off[ncell] > 65535 || map->con_cell_off[ncell] > 65535)
+    return fail(CAT_ERR_LIMIT, "grid lists too long for 16-bit offsets");
+  for (int h = 0; h < H; ++h)
+    if (map->hull_off[h + 1] - map->hull_off[h] > 65535) return fail(CAT_ERR_LIMIT, "hull too large");
+  if (!(pr->dt > 0.0)) return fail(CAT_ERR_INVALID, "dt must be > 0");
+  const int P = A * (A - 1) / 2;
+  if (P > 32) return fail(CAT_ERR_LIMIT, "too many agent pairs for one warp");
+
+  // ---- blob
+  const int nreg = map->region_off[A];
+  BlobHeader hd{};
+  int off = sizeof(BlobHeader);
+  auto take = [&](int bytes) { int o = off; off = align_up(off + bytes, 16); return o; };
+  hd.n_hulls = H; hd.n_edges = E; hd.nx = map->nx; hd.ny = map->ny;
+  hd.gx0 = (float)map->grid_x0; hd.gy0 = (float)map->grid_y0; hd.cell = (float)map->cell;
+  hd.inv_cell = (float)(1.0 / map->cell);
+  hd.off_edge = take(E * 16);
+  hd.off_len = take(E * 4);
+  hd.off_hbb = take(H * 16);
+  hd.off_heo = take(H * 4);
+  hd.off_rayoff = take((ncell + 1) * 2);
+  hd.off_raylist = take(map->ray_cell_off[ncell] * 2 + 2);
+  hd.off_conoff = take((ncell + 1) * 2);
+  hd.off_conlist = take(map->con_cell_off[ncell] * 2 + 2);
+  hd.off_dir = take(R * 8);
+  hd.off_regoff = take((A + 1) * 4);
+  hd.off_regions = take((nreg > 0 ? nreg : 1) * 16);
+  hd.off_initpos = take(A * 8);
+  const int blob_bytes = align_up(off, 16);
+  std::vector<unsigned char> blob(blob_bytes, 0);
+  memcpy(blob.data(), &hd, sizeof(hd));
+  {
+    float* e = reinterpret_cast<float*>(blob.data() + hd.off_edge);
+    float* l = reinterpret_cast<float*>(blob.data() + hd.off_len);
+    for (int i = 0; i < E; ++i) {
+      e[4 * i + 0] = (float)map->vert[2 * i]; e[4 * i + 1] = (float)map->vert[2 * i + 1];
+      e[4 * i + 2] = (float)map->normal[2 * i]; e[4 * i + 3] = (float)map->normal[2 * i + 1];
+      l[i] = (float)map->edge_len[i];
+    }
+    float* bb = reinterpret_cast<float*>(blob.data() + hd.off_hbb);
+    uint32_t* eo = reinterpret_cast<uint32_t*>(blob.data() + hd.off_heo);
+    for (int h = 0; h < H; ++h) {
+      // shape bb = raw hull bb grown by the wall radius; rounded outwards so fp32 never shrinks it
+      bb[4 * h + 0] = nextafterf((float)(map->hull_bb[4 * h + 0] - pr->wall_radius), -INFINITY);
+      bb[4 * h + 1] = nextafterf((float)(map->hull_bb[4 * h + 1] - pr->wall_radius), -INFINITY);
+      bb[4 * h + 2] = nextafterf((float)(map->hull_bb[4 * h + 2] + pr->wall_radius), INFINITY);
+      bb[4 * h + 3] = nextafterf((float)(map->hull_bb[4 * h + 3] + pr->wall_radius), INFINITY);
+      eo[h] = (uint32_t)map->hull_off[h] | ((uint32_t)(map->hull_off[h + 1] - map->hull_off[h]) << 16);
+    }
+    uint16_t* ro = reinterpret_cast<uint16_t*>(blob.data() + hd.off_rayoff);
+    uint16_t* co = reinterpret_cast<uint16_t*>(blob.data() + hd.off_conoff);
+    for (int c = 0; c <= ncell; ++c) { ro[c] = (uint16_t)map->ray_cell_off[c]; co[c] = (uint16_t)map->con_cell_off[c]; }
+    uint16_t* rl = reinterpret_cast<uint16_t*>(blob.data() + hd.off_raylist);
+    for (int i = 0; i < map->ray_cell_off[ncell]; ++i) rl[i] = (uint16_t)map->ray_cell_hulls[i];
+    uint16_t* cl = reinterpret_cast<uint16_t*>(blob.data() + hd.off_conlist);
+    for (int i = 0; i < map->con_cell_off[ncell]; ++i) cl[i] = (uint16_t)map->con_cell_hulls[i];
+    float* dir = reinterpret_cast<float*>(blob.data() + hd.off_dir);
+    const double step = (2.0 * M_PI) / (double)R;  // entity.py:182 linspace(0, 2pi, R, endpoint=False)
+    for (int i = 0; i < R; ++i) { dir[2 * i] = (float)cos(i * step); dir[2 * i + 1] = (float)sin(i * step); }
+    int32_t* rg = reinterpret_cast<int32_t*>(blob.data() + hd.off_regoff);
+    for (int a = 0; a <= A; ++a) rg[a] = map->region_off[a];
+    float* rr = reinterpret_cast<float*>(blob.data() + hd.off_regions);
+    for (int i = 0; i < nreg * 4; ++i) rr[i] = (float)map->regions[i];
+    float* ip = reinterpret_cast<float*>(blob.data() + hd.off_initpos);
+    for (int i = 0; i < 2 * A; ++i) ip[i] = (float)map->init_pos[i];
+  }
+
+  CUDA_TRY(cudaSetDevice(device));
+  CatEnv* env = new CatEnv();
+  env->device = device;
+  env->n_worlds = n_worlds;
+  cudaError_t ce = cudaMalloc(&env->blob_dev, blob_bytes);
+  if (ce != cudaSuccess) { delete env; return fail(CAT_ERR_CUDA, std::string("cudaMalloc(map blob): ") + cudaGetErrorString(ce)); }
+  ce = cudaMemcpy(env->blob_dev, blob.data(), blob_bytes, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, std::string("cudaMemcpy(map blob): ") + cudaGetErrorString(ce)); }
+
+  KParams& k = env->kp;
+  k.blob = env->blob_dev; k.blob_bytes = blob_bytes;
+  k.n_worlds = n_worlds; k.gid0 = gid0;
+  k.A = A; k.nc = map->n_cops; k.R = R; k.P = P; k.nrays = A * R; k.nrays_pad = align_up(A * R, 32);
+  k.maxc = A * kSlots + P;
+  // record layout (4-byte words)
+  k.o_vel = 2 * A; k.o_vb = 4 * A; k.o_tc = 6 * A; k.o_wkey = 8 * A; k.o_wjn = 8 * A + A * kSlots;
+  k.o_page = 8 * A + 2 * A * kSlots; k.o_pjn = k.o_page + P; k.o_sc = k.o_pjn + P; k.o_ep = k.o_sc + 1;
+  k.rec_words = align_up(k.o_ep + 1, 32);
+  // scratch layout (bytes)
+  int so = k.rec_words * 4;
+  auto stake = [&](int bytes) { int o = so; so = align_up(so + bytes, 16); return o; };
+  k.s_rdist = stake(k.nrays_pad * 2);
+  k.s_rtype = stake(k.nrays_pad);
+  k.s_min = stake(CAT_MAX_AGENTS * 4);
+  k.s_near = stake(CAT_MAX_AGENTS * kNear * 2);
+  k.s_nearcnt = stake(CAT_MAX_AGENTS * 4);
+  k.s_con = stake(k.maxc * 32);
+  k.s_ccount = stake(CAT_MAX_AGENTS * 4);
+  k.s_order = stake(k.maxc);
+  k.scratch_bytes = align_up(so, 128);
+  k.state_dim = 0;
+  for (int a = 0; a < A; ++a) k.state_dim += 4 * R + 2 * (a < map->n_cops ? map->n_cops : map->n_thieves);
+  k.dt = (float)pr->dt; k.inv_dt = (float)(1.0 / pr->dt);
+  k.impulse = (float)pr->unit_velocity; k.inv_mass = (float)(1.0 / pr->unit_mass);
+  k.agent_r = (float)pr->unit_size; k.max_speed = (float)pr->max_speed; k.term_r = (float)pr->termination_radius;
+  k.ray_len = (float)pr->ray_length; k.ray_r = (float)pr->ray_radius; k.wall_r = (float)pr->wall_radius;
+  k.slop = (float)pr->collision_slop; k.bias_coef = (float)(1.0 - pow(pr->collision_bias, pr->dt));
+  k.iterations = pr->iterations; k.persistence = pr->collision_persistence; k.max_steps = pr->max_step_count;
+  k.stale = pr->stale_shape_cache; k.auto_reset = pr->auto_reset; k.seed = pr->seed;
+
+  env->smem_bytes = align_up(blob_bytes, 128) + kWarpsPerCta * k.scratch_bytes;
+  int max_optin = 0;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (env->smem_bytes > max_optin) {
+    cudaFree(env->blob_dev); delete env;
+    return fail(CAT_ERR_LIMIT, "map does not fit in shared memory (" + std::to_string(env->smem_bytes) + " B)");
+  }
+  ce = cudaFuncSetAttribute(cat_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_bytes);
+  if (ce != cudaSuccess) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
+  int n_sm = 0, occ = 0;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_world_kernel, kThreads, env->smem_bytes);
+  if (ce != cudaSuccess || occ < 1) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, "occupancy query failed"); }
+  const int need = (n_worlds + kWarpsPerCta - 1) / kWarpsPerCta;
+  env->grid = need < n_sm * occ ? need : n_sm * occ;  // persistent: at most one resident wave
+
+  CatEnvInfo& inf = env->info;
+  inf.n_worlds = n_worlds; inf.n_agents = A; inf.n_cops = map->n_cops; inf.n_thieves = map->n_thieves;
+  inf.n_rays = R; inf.n_hulls = H; inf.n_edges = E; inf.state_dim = k.state_dim; inf.record_words = k.rec_words;
+  inf.map_blob_bytes = blob_bytes; inf.smem_bytes_per_cta = env->smem_bytes; inf.warps_per_cta = kWarpsPerCta;
+  inf.grid = env->grid; inf.n_pairs = P;
+  *out = env;
+  return CAT_OK;
+}
+
+int cat_env_destroy(CatEnv* env) {
+  if (!env) return CAT_OK;
+  cudaSetDevice(env->device);
+  if (env->blob_dev) cudaFree(env->blob_dev);
+  delete env;
+  return CAT_OK;
+}
+
+int cat_env_info(const CatEnv* env, CatEnvInfo* info) {
+  if (!env || !info) return fail(CAT_ERR_INVALID, "null argument");
+  *info = env->info;
+  return CAT_OK;
+}
+
+int cat_env_set_seed(CatEnv* env, uint64_t seed) {
+  if (!env) return fail(CAT_ERR_INVALID, "null env");
+  env->kp.seed = seed;
+  return CAT_OK;
+}
+
+size_t cat_env_state_bytes(const CatEnv* env) {
+  return env ? (size_t)env->n_worlds * env->kp.rec_words * 4 : 0;
+}
+
+static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, void* stream) {
+  if (!env || !state_dev) return fail(CAT_ERR_INVALID, "null env/state");
+  KParams k = env->kp;
+  k.state = reinterpret_cast<float*>(state_dev);
+  k.mode = mode;
+  if (io) {
+    if (mode == MODE_STEP) {
+      if (!io->actions) return fail(CAT_ERR_INVALID, "step needs actions");
+      if (io->actions_kind < 0 || io->actions_kind > 3) return fail(CAT_ERR_INVALID, "bad actions_kind");
+      k.actions_kind = io->actions_kind;
+      if (io->actions_kind == 3) for (int a = 0; a < k.A; ++a) k.actions[a] = reinterpret_cast<const void* const*>(io->actions)[a];
+      else k.actions[0] = io->actions;
+    }
+    k.reset_mask = io->reset_mask;
+    k.obs_dist = io->obs_dist; k.obs_type = io->obs_type; k.reward = io->reward; k.terminated = io->terminated;
+    k.truncated = io->truncated; k.winner = io->winner; k.shared_dist = io->shared_dist; k.shared_type = io->shared_type;
+    k.team_pos = io->team_pos; k.obs_f32 = io->obs_f32; k.state_f32 = io->state_f32; k.hit_point = io->hit_point;
+  } else if (mode == MODE_STEP) {
+    return fail(CAT_ERR_INVALID, "step needs a CatStepIO");
+  }
+  cat_world_kernel<<<env->grid, kThreads, env->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(k);
+  CUDA_TRY(cudaGetLastError());
+  return CAT_OK;
+}
+
+int cat_env_init_state(CatEnv* env, void* state_dev, void* stream) { return launch(env, state_dev, nullptr, MODE_INIT, stream); }
+int cat_env_reset(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream) { return launch(env, state_dev, io, MODE_RESET, stream); }
+int cat_env_step(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream) { return launch(env, state_dev, io, MODE_STEP, stream); }
+int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream) { return launch(env, state_dev, io, MODE_OBSERVE, stream); }
+
+static int state_view(CatEnv* env, void* state_dev, const CatStateView* view, int set, void* stream) {
+  if (!env || !state_dev || !view) return fail(CAT_ERR_INVALID, "null argument");
+  const KParams& k = env->kp;
+  ViewParams p{};
+  p.state = reinterpret_cast<float*>(state_dev);
+  p.rec_words = k.rec_words; p.n_worlds = k.n_worlds; p.A = k.A; p.P = k.P;
+  p.o_vel = k.o_vel; p.o_vb = k.o_vb; p.o_tc = k.o_tc; p.o_wkey = k.o_wkey; p.o_wjn = k.o_wjn;
+  p.o_page = k.o_page; p.o_pjn = k.o_pjn; p.o_sc = k.o_sc; p.o_ep = k.o_ep;
+  p.v = *view; p.set = set;
+  const int threads = 128, blocks = (k.n_worlds + threads - 1) / threads;
+  cat_state_view_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return CAT_OK;
+}
+
+int cat_env_get_state(CatEnv* env, const void* state_dev, const CatStateView* view, void* stream) {
+  return state_view(env, const_cast<void*>(state_dev), view, 0, stream);
+}
+int cat_env_set_state(CatEnv* env, void* state_dev, const CatStateView* view, void* stream) {
+  return state_view(env, state_dev, view, 1, stream);
+}
+
+int cat_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values, float* returns,
+            float* advantages, double* stats_dev, int32_t T, int32_t M, float gamma, float lam, void* stream) {
+  if (!rewards || !dones || !values || !last_values || !returns || !advantages || !stats_dev)
+    return fail(CAT_ERR_INVALID, "null argument");
+  if (T < 1 || M < 1) return fail(CAT_ERR_INVALID, "T and M must be >= 1");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(double), s));
+  const int threads = 256, blocks = (M + threads - 1) / threads;
+  cat_gae_kernel<<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M,
+                                             gamma, lam);
+  CUDA_TRY(cudaGetLastError());
+  return CAT_OK;
+}
+
+int cat_adv_normalize(float* advantages, int64_t n, const double* stats_dev, int64_t count, void* stream) {
+  if (!advantages || !stats_dev) return fail(CAT_ERR_INVALID, "null argument");
+  if (n < 1 || count < 1) return fail(CAT_ERR_INVALID, "n and count must be >= 1");
+  if ((reinterpret_cast<uintptr_t>(advantages) & 15) != 0) return fail(CAT_ERR_INVALID, "advantages must be 16-byte aligned");
+  const int threads = 256;
+  long long blocks = (n / 4 + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cat_adv_normalize_kernel<<<(int)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(advantages, n, stats_dev, count);
+  CUDA_TRY(cudaGetLastError());
+  return CAT_OK;
+}
+
+}  // extern "C"

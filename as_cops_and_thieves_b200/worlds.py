@@ -1,0 +1,212 @@
+"""``CatWorlds`` — N lockstep worlds on one GPU behind the C ABI (``include/cat_b200.h``).
+
+Thin host object: owns the PyTorch tensors (packed state buffer + outputs), builds the
+``CatStepIO`` pointer table once, and enqueues one kernel launch per ``reset`` / ``step`` /
+``observe`` on the current torch CUDA stream.  No compute happens in Python and there is no CPU
+path: constructing it without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CatEnvInfo, CatMapDesc, CatParams, CatStateView, CatStepIO, CAT_WALL_SLOTS
+from .maps import CompiledMap
+from .params import EnvParams
+
+ActionsLike = Union[torch.Tensor, Mapping[str, torch.Tensor], Sequence[torch.Tensor]]
+
+
+def _require_cuda(device: torch.device) -> None:
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise _lib.CatError(
+            "as_cops_and_thieves_b200 needs a CUDA device (sm_100a); there is no CPU fallback "
+            f"(requested device={device}, torch.cuda.is_available()={torch.cuda.is_available()})")
+
+
+class CatWorlds:
+    def __init__(self, cmap: CompiledMap, n_worlds: int, *, device: Union[str, torch.device] = "cuda:0",
+                 gid0: int = 0, params: Optional[EnvParams] = None, want_f32: bool = True,
+                 want_hits: bool = False, **overrides):
+        self.device = torch.device(device)
+        _require_cuda(self.device)
+        self.L = _lib.load()
+        self.cmap = cmap
+        p = (params or EnvParams()).as_dict()
+        p.update(overrides)
+        self.params = p
+        self.n_worlds = int(n_worlds)
+        self.gid0 = int(gid0)
+
+        self._keep = dict(
+            hull_off=np.ascontiguousarray(cmap.hull_off, np.int32),
+            vert=np.ascontiguousarray(cmap.vert, np.float64),
+            normal=np.ascontiguousarray(cmap.normal, np.float64),
+            edge_len=np.ascontiguousarray(cmap.edge_len, np.float64),
+            hull_bb=np.ascontiguousarray(cmap.hull_bb, np.float64),
+            init_pos=np.ascontiguousarray(cmap.init_pos, np.float64),
+            region_off=np.ascontiguousarray(cmap.region_off, np.int32),
+            regions=np.ascontiguousarray(cmap.regions if len(cmap.regions) else np.zeros((1, 4)), np.float64),
+            ray_cell_off=np.ascontiguousarray(cmap.ray_cell_off, np.int32),
+            ray_cell_hulls=np.ascontiguousarray(np.append(cmap.ray_cell_hulls, 0), np.int32),
+            con_cell_off=np.ascontiguousarray(cmap.con_cell_off, np.int32),
+            con_cell_hulls=np.ascontiguousarray(np.append(cmap.con_cell_hulls, 0), np.int32),
+        )
+        k = self._keep
+        md = CatMapDesc(
+            cmap.n_hulls, cmap.n_edges, _lib.np_ptr(k["hull_off"]), _lib.np_ptr(k["vert"]), _lib.np_ptr(k["normal"]),
+            _lib.np_ptr(k["edge_len"]), _lib.np_ptr(k["hull_bb"]), cmap.n_cops, cmap.n_thieves,
+            _lib.np_ptr(k["init_pos"]), _lib.np_ptr(k["region_off"]), _lib.np_ptr(k["regions"]),
+            cmap.grid_x0, cmap.grid_y0, cmap.cell, cmap.nx, cmap.ny,
+            _lib.np_ptr(k["ray_cell_off"]), _lib.np_ptr(k["ray_cell_hulls"]),
+            _lib.np_ptr(k["con_cell_off"]), _lib.np_ptr(k["con_cell_hulls"]))
+        cp = CatParams(**{name: p[name] for name, _ in CatParams._fields_})
+        handle = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(self.L.cat_env_create(C.byref(md), C.byref(cp), self.n_worlds, self.gid0, dev_index,
+                                         C.byref(handle)), "cat_env_create")
+        self._h = handle
+        info = CatEnvInfo()
+        _lib.check(self.L.cat_env_info(self._h, C.byref(info)), "cat_env_info")
+        self.info = info
+        self.A, self.R, self.S, self.P = info.n_agents, info.n_rays, info.state_dim, info.n_pairs
+        self.n_cops, self.n_thieves = info.n_cops, info.n_thieves
+
+        N, A, R, dev = self.n_worlds, self.A, self.R, self.device
+        nbytes = int(self.L.cat_env_state_bytes(self._h))
+        self.state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)   # packed per-world records
+        self.obs_dist = torch.zeros((N, A, R), dtype=torch.float16, device=dev)
+        self.obs_type = torch.zeros((N, A, R), dtype=torch.uint8, device=dev)
+        self.reward = torch.zeros((N, A), dtype=torch.float32, device=dev)
+        self.terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.winner = torch.full((N,), -1, dtype=torch.int8, device=dev)
+        self.shared_dist = torch.zeros((N, 2, R), dtype=torch.float16, device=dev)
+        self.shared_type = torch.zeros((N, 2, R), dtype=torch.uint8, device=dev)
+        self.team_pos = torch.zeros((N, A, 2), dtype=torch.float16, device=dev)
+        self.obs_f32 = torch.zeros((A, N, 2 * R), dtype=torch.float32, device=dev) if want_f32 else None
+        self.state_f32 = torch.zeros((N, self.S), dtype=torch.float32, device=dev) if want_f32 else None
+        self.hit_point = torch.zeros((N, A, R, 2), dtype=torch.float32, device=dev) if want_hits else None
+        self._io = self._make_io()
+        self._ptr_table = (C.c_void_p * 8)()
+        _lib.check(self.L.cat_env_init_state(self._h, self.state.data_ptr(), self._stream()), "cat_env_init_state")
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _make_io(self) -> CatStepIO:
+        def dp(t):
+            return None if t is None else t.data_ptr()
+        return CatStepIO(None, 0, None, dp(self.obs_dist), dp(self.obs_type), dp(self.reward), dp(self.terminated),
+                         dp(self.truncated), dp(self.winner), dp(self.shared_dist), dp(self.shared_type),
+                         dp(self.team_pos), dp(self.obs_f32), dp(self.state_f32), dp(self.hit_point))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.L.cat_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_seed(self, seed: int) -> None:
+        _lib.check(self.L.cat_env_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), "cat_env_set_seed")
+        self.params["seed"] = int(seed)
+
+    # ------------------------------------------------------------------ the three launches
+    def reset(self, mask: Optional[torch.Tensor] = None) -> None:
+        """``BaseEnv.reset`` for the masked worlds (all if ``mask`` is None); fills the obs outputs."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert mask.numel() == self.n_worlds
+        self._io.reset_mask = None if mask is None else mask.data_ptr()
+        _lib.check(self.L.cat_env_reset(self._h, self.state.data_ptr(), C.byref(self._io), self._stream()),
+                   "cat_env_reset")
+        self._io.reset_mask = None
+
+    def step(self, actions: ActionsLike) -> None:
+        """``BaseEnv.step`` for every world: one kernel launch on the current stream."""
+        io = self._io
+        if isinstance(actions, torch.Tensor):
+            if actions.device != self.device or not actions.is_contiguous() or actions.numel() != self.n_worlds * self.A:
+                raise ValueError("actions must be a contiguous (N, A) tensor on the env's device")
+            kind = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}.get(actions.dtype)
+            if kind is None:
+                raise ValueError(f"unsupported action dtype {actions.dtype}")
+            io.actions, io.actions_kind = actions.data_ptr(), kind
+        else:
+            seq = list(actions.values()) if isinstance(actions, Mapping) else list(actions)
+            if len(seq) != self.A:
+                raise ValueError(f"need {self.A} per-agent action tensors")
+            for a, t in enumerate(seq):
+                if t.dtype != torch.int64 or t.device != self.device or not t.is_contiguous() or t.numel() != self.n_worlds:
+                    raise ValueError("per-agent actions must be contiguous int64 tensors of N elements on the env's device")
+                self._ptr_table[a] = t.data_ptr()
+            io.actions, io.actions_kind = C.cast(self._ptr_table, C.c_void_p), 3
+        _lib.check(self.L.cat_env_step(self._h, self.state.data_ptr(), C.byref(io), self._stream()), "cat_env_step")
+
+    def observe(self) -> None:
+        _lib.check(self.L.cat_env_observe(self._h, self.state.data_ptr(), C.byref(self._io), self._stream()),
+                   "cat_env_observe")
+
+    # ------------------------------------------------------------------ state access (parity tests, checkpoints)
+    def _view_tensors(self) -> Dict[str, torch.Tensor]:
+        N, A, P, dev, K = self.n_worlds, self.A, self.P, self.device, CAT_WALL_SLOTS
+        return dict(
+            pos=torch.zeros((N, A, 2), dtype=torch.float32, device=dev),
+            vel=torch.zeros((N, A, 2), dtype=torch.float32, device=dev),
+            vbias=torch.zeros((N, A, 2), dtype=torch.float32, device=dev),
+            tc=torch.zeros((N, A, 2), dtype=torch.float32, device=dev),
+            step_count=torch.zeros(N, dtype=torch.int32, device=dev),
+            episode=torch.zeros(N, dtype=torch.int32, device=dev),
+            wall_hull=torch.full((N, A, K), -1, dtype=torch.int32, device=dev),
+            wall_age=torch.full((N, A, K), -1, dtype=torch.int32, device=dev),
+            wall_jn=torch.zeros((N, A, K), dtype=torch.float32, device=dev),
+            pair_age=torch.full((N, max(P, 1)), -1, dtype=torch.int32, device=dev),
+            pair_jn=torch.zeros((N, max(P, 1)), dtype=torch.float32, device=dev),
+        )
+
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        t = self._view_tensors()
+        view = CatStateView(*[t[name].data_ptr() for name, _ in CatStateView._fields_])
+        _lib.check(self.L.cat_env_get_state(self._h, self.state.data_ptr(), C.byref(view), self._stream()),
+                   "cat_env_get_state")
+        return t
+
+    def set_state(self, **fields: torch.Tensor) -> None:
+        """Overwrite selected state fields (``pos``, ``vel``, ``vbias``, ``tc``, ``step_count``, ``episode``,
+        ``wall_hull``+``wall_age``+``wall_jn``, ``pair_age``+``pair_jn``)."""
+        proto = self._view_tensors()
+        ptrs, keep = [], []
+        for name, _ in CatStateView._fields_:
+            if name in fields:
+                t = torch.as_tensor(fields[name]).to(device=self.device, dtype=proto[name].dtype).contiguous()
+                if t.numel() != proto[name].numel():
+                    raise ValueError(f"{name}: expected {tuple(proto[name].shape)}, got {tuple(t.shape)}")
+                keep.append(t)
+                ptrs.append(t.data_ptr())
+            else:
+                ptrs.append(None)
+        unknown = set(fields) - {n for n, _ in CatStateView._fields_}
+        if unknown:
+            raise ValueError(f"unknown state fields {sorted(unknown)}")
+        view = CatStateView(*ptrs)
+        _lib.check(self.L.cat_env_set_state(self._h, self.state.data_ptr(), C.byref(view), self._stream()),
+                   "cat_env_set_state")
+        torch.cuda.current_stream(self.device).synchronize()  # `keep` tensors must outlive the copy
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Checkpoint = the packed state buffer (everything else is recomputed by ``observe``)."""
+        return {"state": self.state.clone(), "seed": torch.tensor(self.params["seed"])}
+
+    def load_state_dict(self, sd: Mapping[str, torch.Tensor]) -> None:
+        self.state.copy_(sd["state"].to(self.device))
+        self.set_seed(int(sd["seed"]))

@@ -1,0 +1,179 @@
+/* cat_b200 — C ABI of the B200-native batched cops-and-thieves environment step.
+ *
+ * The reference (Hevagog/as-cops-and-thieves) is pure Python over pymunk's CFFI; it has no FFI
+ * seam of its own.  Each entry point below replaces the reference call(s) named beside it; the
+ * Python class that mirrors the reference's PettingZoo / skrl surface
+ * (as_cops_and_thieves_b200/env.py) is the only caller.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every `*_dev` / device pointer is CUDA device memory owned by the caller
+ *     (PyTorch tensors); the library owns only the staged map constants inside CatEnv;
+ *   - all work is enqueued on the caller's stream (`stream` = cudaStream_t as void*), no internal
+ *     synchronisation, CUDA-graph capturable; one CatEnv per GPU / rank; not thread-safe per CatEnv;
+ *   - return 0 on success, negative CatStatus on failure; never throws, never exits;
+ *     cat_last_error() returns a thread-local message for the last failure;
+ *   - there is NO CPU fallback: every compute entry point fails with CAT_ERR_CUDA without a GPU.
+ *
+ * Layouts (N worlds, A = n_cops + n_thieves agents ordered cops then thieves
+ * [base_env.py:91-96], R rays):
+ *   obs_dist  f16 [N][A][R]   entity.py:200-210   (float16 chain reproduced bit-for-bit)
+ *   obs_type  u8  [N][A][R]   entity.py:222-241   (WALL 0, COP 1, THIEF 2, EMPTY 4)
+ *   reward    f32 [N][A]      cop.py:49-75, thief.py:48-69
+ *   terminated u8 [N]         captured or timed out (entity.py:146)
+ *   truncated  u8 [N]         timed out (base_env.py:397)
+ *   winner     i8 [N]         -1 none, 0 cop, 1 thief (base_env.py:399-411)
+ *   shared_dist f16 [N][2][R], shared_type u8 [N][2][R]   observation_spaces.py:97-121 (team 0 cops, 1 thieves)
+ *   team_pos  f16 [N][A][2]   observation_spaces.py:92-95
+ *   obs_f32   f32 [A][N][2R]  per-agent obs as skrl flattens it: [distance | object_type]
+ *   state_f32 f32 [N][S]      env.state() as skrl flattens it, S = sum_a (4R + 2*team_size(a))
+ *   hit_point f32 [N][A][R][2] pre-quantisation hit point (parity/debug)
+ */
+#ifndef CAT_B200_H
+#define CAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAT_ABI_VERSION 1
+#define CAT_MAX_AGENTS 8
+#define CAT_MAX_RAYS 128
+#define CAT_WALL_SLOTS 4 /* cached wall arbiters kept per agent */
+
+typedef enum {
+  CAT_OK = 0,
+  CAT_ERR_INVALID = -1, /* bad argument */
+  CAT_ERR_CUDA = -2,    /* CUDA runtime error (incl. no device) */
+  CAT_ERR_LIMIT = -3,   /* map / agent / ray count exceeds a compiled limit */
+} CatStatus;
+
+/* Host-side description of one compiled map (what maps.compile_map() yields; replaces
+ * Map.populate_space + pymunk.Poly hulls, /root/reference/src/maps/map.py:119-128). */
+typedef struct {
+  int32_t n_hulls, n_edges;
+  const int32_t* hull_off; /* [H+1] */
+  const double* vert;      /* [E][2] hull vertices, CCW; edge i runs vert[i-1] -> vert[i] */
+  const double* normal;    /* [E][2] outward unit normals */
+  const double* edge_len;  /* [E] */
+  const double* hull_bb;   /* [H][4] l,b,r,t of the raw hull */
+  int32_t n_cops, n_thieves;
+  const double* init_pos;    /* [A][2] */
+  const int32_t* region_off; /* [A+1] */
+  const double* regions;     /* [n_regions][4] x,y,w,h */
+  double grid_x0, grid_y0, cell;
+  int32_t nx, ny;
+  const int32_t* ray_cell_off;   /* [nx*ny+1] hulls within ray reach of each cell (ascending ids) */
+  const int32_t* ray_cell_hulls;
+  const int32_t* con_cell_off;   /* [nx*ny+1] hulls within contact reach of each cell */
+  const int32_t* con_cell_hulls;
+} CatMapDesc;
+
+/* pyproject.toml:12-19 [tool.physical-params], entity.py:84-86, Chipmunk space defaults, SimpleEnv defaults */
+typedef struct {
+  double dt;              /* simple_env.py:20 (1/60) */
+  int32_t max_step_count; /* simple_env.py:19 (400) */
+  double unit_velocity, unit_mass, unit_size, max_speed, termination_radius;
+  double ray_length, ray_radius, wall_radius;
+  int32_t n_rays;
+  int32_t iterations; /* cpSpace iterations (10) */
+  double collision_slop, collision_bias;
+  int32_t collision_persistence;
+  int32_t stale_shape_cache; /* 1 = pymunk behaviour: reset leaves the query centres of the shapes stale */
+  int32_t auto_reset;        /* 1 = done worlds are re-spawned inside the step and emit the reset observation */
+  uint64_t seed;
+} CatParams;
+
+typedef struct {
+  /* input (step only) */
+  const void* actions;   /* kind 0: u8 [N][A]; 1: i32 [N][A]; 2: i64 [N][A]; 3: HOST array of A device pointers to i64 [N] */
+  int32_t actions_kind;
+  /* input (reset only): u8 [N] device mask, NULL = every world */
+  const uint8_t* reset_mask;
+  /* outputs — device pointers, any may be NULL */
+  uint16_t* obs_dist;
+  uint8_t* obs_type;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  int8_t* winner;
+  uint16_t* shared_dist;
+  uint8_t* shared_type;
+  uint16_t* team_pos;
+  float* obs_f32;
+  float* state_f32;
+  float* hit_point;
+} CatStepIO;
+
+typedef struct {
+  int32_t n_worlds, n_agents, n_cops, n_thieves, n_rays, n_hulls, n_edges;
+  int32_t state_dim;          /* S of state_f32 */
+  int32_t record_words;       /* 4-byte words per world in the packed state buffer */
+  int32_t map_blob_bytes;     /* bytes staged into shared memory per CTA */
+  int32_t smem_bytes_per_cta;
+  int32_t warps_per_cta;
+  int32_t grid;               /* CTAs launched by cat_env_step */
+  int32_t n_pairs;
+} CatEnvInfo;
+
+/* SoA view of the world state for get/set (device pointers; any may be NULL = skip). */
+typedef struct {
+  float* pos;          /* [N][A][2] */
+  float* vel;          /* [N][A][2] */
+  float* vbias;        /* [N][A][2] */
+  float* tc;           /* [N][A][2] cached shape centres the queries see */
+  int32_t* step_count; /* [N] */
+  uint32_t* episode;   /* [N] */
+  int32_t* wall_hull;  /* [N][A][CAT_WALL_SLOTS] hull id, -1 empty */
+  int32_t* wall_age;   /* [N][A][CAT_WALL_SLOTS] */
+  float* wall_jn;      /* [N][A][CAT_WALL_SLOTS] */
+  int32_t* pair_age;   /* [N][P] pairs (i<j) in i-major order, -1 empty */
+  float* pair_jn;      /* [N][P] */
+} CatStateView;
+
+typedef struct CatEnv CatEnv;
+
+int cat_abi_version(void);
+const char* cat_last_error(void);
+
+/* BaseEnv.__init__ (base_env.py:51-121): stage the map, fix the constants.  gid0 = global id of
+ * this rank's world 0 (spawn RNG is keyed by global world id). */
+int cat_env_create(const CatMapDesc* map, const CatParams* params, int32_t n_worlds, int64_t gid0,
+                   int32_t device, CatEnv** out);
+int cat_env_destroy(CatEnv* env);
+int cat_env_info(const CatEnv* env, CatEnvInfo* info);
+/* reset(seed=...) (base_env.py:307-311): re-key the spawn RNG of this environment */
+int cat_env_set_seed(CatEnv* env, uint64_t seed);
+/* bytes of the caller-owned packed state buffer (`state_dev` below) */
+size_t cat_env_state_bytes(const CatEnv* env);
+
+/* fresh-environment state: agents at their map positions (entity.py:115), nothing cached */
+int cat_env_init_state(CatEnv* env, void* state_dev, void* stream);
+/* BaseEnv.reset (base_env.py:286-352) for the masked worlds */
+int cat_env_reset(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);
+/* BaseEnv.step (base_env.py:354-413) for every world, one launch */
+int cat_env_step(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);
+/* Entity.get_observation + get_shared_observations of the current state (entity.py:159-220,
+ * observation_spaces.py:67-131) without stepping */
+int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);
+/* parity-test access to the hidden state */
+int cat_env_get_state(CatEnv* env, const void* state_dev, const CatStateView* view, void* stream);
+int cat_env_set_state(CatEnv* env, void* state_dev, const CatStateView* view, void* stream);
+
+/* skrl MAPPO._update GAE (call site agent_learning_utils.py:198-199).
+ * rewards/values [T][M] f32, dones [T][M] u8, last_values [M]; returns/advantages [T][M].
+ * stats_dev: 2 doubles {sum(adv), sum(adv^2)} accumulated by this call (zeroed first). */
+int cat_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values,
+            float* returns, float* advantages, double* stats_dev, int32_t T, int32_t M, float gamma,
+            float lam, void* stream);
+/* advantages = (advantages - mean) / (std + 1e-8) with mean/std (unbiased) from stats over `count`
+ * samples; all-reduce stats and count across ranks first for a global normalisation. */
+int cat_adv_normalize(float* advantages, int64_t n, const double* stats_dev, int64_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAT_B200_H */
