@@ -34,6 +34,7 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMinCtasPerSm = 3;
 constexpr int kSlots = CAT_WALL_SLOTS;
 constexpr int kNear = 4;            // hulls an origin can be "inside" (alpha = 0 rule) per agent
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
@@ -74,7 +75,7 @@ struct MapView {
   const uint16_t* ray_list;
   const uint16_t* con_off;
   const uint16_t* con_list;
-  const float2* dir;       // unit ray directions
+  const float4* dir;       // per ray: ux, uy, 1/ux, 1/uy (unit direction and its reciprocals)
   const int32_t* reg_off;
   const float4* regions;
   const float2* init_pos;
@@ -134,7 +135,7 @@ __device__ __forceinline__ MapView make_view(const unsigned char* blob) {
   m.ray_list = reinterpret_cast<const uint16_t*>(blob + h->off_raylist);
   m.con_off = reinterpret_cast<const uint16_t*>(blob + h->off_conoff);
   m.con_list = reinterpret_cast<const uint16_t*>(blob + h->off_conlist);
-  m.dir = reinterpret_cast<const float2*>(blob + h->off_dir);
+  m.dir = reinterpret_cast<const float4*>(blob + h->off_dir);
   m.reg_off = reinterpret_cast<const int32_t*>(blob + h->off_regoff);
   m.regions = reinterpret_cast<const float4*>(blob + h->off_regions);
   m.init_pos = reinterpret_cast<const float2*>(blob + h->off_initpos);
@@ -147,135 +148,155 @@ __device__ __forceinline__ MapView make_view(const unsigned char* blob) {
 
 // Closest feature of the raw hull to point p (CircleToPoly's GJK/EPA result for a point):
 // d = signed distance (negative inside: least-penetration edge), n = unit vector from p towards
-// the hull surface.  Same quantity cpPolyShapePointQuery reports as +-minDist.
-__device__ __forceinline__ void hull_closest(const MapView& m, int h, float px, float py, float& d, float& nx,
-                                             float& ny) {
-  const uint32_t eo = m.hull_eo[h];
+// the hull surface.  Same quantity cpPolyShapePointQuery reports as +-minDist.  Everything is
+// evaluated relative to the hull's own vertices so that d keeps ~1e-6 absolute accuracy.
+__device__ __noinline__ float3 hull_closest_impl(const float4* __restrict__ edge, uint32_t eo, float px, float py) {
   const int o = eo & 0xFFFF, n = eo >> 16;
   bool inside = true, binterior = false;
   float maxpd = -CUDART_INF_F, mnx = 0.f, mny = 0.f;
-  float bestd2 = CUDART_INF_F, bqx = px, bqy = py, benx = 0.f, beny = 0.f;
-  float4 pv = m.edge[o + n - 1];
+  float bestd2 = CUDART_INF_F, bdx = 0.f, bdy = 0.f, benx = 0.f, beny = 0.f, bpd = 0.f;
+  float4 pv = edge[o + n - 1];
   float v0x = pv.x, v0y = pv.y;
   for (int i = 0; i < n; ++i) {
-    const float4 e = m.edge[o + i];
-    const float rx = px - e.x, ry = py - e.y;
-    const float pd = rx * e.z + ry * e.w;
+    const float4 e = edge[o + i];
+    const float pd = (px - e.x) * e.z + (py - e.y) * e.w;
     if (pd > 0.f) inside = false;
     if (pd > maxpd) { maxpd = pd; mnx = e.z; mny = e.w; }
     const float edx = e.x - v0x, edy = e.y - v0y;
-    float t = ((px - v0x) * edx + (py - v0y) * edy) / (edx * edx + edy * edy);
+    const float r0x = px - v0x, r0y = py - v0y;
+    float t = (r0x * edx + r0y * edy) / (edx * edx + edy * edy);
     const bool interior = (t > 0.f) && (t < 1.f);
     t = fminf(fmaxf(t, 0.f), 1.f);
-    const float qx = v0x + edx * t, qy = v0y + edy * t;
-    const float ddx = px - qx, ddy = py - qy;
-    const float d2 = ddx * ddx + ddy * ddy;
-    if (d2 < bestd2) { bestd2 = d2; bqx = qx; bqy = qy; benx = e.z; beny = e.w; binterior = interior; }
+    const float ddx = r0x - edx * t, ddy = r0y - edy * t;  // p - q
+    const float d2 = interior ? pd * pd : ddx * ddx + ddy * ddy;
+    if (d2 < bestd2) { bestd2 = d2; bdx = ddx; bdy = ddy; benx = e.z; beny = e.w; binterior = interior; bpd = pd; }
     v0x = e.x; v0y = e.y;
   }
-  if (inside) { d = maxpd; nx = -mnx; ny = -mny; return; }
-  d = sqrtf(bestd2);
-  if (binterior) { nx = -benx; ny = -beny; }
-  else { const float inv = 1.f / (d + 1.17549435e-38f); nx = (bqx - px) * inv; ny = (bqy - py) * inv; }
+  if (inside) return make_float3(maxpd, -mnx, -mny);
+  if (binterior) return make_float3(fabsf(bpd), -benx, -beny);
+  const float d = sqrtf(bestd2);
+  const float inv = 1.f / (d + 1.17549435e-38f);
+  return make_float3(d, -bdx * inv, -bdy * inv);
+}
+
+__device__ __forceinline__ void hull_closest(const MapView& m, int h, float px, float py, float& d, float& nx,
+                                             float& ny) {
+  const float3 r = hull_closest_impl(m.edge, m.hull_eo[h], px, py);
+  d = r.x; nx = r.y; ny = r.z;
 }
 
 // cpBBSegmentQuery(bb, a, b) < 1: the BB-tree visits a leaf only if the THIN segment enters its bb.
-__device__ __forceinline__ bool thin_bb_hit(const float4 bb, float ox, float oy, float dx, float dy) {
+// (idx, idy) = 1 / (b - a) per axis (unused where the delta is exactly zero).
+__device__ __forceinline__ bool thin_bb_hit(const float4 bb, float ox, float oy, bool zx, bool zy, float idx,
+                                            float idy) {
   float tmin = -CUDART_INF_F, tmax = CUDART_INF_F;
-  if (dx == 0.f) {
+  if (zx) {
     if (ox < bb.x || bb.z < ox) return false;
   } else {
-    const float inv = 1.f / dx;
-    const float t1 = (bb.x - ox) * inv, t2 = (bb.z - ox) * inv;
-    tmin = fmaxf(tmin, fminf(t1, t2));
-    tmax = fminf(tmax, fmaxf(t1, t2));
+    const float t1 = (bb.x - ox) * idx, t2 = (bb.z - ox) * idx;
+    tmin = fminf(t1, t2);
+    tmax = fmaxf(t1, t2);
   }
-  if (dy == 0.f) {
+  if (zy) {
     if (oy < bb.y || bb.w < oy) return false;
   } else {
-    const float inv = 1.f / dy;
-    const float t1 = (bb.y - oy) * inv, t2 = (bb.w - oy) * inv;
+    const float t1 = (bb.y - oy) * idy, t2 = (bb.w - oy) * idy;
     tmin = fmaxf(tmin, fminf(t1, t2));
     tmax = fminf(tmax, fmaxf(t1, t2));
   }
   return (tmin <= tmax) && (0.f <= tmax) && (tmin < 1.f);
 }
 
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct Hit {
-  float s;        // distance along the ray of the fat-ray centre at first touch (alpha * L)
-  float nx, ny;   // surface normal at the hit (hit point = centre - n * ray_radius)
-  int id;         // -1 none, < H hull, H + j agent j
+  float s;    // distance along the ray of the fat-ray centre at first touch (alpha * L)
+  int id;     // -1 none, < H hull, H + j agent j
+  int feat;   // walls: edge index * 2 + (1 = bevelled vertex, 0 = plane); the normal is rebuilt once at the end
 };
 
-// cpPolyShapeSegmentQuery for hull h against the ray o + s*u, s in [0, L): planes offset by
-// rsum = wall_r + ray_r, then the bevelled vertexes as circles of radius rsum.
-// The alpha = 0 "start inside" rule of cpShapeSegmentQuery is handled by the caller.
-__device__ __forceinline__ void ray_hull(const MapView& m, int h, float ox, float oy, float ux, float uy, float L,
-                                         float rsum, Hit& best) {
-  const float4 bb = m.hull_bb[h];
-  if (!thin_bb_hit(bb, ox, oy, ux * L, uy * L)) return;
-  const uint32_t eo = m.hull_eo[h];
-  const int o = eo & 0xFFFF, n = eo >> 16;
-  const float rs2 = rsum * rsum, inv_rs = 1.f / rsum;
-  for (int i = 0; i < n; ++i) {
-    const float4 e = m.edge[o + i];
-    const float len = m.edge_len[o + i];
-    const float rx = ox - e.x, ry = oy - e.y;
-    // plane i: d = a.n - v0.n - rsum ; t = d / (a.n - b.n)
-    const float d = rx * e.z + ry * e.w - rsum;
-    const float un = ux * e.z + uy * e.w;
-    if (d >= 0.f && un < 0.f) {
-      const float s = d / (-un);
-      if (s < L && s <= best.s) {
-        const float c = e.z * (ry + s * uy) - e.w * (rx + s * ux);  // cross(n, P - v_i) in [-len, 0]
-        if (c >= -len && c <= 0.f) { best.s = s; best.nx = e.z; best.ny = e.w; best.id = h; }
-      }
-    }
-    // bevel circle at v_i (CircleSegmentQuery), perpendicular-offset form of the discriminant
-    const float b = rx * ux + ry * uy;
-    const float cp = rx * uy - ry * ux;
-    const float disc = rs2 - cp * cp;
-    if (disc >= 0.f) {
-      const float s = -b - sqrtf(disc);
-      if (s >= 0.f && s < L && s <= best.s) {
-        best.s = s; best.nx = (rx + s * ux) * inv_rs; best.ny = (ry + s * uy) * inv_rs; best.id = h;
-      }
-    }
+struct Ray {
+  float ox, oy, ux, uy, L;
+  bool zx, zy;      // direction component exactly zero (cpBBSegmentQuery special case)
+  float idx, idy;   // 1 / (L * u)
+};
+
+// One edge of cpPolyShapeSegmentQuery against the ray o + s*u, s in [0, L): plane i offset by
+// rsum = wall_r + ray_r (accepted inside the edge's tangential extent) and the bevelled vertex v_i
+// as a circle of radius rsum (CircleSegmentQuery, perpendicular-offset form of the discriminant).
+__device__ __forceinline__ void ray_edge(const MapView& m, int ei, int h, const Ray& r, float rsum, float rs2,
+                                         Hit& best) {
+  const float4 e = m.edge[ei];
+  const float rx = r.ox - e.x, ry = r.oy - e.y;
+  const float d = fmaf(rx, e.z, fmaf(ry, e.w, -rsum));   // a.n - v0.n - rsum
+  const float un = fmaf(r.ux, e.z, r.uy * e.w);          // (b.n - a.n) / L
+  if (d >= 0.f && un < 0.f) {
+    const float s = __fdividef(d, -un);
+    const float c = fmaf(e.z, fmaf(s, r.uy, ry), -e.w * fmaf(s, r.ux, rx));  // cross(n, P - v_i) in [-len, 0]
+    if (s < r.L && s <= best.s && c <= 0.f && c >= -m.edge_len[ei]) { best.s = s; best.id = h; best.feat = ei * 2; }
   }
+  const float cp = fmaf(rx, r.uy, -ry * r.ux);
+  const float disc = fmaf(-cp, cp, rs2);
+  if (disc >= 0.f) {
+    const float s = -fmaf(rx, r.ux, ry * r.uy) - fast_sqrt(disc);
+    if (s >= 0.f && s < r.L && s <= best.s) { best.s = s; best.id = h; best.feat = ei * 2 + 1; }
+  }
+}
+
+// Surface normal of a wall hit (plane: the edge normal; bevel: from the vertex to the ray centre).
+__device__ __forceinline__ float2 wall_hit_normal(const MapView& m, const Hit& hit, const Ray& r, float rsum) {
+  const float4 e = m.edge[hit.feat >> 1];
+  if ((hit.feat & 1) == 0) return make_float2(e.z, e.w);
+  const float inv = 1.f / rsum;
+  return make_float2((r.ox - e.x + hit.s * r.ux) * inv, (r.oy - e.y + hit.s * r.uy) * inv);
 }
 
 // CircleSegmentQuery against an agent circle (cached centre c, radius r1) with ray radius r2.
-__device__ __forceinline__ void ray_circle(float cx, float cy, float rs, float ox, float oy, float ux, float uy,
-                                           float L, int id, Hit& best) {
-  const float rx = ox - cx, ry = oy - cy;
-  const float b = rx * ux + ry * uy;
-  const float cp = rx * uy - ry * ux;
-  const float disc = rs * rs - cp * cp;
+__device__ __forceinline__ void ray_circle(float cx, float cy, float rs, const Ray& r, int id, Hit& best) {
+  const float rx = r.ox - cx, ry = r.oy - cy;
+  const float cp = fmaf(rx, r.uy, -ry * r.ux);
+  const float disc = fmaf(-cp, cp, rs * rs);
   if (disc >= 0.f) {
-    const float s = -b - sqrtf(disc);
-    if (s >= 0.f && s < L && s < best.s) {
-      const float inv = 1.f / rs;
-      best.s = s; best.nx = (rx + s * ux) * inv; best.ny = (ry + s * uy) * inv; best.id = id;
-    }
+    const float s = -fmaf(rx, r.ux, ry * r.uy) - fast_sqrt(disc);
+    if (s >= 0.f && s < r.L && s < best.s) { best.s = s; best.id = id; }
   }
 }
 
-// Thin segment a -> b against hull h with query radius 0 (capture line of sight,
-// base_env.py:536-544): true if the hull blocks (alpha < 1), including the alpha = 0 rule.
-__device__ __forceinline__ bool los_hull_blocks(const MapView& m, int h, float ax, float ay, float bx, float by,
-                                                float wall_r) {
-  const float4 bb = m.hull_bb[h];
-  const float dx = bx - ax, dy = by - ay;
-  if (!thin_bb_hit(bb, ax, ay, dx, dy)) return false;
-  float d, nx, ny;
-  hull_closest(m, h, ax, ay, d, nx, ny);
-  if (d - wall_r <= 0.f) return true;  // start point inside the rounded hull
-  const float L = sqrtf(dx * dx + dy * dy);
-  if (!(L > 0.f)) return false;
-  Hit best; best.s = L; best.id = -1; best.nx = best.ny = 0.f;
-  const float inv = 1.f / L;
-  ray_hull(m, h, ax, ay, dx * inv, dy * inv, L, wall_r, best);
-  return best.id >= 0;
+__device__ __forceinline__ Ray make_ray(float ax, float ay, float dx, float dy) {
+  Ray r;
+  r.ox = ax; r.oy = ay;
+  r.L = sqrtf(dx * dx + dy * dy);
+  const float inv = r.L > 0.f ? 1.f / r.L : 0.f;
+  r.ux = dx * inv; r.uy = dy * inv;
+  r.zx = dx == 0.f; r.zy = dy == 0.f;
+  r.idx = r.zx ? 0.f : 1.f / dx;
+  r.idy = r.zy ? 0.f : 1.f / dy;
+  return r;
+}
+
+// Thin segment a -> b against the wall hulls h0, h0+32, ... with query radius 0 (capture line of
+// sight, base_env.py:536-544): true if any blocks (alpha < 1), including the alpha = 0 rule.
+// Rare path (only evaluated for thief-cop pairs closer than the capture radius): not inlined.
+__device__ __noinline__ bool los_blocked(const unsigned char* blob, int h0, float ax, float ay, float bx, float by,
+                                         float wall_r) {
+  const MapView m = make_view(blob);
+  const Ray r = make_ray(ax, ay, bx - ax, by - ay);
+  bool blocked = false;
+  for (int h = h0; h < m.H && !blocked; h += 32) {
+    if (!thin_bb_hit(m.hull_bb[h], ax, ay, r.zx, r.zy, r.idx, r.idy)) continue;
+    const float3 c = hull_closest_impl(m.edge, m.hull_eo[h], ax, ay);
+    if (c.x - wall_r <= 0.f) { blocked = true; break; }  // start point inside the rounded hull
+    if (!(r.L > 0.f)) continue;
+    Hit best; best.s = r.L; best.id = -1; best.feat = 0;
+    const uint32_t eo = m.hull_eo[h];
+    for (int ei = eo & 0xFFFF, ee = (eo & 0xFFFF) + (eo >> 16); ei < ee; ++ei) ray_edge(m, ei, h, r, wall_r, wall_r * wall_r, best);
+    blocked = best.id >= 0;
+  }
+  return blocked;
 }
 
 __device__ __forceinline__ int grid_cell(const MapView& m, float x, float y) {
@@ -299,11 +320,17 @@ struct Warp {
 };
 
 // Sensor sweep of every agent of one world (entity.py:159-220) into shared memory.
+//
+// One lane per ray.  The wall traversal is a single warp-converged loop: every iteration each lane
+// that still has work first *fetches* (walks grid cells / cell lists until it holds a hull whose bb
+// the thin ray enters — short, cheap, divergent) and then all lanes together test ONE edge of
+// their current hull (the expensive part, converged).  Lanes therefore pay for the longest edge
+// sequence in the warp, not for the sum of everyone's nested loops.
 __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
   const int A = k.A, R = k.R, lane = w.lane;
   const float* pos = w.rec;
   const float* tc = w.rec + k.o_tc;
-  const float L = k.ray_len, rsum = k.wall_r + k.ray_r;
+  const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len, rs2 = rsum * rsum;
   // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates
   if (lane < A) {
     const float px = pos[2 * lane], py = pos[2 * lane + 1];
@@ -312,6 +339,8 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
     if (cell >= 0) {
       for (int q = m.ray_off[cell]; q < m.ray_off[cell + 1]; ++q) {
         const int h = m.ray_list[q];
+        const float4 bb = m.hull_bb[h];  // already grown by wall_r: cheap reject before the exact distance
+        if (px < bb.x - k.ray_r || px > bb.z + k.ray_r || py < bb.y - k.ray_r || py > bb.w + k.ray_r) continue;
         float d, nx, ny;
         hull_closest(m, h, px, py, d, nx, ny);
         if (d - k.wall_r <= k.ray_r && cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
@@ -324,83 +353,112 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
 
   for (int r0 = 0; r0 < k.nrays_pad; r0 += 32) {
     const int r = r0 + lane;
-    if (r < k.nrays) {
-      const int a = r / R, i = r - a * R;
-      const float ox = pos[2 * a], oy = pos[2 * a + 1];
-      const float2 u = m.dir[i];
-      Hit best; best.s = L; best.id = -1; best.nx = 0.f; best.ny = 0.f;
-      bool zero_hit = false;   // alpha = 0: point stays at the ray end (cpShapeSegmentQuery)
-      // dynamic shapes: the other agents' cached centres
-      for (int j = 0; j < A; ++j) {
-        if (j == a) continue;
-        const float cx = tc[2 * j], cy = tc[2 * j + 1];
-        const float ddx = ox - cx, ddy = oy - cy;
-        if (sqrtf(ddx * ddx + ddy * ddy) - k.agent_r <= k.ray_r) {
-          if (!zero_hit) { zero_hit = true; best.s = 0.f; best.id = m.H + j; }
-        } else if (!zero_hit) {
-          ray_circle(cx, cy, k.agent_r + k.ray_r, ox, oy, u.x, u.y, L, m.H + j, best);
-        }
+    const bool valid = r < k.nrays;
+    const int a = valid ? r / R : 0, i = valid ? r - a * R : 0;
+    const float4 dv = m.dir[i];
+    Ray ry_;
+    ry_.ox = pos[2 * a]; ry_.oy = pos[2 * a + 1]; ry_.ux = dv.x; ry_.uy = dv.y; ry_.L = L;
+    ry_.zx = dv.x == 0.f; ry_.zy = dv.y == 0.f;
+    ry_.idx = dv.z * inv_L; ry_.idy = dv.w * inv_L;
+    const float ox = ry_.ox, oy = ry_.oy;
+    Hit best; best.s = L; best.id = -1; best.feat = 0;
+    bool zero_hit = false;   // alpha = 0: point stays at the ray end (cpShapeSegmentQuery)
+    // dynamic shapes: the other agents' cached centres
+    const float reach = k.agent_r + k.ray_r;
+    for (int j = 0; j < A; ++j) {
+      if (j == a) continue;
+      const float cx = tc[2 * j], cy = tc[2 * j + 1];
+      const float ddx = ox - cx, ddy = oy - cy;
+      if (ddx * ddx + ddy * ddy <= reach * reach) {  // |a - c| - r <= ray_r
+        if (!zero_hit) { zero_hit = true; best.s = 0.f; best.id = m.H + j; }
+      } else if (!zero_hit) {
+        ray_circle(cx, cy, reach, ry_, m.H + j, best);
       }
-      // static shapes with the origin inside their reach: visited only if the thin ray enters the bb
-      const uint32_t ncnt = w.nearcnt[a];
-      bool wall_zero = false;
-      for (uint32_t q = 0; q < ncnt; ++q) {
-        const int h = w.near[a * kNear + q];
-        if (!wall_zero && thin_bb_hit(m.hull_bb[h], ox, oy, u.x * L, u.y * L)) {
-          wall_zero = true; zero_hit = true; best.s = 0.f; best.id = h;  // static index is queried first
-        }
+    }
+    // static shapes with the origin inside their reach: visited only if the thin ray enters the bb
+    const uint32_t ncnt = w.nearcnt[a];
+    bool wall_zero = false;
+    for (uint32_t q = 0; q < ncnt; ++q) {
+      const int h = w.near[a * kNear + q];
+      if (!wall_zero && thin_bb_hit(m.hull_bb[h], ox, oy, ry_.zx, ry_.zy, ry_.idx, ry_.idy)) {
+        wall_zero = true; zero_hit = true; best.s = 0.f; best.id = h;  // static index is queried first
       }
-      if (!zero_hit) {
-        // walk the uniform grid along the ray; stop once the next cell starts beyond the best hit
-        const float gx = (ox - m.gx0) * m.inv_cell, gy = (oy - m.gy0) * m.inv_cell;
-        const float dgx = u.x * m.inv_cell, dgy = u.y * m.inv_cell;  // grid units per unit distance
-        float t0 = 0.f, t1 = best.s;
-        bool ok = true;
-        if (dgx != 0.f) {
-          const float ta = (0.f - gx) / dgx, tb = ((float)m.nx - gx) / dgx;
-          t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-        } else if (gx < 0.f || gx >= (float)m.nx) ok = false;
-        if (dgy != 0.f) {
-          const float ta = (0.f - gy) / dgy, tb = ((float)m.ny - gy) / dgy;
-          t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-        } else if (gy < 0.f || gy >= (float)m.ny) ok = false;
-        if (ok && t0 <= t1) {
-          const float sx = gx + dgx * t0, sy = gy + dgy * t0;
-          int ix = min(max((int)floorf(sx), 0), m.nx - 1);
-          int iy = min(max((int)floorf(sy), 0), m.ny - 1);
-          const int stepx = dgx > 0.f ? 1 : -1, stepy = dgy > 0.f ? 1 : -1;
-          const float tdx = dgx != 0.f ? fabsf(1.f / dgx) : CUDART_INF_F;
-          const float tdy = dgy != 0.f ? fabsf(1.f / dgy) : CUDART_INF_F;
-          float tmx = dgx != 0.f ? ((float)(ix + (stepx > 0 ? 1 : 0)) - gx) / dgx : CUDART_INF_F;
-          float tmy = dgy != 0.f ? ((float)(iy + (stepy > 0 ? 1 : 0)) - gy) / dgy : CUDART_INF_F;
-          int last1 = -1, last2 = -1;
-          for (int guard = 0; guard < 4096; ++guard) {
-            const int cell = iy * m.nx + ix;
-            const int qb = m.ray_off[cell], qe = m.ray_off[cell + 1];
-            for (int q = qb; q < qe; ++q) {
-              const int h = m.ray_list[q];
-              if (h == last1 || h == last2) continue;
-              last2 = last1; last1 = h;
-              ray_hull(m, h, ox, oy, u.x, u.y, L, rsum, best);
-            }
-            const float tn = fminf(tmx, tmy);
-            if (!(tn < best.s)) break;
-            if (tmx < tmy) { ix += stepx; tmx += tdx; } else { iy += stepy; tmy += tdy; }
-            if (ix < 0 || iy < 0 || ix >= m.nx || iy >= m.ny) break;
+    }
+
+    // ---- uniform-grid walk set-up (clip the ray to the grid, find the first cell)
+    bool active = valid && !zero_hit;
+    int ix = 0, iy = 0, stepx = 1, stepy = 1, q = 0, qe = 0, ei = 0, ee = 0, hcur = -1, last1 = -1, last2 = -1;
+    float tmx = CUDART_INF_F, tmy = CUDART_INF_F, tdx = CUDART_INF_F, tdy = CUDART_INF_F;
+    if (active) {
+      const float gx = (ox - m.gx0) * m.inv_cell, gy = (oy - m.gy0) * m.inv_cell;
+      const float igx = dv.z * m.cell, igy = dv.w * m.cell;  // ray distance per grid unit along each axis
+      float t0 = 0.f, t1 = best.s;
+      if (!ry_.zx) {
+        const float ta = (0.f - gx) * igx, tb = ((float)m.nx - gx) * igx;
+        t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+      } else if (gx < 0.f || gx >= (float)m.nx) active = false;
+      if (!ry_.zy) {
+        const float ta = (0.f - gy) * igy, tb = ((float)m.ny - gy) * igy;
+        t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+      } else if (gy < 0.f || gy >= (float)m.ny) active = false;
+      if (!(t0 <= t1)) active = false;
+      if (active) {
+        const float sx = gx + dv.x * m.inv_cell * t0, sy = gy + dv.y * m.inv_cell * t0;
+        ix = min(max((int)floorf(sx), 0), m.nx - 1);
+        iy = min(max((int)floorf(sy), 0), m.ny - 1);
+        stepx = dv.x > 0.f ? 1 : -1; stepy = dv.y > 0.f ? 1 : -1;
+        tdx = ry_.zx ? CUDART_INF_F : fabsf(igx);
+        tdy = ry_.zy ? CUDART_INF_F : fabsf(igy);
+        tmx = ry_.zx ? CUDART_INF_F : ((float)(ix + (stepx > 0 ? 1 : 0)) - gx) * igx;
+        tmy = ry_.zy ? CUDART_INF_F : ((float)(iy + (stepy > 0 ? 1 : 0)) - gy) * igy;
+        const int cell = iy * m.nx + ix;
+        q = m.ray_off[cell]; qe = m.ray_off[cell + 1];
+      }
+    }
+    // ---- converged traversal: fetch (divergent, cheap) then one edge test (converged)
+    for (;;) {
+      if (active && ei == ee) {
+        for (;;) {
+          if (q < qe) {
+            const int h = m.ray_list[q++];
+            if (h == last1 || h == last2) continue;
+            last2 = last1; last1 = h;
+            if (!thin_bb_hit(m.hull_bb[h], ox, oy, ry_.zx, ry_.zy, ry_.idx, ry_.idy)) continue;
+            const uint32_t eo = m.hull_eo[h];
+            ei = eo & 0xFFFF; ee = ei + (eo >> 16); hcur = h;
+            break;
           }
+          // next cell; stop once it starts beyond the best hit (or the sensor range) or leaves the grid
+          if (!(fminf(tmx, tmy) < best.s)) { active = false; break; }
+          if (tmx < tmy) { ix += stepx; tmx += tdx; } else { iy += stepy; tmy += tdy; }
+          if (ix < 0 || iy < 0 || ix >= m.nx || iy >= m.ny) { active = false; break; }
+          const int cell = iy * m.nx + ix;
+          q = m.ray_off[cell]; qe = m.ray_off[cell + 1];
         }
       }
+      if (!__any_sync(0xFFFFFFFFu, active)) break;
+      if (active) { ray_edge(m, ei, hcur, ry_, rsum, rs2, best); ++ei; }
+    }
+
+    if (valid) {
       // entity.py:200-215 — float16 chain, reproduced at each of its rounding points
       uint16_t dbits;
       uint8_t type;
-      float hx, hy;
+      float hx = ox + L * dv.x, hy = oy + L * dv.y;   // ray end: reported when nothing is hit or alpha = 0
       if (best.id < 0) {
         dbits = __half_as_ushort(__float2half_rn(L));
         type = TYPE_EMPTY;
-        hx = ox + L * u.x; hy = oy + L * u.y;
       } else {
-        if (zero_hit) { hx = ox + L * u.x; hy = oy + L * u.y; }
-        else { hx = ox + best.s * u.x - best.nx * k.ray_r; hy = oy + best.s * u.y - best.ny * k.ray_r; }
+        if (!zero_hit) {
+          float2 n;
+          if (best.id < m.H) n = wall_hit_normal(m, best, ry_, rsum);
+          else {
+            const int j = best.id - m.H;
+            const float inv = 1.f / reach;
+            n = make_float2((ox - tc[2 * j] + best.s * dv.x) * inv, (oy - tc[2 * j + 1] + best.s * dv.y) * inv);
+          }
+          hx = ox + best.s * dv.x - n.x * k.ray_r; hy = oy + best.s * dv.y - n.y * k.ray_r;
+        }
         const float pxh = __half2float(__float2half_rn(hx)), pyh = __half2float(__float2half_rn(hy));
         const float oxh = __half2float(__float2half_rn(ox)), oyh = __half2float(__float2half_rn(oy));
         const float dxh = __half2float(__float2half_rn(pxh - oxh));
@@ -535,6 +593,8 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
     if (cell >= 0) {
       for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && cnt < (uint32_t)kSlots; ++q) {
         const int h = m.con_list[q];
+        const float4 bb = m.hull_bb[h];  // QueryReject: the shape bbs must overlap (hull bb already grown by wall_r)
+        if (px + k.agent_r < bb.x || bb.z < px - k.agent_r || py + k.agent_r < bb.y || bb.w < py - k.agent_r) continue;
         float d, nx, ny;
         hull_closest(m, h, px, py, d, nx, ny);
         if (d <= rsum_w) {  // CircleToPoly: d <= r_circle + r_poly
@@ -719,7 +779,7 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads) cat_world_kernel(const __grid_constant__ KParams k) {
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(const __grid_constant__ KParams k) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -787,83 +847,75 @@ __global__ void __launch_bounds__(kThreads) cat_world_kernel(const __grid_consta
     for (int i = lane; i < k.rec_words; i += 32) w.rec[i] = grec[i];
     __syncwarp();
 
-    if (k.mode == MODE_OBSERVE) {
-      observe_world(k, m, w, world);
-      write_observation(k, w, world);
+    bool do_step = k.mode == MODE_STEP, do_reset = k.mode == MODE_RESET;
+    bool captured = false, timeout = false;
+    if (do_step) {  // ---------------- base_env.py:354-383 ----------------
+      const float* pos = w.rec;
+      float* vel = w.rec + k.o_vel;
+      const int step_count = reci[k.o_sc] + 1;  // :372
       __syncwarp();
-      continue;
-    }
-    if (k.mode == MODE_RESET) {
-      reset_world(k, m, w, world);
-      observe_world(k, m, w, world);
-      write_observation(k, w, world);
-      __syncwarp();
-      for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
-      __syncwarp();
-      continue;
-    }
-
-    // ---------------- MODE_STEP: base_env.py:354-413 ----------------
-    const float* pos = w.rec;
-    float* vel = w.rec + k.o_vel;
-    const int step_count = reci[k.o_sc] + 1;  // :372
-    __syncwarp();
-    if (lane == 0) reci[k.o_sc] = step_count;
-
-    // _termination_criterion (:521-554): thief-major; LOS blocked by walls only; dist < radius (strict)
-    bool captured = false;
-    for (int t = k.nc; t < A && !captured; ++t)
-      for (int c = 0; c < k.nc && !captured; ++c) {
-        const float tx = pos[2 * t], ty = pos[2 * t + 1], cx = pos[2 * c], cy = pos[2 * c + 1];
-        const float dx = tx - cx, dy = ty - cy;
-        if (sqrtf(dx * dx + dy * dy) < k.term_r) {
-          bool blocked = false;
-          for (int h = lane; h < m.H; h += 32) blocked = blocked || los_hull_blocks(m, h, tx, ty, cx, cy, k.wall_r);
-          if (!__any_sync(0xFFFFFFFFu, blocked)) captured = true;
+      if (lane == 0) reci[k.o_sc] = step_count;
+      // _termination_criterion (:521-554): thief-major; LOS blocked by walls only; dist < radius (strict)
+      for (int t = k.nc; t < A && !captured; ++t)
+        for (int c = 0; c < k.nc && !captured; ++c) {
+          const float tx = pos[2 * t], ty = pos[2 * t + 1], cx = pos[2 * c], cy = pos[2 * c + 1];
+          const float dx = tx - cx, dy = ty - cy;
+          if (sqrtf(dx * dx + dy * dy) < k.term_r) {
+            const bool blocked = los_blocked(smem, lane, tx, ty, cx, cy, k.wall_r);
+            if (!__any_sync(0xFFFFFFFFu, blocked)) captured = true;
+          }
         }
+      timeout = !captured && step_count >= k.max_steps;
+      // Entity._perform_action (entity.py:126-134)
+      if (lane < A) {
+        int act;
+        const size_t ai = (size_t)world * A + lane;
+        if (k.actions_kind == 0) act = reinterpret_cast<const uint8_t*>(k.actions[0])[ai];
+        else if (k.actions_kind == 1) act = reinterpret_cast<const int32_t*>(k.actions[0])[ai];
+        else if (k.actions_kind == 2) act = (int)reinterpret_cast<const long long*>(k.actions[0])[ai];
+        else act = (int)reinterpret_cast<const long long*>(k.actions[lane])[world];
+        float fx = 0.f, fy = 0.f;
+        if (act == 0) fx = -k.impulse; else if (act == 1) fy = k.impulse;
+        else if (act == 2) fx = k.impulse; else if (act == 3) fy = -k.impulse;
+        float vx = vel[2 * lane] + fx * k.inv_mass, vy = vel[2 * lane + 1] + fy * k.inv_mass;
+        const float sp = sqrtf(vx * vx + vy * vy);
+        if (sp > k.max_speed) { vx = vx / sp * k.max_speed; vy = vy / sp * k.max_speed; }
+        vel[2 * lane] = vx; vel[2 * lane + 1] = vy;
       }
-    const bool timeout = !captured && step_count >= k.max_steps;
-
-    // Entity._perform_action (entity.py:126-134)
-    if (lane < A) {
-      int act;
-      const size_t ai = (size_t)world * A + lane;
-      if (k.actions_kind == 0) act = reinterpret_cast<const uint8_t*>(k.actions[0])[ai];
-      else if (k.actions_kind == 1) act = reinterpret_cast<const int32_t*>(k.actions[0])[ai];
-      else if (k.actions_kind == 2) act = (int)reinterpret_cast<const long long*>(k.actions[0])[ai];
-      else act = (int)reinterpret_cast<const long long*>(k.actions[lane])[world];
-      float fx = 0.f, fy = 0.f;
-      if (act == 0) fx = -k.impulse; else if (act == 1) fy = k.impulse;
-      else if (act == 2) fx = k.impulse; else if (act == 3) fy = -k.impulse;
-      float vx = vel[2 * lane] + fx * k.inv_mass, vy = vel[2 * lane + 1] + fy * k.inv_mass;
-      const float sp = sqrtf(vx * vx + vy * vy);
-      if (sp > k.max_speed) { vx = vx / sp * k.max_speed; vy = vy / sp * k.max_speed; }
-      vel[2 * lane] = vx; vel[2 * lane + 1] = vy;
-    }
-    __syncwarp();
-
-    observe_world(k, m, w, world);  // entity.py:143, pre-physics state
-    if (lane < A && k.reward)
-      k.reward[(size_t)world * A + lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
-    const bool done = captured || timeout;
-    const bool will_reset = done && k.auto_reset;
-    if (!will_reset) write_observation(k, w, world);
-    if (lane == 0) {
-      if (k.terminated) k.terminated[world] = done ? 1 : 0;  // entity.py:146
-      if (k.truncated) k.truncated[world] = timeout ? 1 : 0;   // base_env.py:397
-      if (k.winner) k.winner[world] = done ? (captured ? 0 : 1) : -1;
-    }
-    __syncwarp();
-
-    physics_world(k, m, w);  // base_env.py:392
-
-    if (will_reset) {  // emit the observation of the re-spawned state
-      reset_world(k, m, w, world);
-      observe_world(k, m, w, world);
-      write_observation(k, w, world);
       __syncwarp();
     }
-    for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
+
+    // One call site each for the sensor sweep, the output writer, the physics and the re-spawn:
+    //   STEP    : observe -> rewards/flags -> (write) -> physics -> [done: reset -> observe -> write]
+    //   RESET   : reset -> observe -> write
+    //   OBSERVE : observe -> write
+    for (;;) {
+      if (do_reset) { reset_world(k, m, w, world); do_reset = false; }
+      observe_world(k, m, w, world);  // entity.py:143 — pre-physics state
+      bool again = false;
+      if (do_step) {
+        if (lane < A && k.reward)
+          k.reward[(size_t)world * A + lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
+        const bool done = captured || timeout;
+        if (lane == 0) {
+          if (k.terminated) k.terminated[world] = done ? 1 : 0;  // entity.py:146
+          if (k.truncated) k.truncated[world] = timeout ? 1 : 0;   // base_env.py:397
+          if (k.winner) k.winner[world] = done ? (captured ? 0 : 1) : -1;
+        }
+        again = done && k.auto_reset;  // emit the observation of the re-spawned state instead
+      }
+      if (!again) write_observation(k, w, world);
+      __syncwarp();
+      if (do_step) {
+        physics_world(k, m, w);  // base_env.py:392
+        do_step = false;
+        if (again) { do_reset = true; continue; }
+      }
+      break;
+    }
+    if (k.mode != MODE_OBSERVE) {
+      for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
+    }
     __syncwarp();
   }
 }
@@ -1030,7 +1082,7 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   hd.off_raylist = take(map->ray_cell_off[ncell] * 2 + 2);
   hd.off_conoff = take((ncell + 1) * 2);
   hd.off_conlist = take(map->con_cell_off[ncell] * 2 + 2);
-  hd.off_dir = take(R * 8);
+  hd.off_dir = take(R * 16);
   hd.off_regoff = take((A + 1) * 4);
   hd.off_regions = take((nreg > 0 ? nreg : 1) * 16);
   hd.off_initpos = take(A * 8);
@@ -1064,7 +1116,11 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
     for (int i = 0; i < map->con_cell_off[ncell]; ++i) cl[i] = (uint16_t)map->con_cell_hulls[i];
     float* dir = reinterpret_cast<float*>(blob.data() + hd.off_dir);
     const double step = (2.0 * M_PI) / (double)R;  // entity.py:182 linspace(0, 2pi, R, endpoint=False)
-    for (int i = 0; i < R; ++i) { dir[2 * i] = (float)cos(i * step); dir[2 * i + 1] = (float)sin(i * step); }
+    for (int i = 0; i < R; ++i) {
+      const float ux = (float)cos(i * step), uy = (float)sin(i * step);
+      dir[4 * i] = ux; dir[4 * i + 1] = uy;
+      dir[4 * i + 2] = ux != 0.f ? 1.f / ux : 0.f; dir[4 * i + 3] = uy != 0.f ? 1.f / uy : 0.f;
+    }
     int32_t* rg = reinterpret_cast<int32_t*>(blob.data() + hd.off_regoff);
     for (int a = 0; a <= A; ++a) rg[a] = map->region_off[a];
     float* rr = reinterpret_cast<float*>(blob.data() + hd.off_regions);

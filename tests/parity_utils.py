@@ -144,3 +144,67 @@ def flat_state_numpy(obs_dist, obs_type, shared_dist, shared_type, team_pos, n_c
                  obs_dist[:, a].astype(np.float32), obs_type[:, a].astype(np.float32),
                  team_pos[:, a0:a1].astype(np.float32).reshape(N, -1)]
     return np.concatenate(cols, axis=1)
+
+
+# ------------------------------------------------------------------ analytic golden vectors
+GOLDEN_DIR = ROOT / "tests" / "golden"
+
+
+def load_analytic():
+    import json
+    from as_cops_and_thieves_b200.maps import Map
+    data = json.load(open(GOLDEN_DIR / "analytic_vectors.json"))
+    m = Map(GOLDEN_DIR / "analytic_map.json")
+    return m, data["vectors"]
+
+
+def vector_params(vec) -> dict:
+    p = dict(auto_reset=int(vec.get("auto_reset", 0)), max_step_count=int(vec.get("max_step_count", 400)))
+    if "capture_radius_override" in vec:
+        p["termination_radius"] = float(vec["capture_radius_override"])
+    return p
+
+
+def eval_vector_oracle(cmap, vec) -> dict:
+    """Run one analytic vector through the CPU oracle."""
+    orc = Oracle(cmap, **vector_params(vec))
+    st = orc.new_state(1)
+    st.pos[0] = np.asarray(vec["pos"], np.float64)
+    st.tc[0] = st.pos[0]
+    if "vel" in vec:
+        st.vel[0] = np.asarray(vec["vel"], np.float64)
+    st.step_count[0] = int(vec.get("step_count", 0))
+    if vec["kind"] == "ray":
+        out = orc.observe(st)
+    else:
+        out = orc.step(st, np.asarray([vec["actions"]], np.int32))
+    return dict(obs_type=out.obs_type[0], obs_dist=out.obs_dist[0], hit_point=out.hit_point[0],
+                reward=out.reward[0], terminated=int(out.terminated[0]), truncated=int(out.truncated[0]),
+                winner=int(out.winner[0]), pos=st.pos[0], vel=st.vel[0], vbias=st.vbias[0])
+
+
+def check_vector(vec, res, pos_tol=1e-6, point_tol=1e-6) -> None:
+    """Assert a backend's result against the analytic expectation (tolerances: fp64 oracle by
+    default; the CUDA tests pass the fp32 tolerances)."""
+    exp = vec["expect"]
+    name = vec["name"]
+    if vec["kind"] == "ray":
+        a, r = vec["agent"], vec["ray"]
+        assert int(res["obs_type"][a, r]) == exp["type"], name
+        want16 = np.float16(exp["distance"])
+        got16 = np.float16(res["obs_dist"][a, r])
+        # the f16 chain quantises the hit point and the origin first: allow one f16 step of the analytic value
+        step16 = float(np.spacing(np.float16(max(abs(exp["distance"]), 1.0))))
+        assert abs(float(got16) - float(want16)) <= 2 * step16, (name, got16, want16)
+        if "point" in exp:
+            np.testing.assert_allclose(res["hit_point"][a, r], exp["point"], atol=point_tol, err_msg=name)
+        return
+    for key in ("terminated", "truncated", "winner"):
+        if key in exp:
+            assert res[key] == exp[key], (name, key, res[key], exp[key])
+    if "reward" in exp:
+        np.testing.assert_allclose(res["reward"], exp["reward"], atol=REWARD_ATOL, err_msg=name)
+    agents = vec.get("check_agents", list(range(len(vec["pos"]))))
+    for key in ("pos", "vel", "vbias"):
+        if key in exp:
+            np.testing.assert_allclose(np.asarray(res[key])[agents], exp[key], atol=pos_tol, err_msg=f"{name}:{key}")

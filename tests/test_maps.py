@@ -1,0 +1,143 @@
+"""Map loader / compiler (host logic, CPU)."""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from as_cops_and_thieves_b200.maps import (Map, compile_map, convex_hull_ccw, free_space_regions, load_named_map,
+                                           builtin_map_path)
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+# SURVEY.md Appendix B (computed from the reference's maps_templates with a monotone-chain hull)
+EXPECTED = {"squarinth": (4, 16, 4), "lbirinth": (6, 24, 4), "grandbyrinth": (4, 16, 4),
+            "labyrinth": (30, 119, 4), "agh-map": (105, 496, 10)}
+
+
+@pytest.mark.parametrize("name", list(EXPECTED))
+def test_hull_and_edge_counts(name):
+    cm = compile_map(load_named_map(name))
+    H, E, mx = EXPECTED[name]
+    assert (cm.n_hulls, cm.n_edges, int(np.diff(cm.hull_off).max())) == (H, E, mx)
+    assert cm.n_cops == 2 and cm.n_thieves == 1
+    assert cm.agent_ids == ["cop_0", "cop_1", "thief_0"]
+
+
+@pytest.mark.parametrize("name", list(EXPECTED))
+def test_hulls_are_convex_ccw_with_outward_unit_normals(name):
+    cm = compile_map(load_named_map(name))
+    for h in range(cm.n_hulls):
+        o, e = cm.hull_off[h], cm.hull_off[h + 1]
+        v = cm.vert[o:e]
+        n = len(v)
+        for i in range(n):
+            a, b, c = v[i - 1], v[i], v[(i + 1) % n]
+            cross = (b[0] - a[0]) * (c[1] - b[1]) - (b[1] - a[1]) * (c[0] - b[0])
+            assert cross > 0, "strictly convex, counter-clockwise, no collinear points"
+        centroid = v.mean(axis=0)
+        for i in range(n):
+            nx, ny = cm.normal[o + i]
+            assert abs(math.hypot(nx, ny) - 1) < 1e-12
+            assert (centroid - v[i]) @ cm.normal[o + i] < 0, "normal points away from the interior"
+            edge = v[i] - v[i - 1]
+            assert abs(edge @ cm.normal[o + i]) < 1e-9
+            assert abs(np.hypot(*edge) - cm.edge_len[o + i]) < 1e-12
+
+
+def test_rect_rule_defaults_and_negative_extents(tmp_path):
+    # map.py:37-52: w/h default to 1; negative extents allowed; ring is closed
+    data = {"window": {"w_px": 100, "h_px": 80}, "canvas": {"w": 10, "h": 8},
+            "objects": {"blocks": [{"x": 3, "y": 4}, {"type": "rect", "x": 10, "y": 10, "w": -4, "h": 2},
+                                   {"type": "poly", "vs": [{"x": 0, "y": 0}, {"x": 2, "y": 0}, {"x": 1, "y": 1},
+                                                           {"x": 2, "y": 2}, {"x": 0, "y": 2}]}]},
+            "agents": [{"type": "cop", "x": 1, "y": 1}, {"type": "thief", "x": 2, "y": 2}]}
+    p = tmp_path / "m.json"
+    p.write_text(json.dumps(data))
+    m = Map(p)
+    assert m.window_dimensions == (100, 80) and m.canvas_dimensions == (10, 8)
+    assert m.blocks[0] == [(3, 4), (4, 4), (4, 5), (3, 5), (3, 4)]
+    assert m.blocks[1][2] == (6, 12)
+    cm = compile_map(m)
+    assert list(np.diff(cm.hull_off)) == [4, 4, 4]          # the concave poly is convexified to its hull
+    assert cm.hull_bb[1].tolist() == [6, 10, 10, 12]
+    assert m.cops_positions == [(1, 1)] and m.thieves_positions == [(2, 2)]
+    assert m.agent_spawn_regions == {}
+
+
+def test_reference_schema_fixture_and_spawn_region_forms():
+    m = Map(GOLDEN / "analytic_map.json")
+    # agent ids count per type in file order (map.py:76-108); env order is cops then thieves
+    assert set(m.agent_spawn_regions) == {"cop_0", "thief_0"}
+    assert len(m.agent_spawn_regions["cop_0"]) == 1          # singular spawn_region -> list of one
+    assert len(m.agent_spawn_regions["thief_0"]) == 2        # plural spawn_regions
+    assert m.cops_positions == [(900, 700), (950, 700)] and m.thieves_positions == [(1000, 700)]
+    cm = compile_map(m)
+    assert cm.region_off.tolist() == [0, 1, 1, 3]            # cop_0, cop_1 (none), thief_0
+    assert list(np.diff(cm.hull_off)) == [4, 4, 4]           # collinear vertex (605,610) dropped
+
+
+def test_labyrinth_without_agents_raises_like_the_reference():
+    with pytest.raises(KeyError):
+        Map(builtin_map_path("labyrinth"))                   # map.py:75 KeyError: 'agents'
+    m = load_named_map("labyrinth")                          # scaled + injected agents
+    assert m.cops_count == 2 and m.thieves_count == 1
+    xs = [v[0] for ring in m.blocks for v in ring]
+    assert max(xs) > 1000
+
+
+def test_unknown_block_type_and_missing_xy():
+    from as_cops_and_thieves_b200.maps import _parse_block
+    with pytest.raises(ValueError):
+        _parse_block({"type": "circle"})
+    with pytest.raises(ValueError):
+        _parse_block({"type": "rect", "x": 1})
+    with pytest.raises(ValueError):
+        _parse_block({"type": "poly"})
+
+
+def test_convex_hull_drops_duplicates_and_collinear():
+    h = convex_hull_ccw([(0, 0), (1, 0), (2, 0), (2, 2), (0, 2), (0, 0), (1, 1)])
+    assert h.tolist() == [[0, 0], [2, 0], [2, 2], [0, 2]]
+
+
+@pytest.mark.parametrize("name", ["squarinth", "labyrinth", "agh-map"])
+def test_grid_lists_are_conservative(name):
+    """Every hull within reach of a point must be listed in the point's cell (both list kinds)."""
+    from oracle.cat_oracle import Oracle
+    cm = compile_map(load_named_map(name))
+    orc = Oracle(cm)
+    rng = np.random.default_rng(0)
+    lo = np.array([cm.grid_x0, cm.grid_y0])
+    hi = lo + np.array([cm.nx, cm.ny]) * cm.cell
+    pts = rng.uniform(lo, hi, size=(1500, 2))
+    for p in pts:
+        c = int((p[1] - cm.grid_y0) // cm.cell) * cm.nx + int((p[0] - cm.grid_x0) // cm.cell)
+        ray = set(cm.ray_cell_hulls[cm.ray_cell_off[c]:cm.ray_cell_off[c + 1]].tolist())
+        con = set(cm.con_cell_hulls[cm.con_cell_off[c]:cm.con_cell_off[c + 1]].tolist())
+        for h in range(cm.n_hulls):
+            d = orc.hull_distance(h, p)
+            if d <= 2.0:
+                assert h in ray
+            if d <= 6.0:
+                assert h in con
+    # lists are sorted ascending (fixes the arbiter order)
+    for off, lst in ((cm.ray_cell_off, cm.ray_cell_hulls), (cm.con_cell_off, cm.con_cell_hulls)):
+        for c in range(cm.nx * cm.ny):
+            seg = lst[off[c]:off[c + 1]]
+            assert np.all(np.diff(seg) > 0)
+
+
+def test_points_outside_grid_are_far_from_every_hull():
+    cm = compile_map(load_named_map("agh-map"))
+    assert cm.grid_x0 <= cm.hull_bb[:, 0].min() - 6.0 and cm.grid_y0 <= cm.hull_bb[:, 1].min() - 6.0
+    assert cm.grid_x0 + cm.nx * cm.cell >= cm.hull_bb[:, 2].max() + 6.0
+    assert cm.grid_y0 + cm.ny * cm.cell >= cm.hull_bb[:, 3].max() + 6.0
+
+
+def test_free_space_regions_override():
+    m = load_named_map("agh-map")
+    cm = compile_map(m, spawn_override=free_space_regions(m))
+    assert cm.region_off.tolist() == [0, 1, 2, 3]
+    assert np.all(cm.regions[:, 2] > 500)
