@@ -32,7 +32,6 @@ class CatMapDesc(C.Structure):
         ("init_pos", C.c_void_p), ("region_off", C.c_void_p), ("regions", C.c_void_p),
         ("grid_x0", C.c_double), ("grid_y0", C.c_double), ("cell", C.c_double),
         ("nx", C.c_int32), ("ny", C.c_int32),
-        ("ray_cell_off", C.c_void_p), ("ray_cell_hulls", C.c_void_p),
         ("con_cell_off", C.c_void_p), ("con_cell_hulls", C.c_void_p),
     ]
 
@@ -91,7 +90,9 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.build()
+    import os
+    override = os.environ.get("CAT_B200_LIB")  # developer knob: load a tuning variant of the extension
+    path = Path(override) if override else _build.build()
     L = C.CDLL(str(path))
     for name in EXPORTS:
         if not hasattr(L, name):

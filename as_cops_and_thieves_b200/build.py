@@ -29,7 +29,7 @@ def nvcc_path() -> str:
 
 def nvcc_cmd(out: Path = LIB, extra=()) -> list:
     cmd = [
-        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-prec-div=false", "-prec-sqrt=false",
         "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-o", str(out), str(SRC),
     ]
     if Path("/usr/bin/g++").exists():

@@ -32,9 +32,15 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef CAT_WARPS_PER_CTA
+#define CAT_WARPS_PER_CTA 8
+#endif
+#ifndef CAT_MIN_CTAS_PER_SM
+#define CAT_MIN_CTAS_PER_SM 4
+#endif
+constexpr int kWarpsPerCta = CAT_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kMinCtasPerSm = 3;
+constexpr int kMinCtasPerSm = CAT_MIN_CTAS_PER_SM;
 constexpr int kSlots = CAT_WALL_SLOTS;
 constexpr int kNear = 4;            // hulls an origin can be "inside" (alpha = 0 rule) per agent
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
@@ -60,7 +66,7 @@ struct BlobHeader {
   int32_t n_hulls, n_edges, nx, ny;
   float gx0, gy0, cell, inv_cell;
   int32_t off_edge, off_len, off_hbb, off_heo;
-  int32_t off_rayoff, off_raylist, off_conoff, off_conlist;
+  int32_t off_nextn, off_edgehull, off_conoff, off_conlist;
   int32_t off_dir, off_regoff, off_regions, off_initpos;
   int32_t pad[4];
 };
@@ -71,8 +77,8 @@ struct MapView {
   const float* edge_len;
   const float4* hull_bb;   // l,b,r,t grown by the wall radius (the shape's bb)
   const uint32_t* hull_eo; // edge offset | count << 16
-  const uint16_t* ray_off;
-  const uint16_t* ray_list;
+  const float2* next_n;      // outward normal of the NEXT edge of the same hull (shares vertex v_i)
+  const uint16_t* edge_hull; // hull of each edge
   const uint16_t* con_off;
   const uint16_t* con_list;
   const float4* dir;       // per ray: ux, uy, 1/ux, 1/uy (unit direction and its reciprocals)
@@ -90,12 +96,12 @@ struct KParams {
   int rec_words;
   int n_worlds;
   long long gid0;
-  int A, nc, R, P, nrays, nrays_pad, maxc;
+  int A, nc, R, P, nrays, nrays_pad, maxc, n_edges;
   int mode;
   // record offsets (words)
-  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep;
+  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags;
   // per-warp scratch offsets (bytes) and size
-  int s_rdist, s_rtype, s_min, s_near, s_nearcnt, s_con, s_ccount, s_order, scratch_bytes;
+  int s_rdist, s_rtype, s_min, s_near, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, scratch_bytes;
   int state_dim;
   // constants
   float dt, inv_dt, impulse, inv_mass, agent_r, max_speed, term_r, ray_len, ray_r, wall_r;
@@ -131,8 +137,8 @@ __device__ __forceinline__ MapView make_view(const unsigned char* blob) {
   m.edge_len = reinterpret_cast<const float*>(blob + h->off_len);
   m.hull_bb = reinterpret_cast<const float4*>(blob + h->off_hbb);
   m.hull_eo = reinterpret_cast<const uint32_t*>(blob + h->off_heo);
-  m.ray_off = reinterpret_cast<const uint16_t*>(blob + h->off_rayoff);
-  m.ray_list = reinterpret_cast<const uint16_t*>(blob + h->off_raylist);
+  m.next_n = reinterpret_cast<const float2*>(blob + h->off_nextn);
+  m.edge_hull = reinterpret_cast<const uint16_t*>(blob + h->off_edgehull);
   m.con_off = reinterpret_cast<const uint16_t*>(blob + h->off_conoff);
   m.con_list = reinterpret_cast<const uint16_t*>(blob + h->off_conlist);
   m.dir = reinterpret_cast<const float4*>(blob + h->off_dir);
@@ -157,6 +163,7 @@ __device__ __noinline__ float3 hull_closest_impl(const float4* __restrict__ edge
   float bestd2 = CUDART_INF_F, bdx = 0.f, bdy = 0.f, benx = 0.f, beny = 0.f, bpd = 0.f;
   float4 pv = edge[o + n - 1];
   float v0x = pv.x, v0y = pv.y;
+#pragma unroll 1
   for (int i = 0; i < n; ++i) {
     const float4 e = edge[o + i];
     const float pd = (px - e.x) * e.z + (py - e.y) * e.w;
@@ -213,11 +220,27 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   return r;
 }
 
-struct Hit {
-  float s;    // distance along the ray of the fat-ray centre at first touch (alpha * L)
-  int id;     // -1 none, < H hull, H + j agent j
-  int feat;   // walls: edge index * 2 + (1 = bevelled vertex, 0 = plane); the normal is rebuilt once at the end
-};
+// Depth-buffer key of a ray: (float bits of s) << 32 | feature.  Walls: edge * 2 + (1 = bevelled vertex);
+// agents: kAgentTag + j — larger than any wall feature, so at equal s the static shape wins, like
+// cpSpaceSegmentQueryFirst (static index first, dynamic only if strictly closer).  s = distance along
+// the ray of the fat-ray centre at first touch (alpha * L).
+constexpr uint32_t kAgentTag = 0x40000000u;
+constexpr uint32_t kNoFeature = 0xFFFFFFFFu;
+__device__ __forceinline__ unsigned long long make_key(float s, uint32_t feat) {
+  return ((unsigned long long)__float_as_uint(s) << 32) | feat;
+}
+
+// atan2 to ~1e-4 rad (odd minimax polynomial on [0,1] + octant folding); callers pad their angular
+// spans by 2e-3 rad, so this only ever adds a spare (edge, ray) test, never drops one.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float a = __fdividef(fminf(ax, ay), fmaxf(fmaxf(ax, ay), 1e-30f));
+  const float q = a * a;
+  float r = fmaf(fmaf(fmaf(-0.0464964749f, q, 0.15931422f), q, -0.327622764f), q * a, a);
+  if (ay > ax) r = 1.57079637f - r;
+  if (x < 0.f) r = 3.14159274f - r;
+  return copysignf(r, y);
+}
 
 struct Ray {
   float ox, oy, ux, uy, L;
@@ -225,45 +248,48 @@ struct Ray {
   float idx, idy;   // 1 / (L * u)
 };
 
-// One edge of cpPolyShapeSegmentQuery against the ray o + s*u, s in [0, L): plane i offset by
-// rsum = wall_r + ray_r (accepted inside the edge's tangential extent) and the bevelled vertex v_i
-// as a circle of radius rsum (CircleSegmentQuery, perpendicular-offset form of the discriminant).
-__device__ __forceinline__ void ray_edge(const MapView& m, int ei, int h, const Ray& r, float rsum, float rs2,
-                                         Hit& best) {
-  const float4 e = m.edge[ei];
+// One edge of cpPolyShapeSegmentQuery against the ray o + s*u: plane i offset by rsum = wall_r + ray_r
+// (accepted inside the edge's tangential extent) and the bevelled vertex v_i as a circle of radius rsum
+// (CircleSegmentQuery, perpendicular-offset form of the discriminant).  Returns the smaller s (INF if
+// neither is hit; range / nearest checks are the caller's) and which of the two it was.
+__device__ __forceinline__ float ray_edge(const float4 e, float len, const Ray& r, float rsum, float rs2, int& kind) {
   const float rx = r.ox - e.x, ry = r.oy - e.y;
   const float d = fmaf(rx, e.z, fmaf(ry, e.w, -rsum));   // a.n - v0.n - rsum
   const float un = fmaf(r.ux, e.z, r.uy * e.w);          // (b.n - a.n) / L
+  float s = CUDART_INF_F;
+  kind = 0;
   if (d >= 0.f && un < 0.f) {
-    const float s = __fdividef(d, -un);
-    const float c = fmaf(e.z, fmaf(s, r.uy, ry), -e.w * fmaf(s, r.ux, rx));  // cross(n, P - v_i) in [-len, 0]
-    if (s < r.L && s <= best.s && c <= 0.f && c >= -m.edge_len[ei]) { best.s = s; best.id = h; best.feat = ei * 2; }
+    const float sp = __fdividef(d, -un);
+    const float c = fmaf(e.z, fmaf(sp, r.uy, ry), -e.w * fmaf(sp, r.ux, rx));  // cross(n, P - v_i) in [-len, 0]
+    if (c <= 0.f && c >= -len) s = sp;
   }
   const float cp = fmaf(rx, r.uy, -ry * r.ux);
   const float disc = fmaf(-cp, cp, rs2);
   if (disc >= 0.f) {
-    const float s = -fmaf(rx, r.ux, ry * r.uy) - fast_sqrt(disc);
-    if (s >= 0.f && s < r.L && s <= best.s) { best.s = s; best.id = h; best.feat = ei * 2 + 1; }
+    const float sc = -fmaf(rx, r.ux, ry * r.uy) - fast_sqrt(disc);
+    if (sc >= 0.f && sc < s) { s = sc; kind = 1; }
   }
+  return s;
 }
 
 // Surface normal of a wall hit (plane: the edge normal; bevel: from the vertex to the ray centre).
-__device__ __forceinline__ float2 wall_hit_normal(const MapView& m, const Hit& hit, const Ray& r, float rsum) {
-  const float4 e = m.edge[hit.feat >> 1];
-  if ((hit.feat & 1) == 0) return make_float2(e.z, e.w);
+__device__ __forceinline__ float2 wall_hit_normal(const MapView& m, uint32_t feat, float s, const Ray& r, float rsum) {
+  const float4 e = m.edge[feat >> 1];
+  if ((feat & 1u) == 0) return make_float2(e.z, e.w);
   const float inv = 1.f / rsum;
-  return make_float2((r.ox - e.x + hit.s * r.ux) * inv, (r.oy - e.y + hit.s * r.uy) * inv);
+  return make_float2((r.ox - e.x + s * r.ux) * inv, (r.oy - e.y + s * r.uy) * inv);
 }
 
-// CircleSegmentQuery against an agent circle (cached centre c, radius r1) with ray radius r2.
-__device__ __forceinline__ void ray_circle(float cx, float cy, float rs, const Ray& r, int id, Hit& best) {
+// CircleSegmentQuery against an agent circle (cached centre c, reach rs = r_agent + r_ray): s or INF.
+__device__ __forceinline__ float ray_circle(float cx, float cy, float rs, const Ray& r) {
   const float rx = r.ox - cx, ry = r.oy - cy;
   const float cp = fmaf(rx, r.uy, -ry * r.ux);
   const float disc = fmaf(-cp, cp, rs * rs);
   if (disc >= 0.f) {
     const float s = -fmaf(rx, r.ux, ry * r.uy) - fast_sqrt(disc);
-    if (s >= 0.f && s < r.L && s < best.s) { best.s = s; best.id = id; }
+    if (s >= 0.f) return s;
   }
+  return CUDART_INF_F;
 }
 
 __device__ __forceinline__ Ray make_ray(float ax, float ay, float dx, float dy) {
@@ -286,15 +312,18 @@ __device__ __noinline__ bool los_blocked(const unsigned char* blob, int h0, floa
   const MapView m = make_view(blob);
   const Ray r = make_ray(ax, ay, bx - ax, by - ay);
   bool blocked = false;
+#pragma unroll 1
   for (int h = h0; h < m.H && !blocked; h += 32) {
     if (!thin_bb_hit(m.hull_bb[h], ax, ay, r.zx, r.zy, r.idx, r.idy)) continue;
     const float3 c = hull_closest_impl(m.edge, m.hull_eo[h], ax, ay);
     if (c.x - wall_r <= 0.f) { blocked = true; break; }  // start point inside the rounded hull
     if (!(r.L > 0.f)) continue;
-    Hit best; best.s = r.L; best.id = -1; best.feat = 0;
     const uint32_t eo = m.hull_eo[h];
-    for (int ei = eo & 0xFFFF, ee = (eo & 0xFFFF) + (eo >> 16); ei < ee; ++ei) ray_edge(m, ei, h, r, wall_r, wall_r * wall_r, best);
-    blocked = best.id >= 0;
+#pragma unroll 1
+    for (int ei = eo & 0xFFFF, ee = (eo & 0xFFFF) + (eo >> 16); ei < ee && !blocked; ++ei) {
+      int kind;
+      blocked = ray_edge(m.edge[ei], m.edge_len[ei], r, wall_r, wall_r * wall_r, kind) < r.L;  // alpha < 1
+    }
   }
   return blocked;
 }
@@ -316,34 +345,124 @@ struct Warp {
   float* con;       // contact entries, 8 words each
   uint32_t* ccount; // wall contacts per agent
   uint8_t* order;   // compact solver order
+  unsigned long long* best;  // per ray: (float bits of s) << 32 | feature id  — the 1-D depth buffer
+  uint16_t* cand;   // candidate edge ids awaiting rasterisation
+  const unsigned char* blob;  // the map blob in shared memory
   int lane;
 };
 
+// Rasterise up to 32 candidate edges (cand[0..n)) of one agent into its per-ray depth buffer `best`.
+// Lane l owns candidate l and computes the span of ray indices whose thin line can come within rsum of
+// the edge (conservative: angle of the offset segment's far end and of the bevel circle, padded); the
+// (edge, ray) pairs of all 32 spans are then flattened with a warp scan so that every lane tests one
+// pair per iteration regardless of how uneven the spans are.  Not inlined: one compact copy keeps the
+// kernel's instruction footprint inside the instruction cache.
+__device__ __noinline__ void raster_batch(const unsigned char* blob, unsigned long long* best, const uint16_t* cand,
+                                          int n, float ox, float oy, float rsum, float L, int R) {
+  const MapView m = make_view(blob);
+  const int lane = threadIdx.x & 31;
+  const float rs2 = rsum * rsum, inv_L = 1.f / L;
+  int e = 0, i0 = 0, cnt = 0;
+  if (lane < n) {
+    e = cand[lane];
+    const float4 ed = m.edge[e];
+    const float bx = ed.x - ox, by = ed.y - oy;           // B - o (B = v_i, the vertex ending the edge)
+    const float nb2 = bx * bx + by * by;
+    if (nb2 <= rs2) { cnt = R; }                           // origin inside the bevel circle: every direction
+    else {
+      const float thB = fast_atan2(by, bx);
+      const float x = fminf(rsum * rsqrtf(nb2), 1.f);
+      const float wv = x * fmaf(0.5708f, x * x, 1.f);     // >= asin(x) on [0,1]: half-width of the bevel circle
+      float lo = -wv, hi = wv;
+      const float pd = -(bx * ed.z + by * ed.w);          // (o - B).n
+      if (pd - rsum >= 0.f) {
+        // offset segment A'B' (B' lies on the bevel circle, already covered): far end A' = B - len*t + n*rsum
+        const float len = m.edge_len[e];
+        const float apx = bx + ed.z * rsum + len * ed.w, apy = by + ed.w * rsum - len * ed.z;   // t = (-ny, nx)
+        float dA = fast_atan2(apy, apx) - thB;
+        dA = dA > CUDART_PI_F ? dA - 2.f * CUDART_PI_F : (dA < -CUDART_PI_F ? dA + 2.f * CUDART_PI_F : dA);
+        lo = fminf(lo, dA); hi = fmaxf(hi, dA);
+      }
+      const float pad = 2e-3f;
+      const float inv_dth = (float)R * (0.5f / CUDART_PI_F);
+      const int ilo = (int)ceilf((thB + lo - pad) * inv_dth), ihi = (int)floorf((thB + hi + pad) * inv_dth);
+      cnt = min(max(ihi - ilo + 1, 0), R);
+      i0 = ilo;                                            // |ilo| < 2R
+      if (i0 < 0) i0 += R;
+      if (i0 < 0) i0 += R;
+      if (i0 >= R) i0 -= R;
+    }
+  }
+  int scan = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, scan, d); if (lane >= d) scan += t; }
+  const int total = __shfl_sync(0xFFFFFFFFu, scan, 31);
+  const int excl = scan - cnt;
+#pragma unroll 1
+  for (int p0 = 0; p0 < total; p0 += 32) {
+    const int p = p0 + lane;
+    int l = 0;   // owner = first lane whose inclusive scan exceeds p
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xFFFFFFFFu, scan, l + step - 1);
+      if (v <= p) l += step;
+    }
+    l = min(l, 31);
+    const int el = __shfl_sync(0xFFFFFFFFu, e, l), i0l = __shfl_sync(0xFFFFFFFFu, i0, l);
+    const int exl = __shfl_sync(0xFFFFFFFFu, excl, l);
+    if (p < total) {
+      int i = i0l + (p - exl);
+      if (i >= R) i -= R;
+      const float4 dv = m.dir[i];
+      Ray r;
+      r.ox = ox; r.oy = oy; r.ux = dv.x; r.uy = dv.y; r.L = L;
+      r.zx = dv.x == 0.f; r.zy = dv.y == 0.f; r.idx = dv.z * inv_L; r.idy = dv.w * inv_L;
+      int kind;
+      const float sHit = ray_edge(m.edge[el], m.edge_len[el], r, rsum, rs2, kind);
+      if (sHit < L) {
+        unsigned long long* slot = &best[i];
+        const unsigned long long key = make_key(sHit, (uint32_t)(el * 2 + kind));
+        // cpBBTree leaf test: a hull is only ever visited if the THIN ray enters its bb (rarely fails, so
+        // it is evaluated only for hits that would win the depth test)
+        if (key < *slot && thin_bb_hit(m.hull_bb[m.edge_hull[el]], ox, oy, r.zx, r.zy, r.idx, r.idy)) atomicMin(slot, key);
+      }
+    }
+  }
+}
+
 // Sensor sweep of every agent of one world (entity.py:159-220) into shared memory.
 //
-// One lane per ray.  The wall traversal is a single warp-converged loop: every iteration each lane
-// that still has work first *fetches* (walks grid cells / cell lists until it holds a hull whose bb
-// the thin ray enters — short, cheap, divergent) and then all lanes together test ONE edge of
-// their current hull (the expensive part, converged).  Lanes therefore pay for the longest edge
-// sequence in the warp, not for the sum of everyone's nested loops.
+// 90 rays from one origin are a 1-D depth buffer, so the walls are RASTERISED into it instead of each
+// ray searching the map: per agent, (1) lanes = rays: seed the buffer with the other agents' circles and
+// the alpha = 0 rules; (2) lanes = edges: keep edges that face the origin and lie within range, then
+// expand them into (edge, ray) pairs spread evenly over the lanes (raster_batch) and resolve the nearest
+// hit per ray with a 64-bit shared-memory atomicMin; (3) lanes = rays: hit point, float16 chain, type.
+// Work is proportional to what is actually in view (~2 edge tests per ray on agh-map), lanes stay
+// converged, and there is no per-ray traversal.
 __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
-  const int A = k.A, R = k.R, lane = w.lane;
+  const int A = k.A, R = k.R, lane = w.lane, E = k.n_edges;
   const float* pos = w.rec;
   const float* tc = w.rec + k.o_tc;
+  const uint32_t flags = reinterpret_cast<const uint32_t*>(w.rec)[k.o_flags];
   const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len, rs2 = rsum * rsum;
-  // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates
+  const float reach = k.agent_r + k.ray_r, reach2 = reach * reach, inv_reach = 1.f / reach;
+  const float range2 = (L + rsum) * (L + rsum);
+  // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates.
+  // Only agents flagged by the last physics step / re-spawn (a wall within contact reach) can have any.
   if (lane < A) {
-    const float px = pos[2 * lane], py = pos[2 * lane + 1];
     uint32_t cnt = 0;
-    const int cell = grid_cell(m, px, py);
-    if (cell >= 0) {
-      for (int q = m.ray_off[cell]; q < m.ray_off[cell + 1]; ++q) {
-        const int h = m.ray_list[q];
-        const float4 bb = m.hull_bb[h];  // already grown by wall_r: cheap reject before the exact distance
-        if (px < bb.x - k.ray_r || px > bb.z + k.ray_r || py < bb.y - k.ray_r || py > bb.w + k.ray_r) continue;
-        float d, nx, ny;
-        hull_closest(m, h, px, py, d, nx, ny);
-        if (d - k.wall_r <= k.ray_r && cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
+    if ((flags >> lane) & 1u) {
+      const float px = pos[2 * lane], py = pos[2 * lane + 1];
+      const int cell = grid_cell(m, px, py);
+      if (cell >= 0) {
+        for (int q = m.con_off[cell]; q < m.con_off[cell + 1]; ++q) {
+          const int h = m.con_list[q];
+          const float4 bb = m.hull_bb[h];  // already grown by wall_r: cheap reject before the exact distance
+          if (px < bb.x - k.ray_r || px > bb.z + k.ray_r || py < bb.y - k.ray_r || py > bb.w + k.ray_r) continue;
+          float d, nx, ny;
+          hull_closest(m, h, px, py, d, nx, ny);
+          if (d - k.wall_r <= k.ray_r && cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
+        }
       }
     }
     w.nearcnt[lane] = cnt;
@@ -351,134 +470,180 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
   }
   __syncwarp();
 
-  for (int r0 = 0; r0 < k.nrays_pad; r0 += 32) {
-    const int r = r0 + lane;
-    const bool valid = r < k.nrays;
-    const int a = valid ? r / R : 0, i = valid ? r - a * R : 0;
-    const float4 dv = m.dir[i];
-    Ray ry_;
-    ry_.ox = pos[2 * a]; ry_.oy = pos[2 * a + 1]; ry_.ux = dv.x; ry_.uy = dv.y; ry_.L = L;
-    ry_.zx = dv.x == 0.f; ry_.zy = dv.y == 0.f;
-    ry_.idx = dv.z * inv_L; ry_.idy = dv.w * inv_L;
-    const float ox = ry_.ox, oy = ry_.oy;
-    Hit best; best.s = L; best.id = -1; best.feat = 0;
-    bool zero_hit = false;   // alpha = 0: point stays at the ray end (cpShapeSegmentQuery)
-    // dynamic shapes: the other agents' cached centres
-    const float reach = k.agent_r + k.ray_r;
-    for (int j = 0; j < A; ++j) {
-      if (j == a) continue;
-      const float cx = tc[2 * j], cy = tc[2 * j + 1];
-      const float ddx = ox - cx, ddy = oy - cy;
-      if (ddx * ddx + ddy * ddy <= reach * reach) {  // |a - c| - r <= ray_r
-        if (!zero_hit) { zero_hit = true; best.s = 0.f; best.id = m.H + j; }
-      } else if (!zero_hit) {
-        ray_circle(cx, cy, reach, ry_, m.H + j, best);
-      }
-    }
-    // static shapes with the origin inside their reach: visited only if the thin ray enters the bb
+  const int nsub = (R + 31) >> 5;
+#pragma unroll 1
+  for (int a = 0; a < A; ++a) {
+    // ---- warp-uniform, per agent
+    const float ox = pos[2 * a], oy = pos[2 * a + 1];
     const uint32_t ncnt = w.nearcnt[a];
-    bool wall_zero = false;
-    for (uint32_t q = 0; q < ncnt; ++q) {
-      const int h = w.near[a * kNear + q];
-      if (!wall_zero && thin_bb_hit(m.hull_bb[h], ox, oy, ry_.zx, ry_.zy, ry_.idx, ry_.idy)) {
-        wall_zero = true; zero_hit = true; best.s = 0.f; best.id = h;  // static index is queried first
-      }
+    int zero_agent = -1;   // first other agent whose circle is within ray_r of the origin (alpha = 0)
+    for (int j = A - 1; j >= 0; --j) {
+      if (j == a) continue;
+      const float ddx = ox - tc[2 * j], ddy = oy - tc[2 * j + 1];
+      if (ddx * ddx + ddy * ddy <= reach2) zero_agent = j;
     }
 
-    // ---- uniform-grid walk set-up (clip the ray to the grid, find the first cell)
-    bool active = valid && !zero_hit;
-    int ix = 0, iy = 0, stepx = 1, stepy = 1, q = 0, qe = 0, ei = 0, ee = 0, hcur = -1, last1 = -1, last2 = -1;
-    float tmx = CUDART_INF_F, tmy = CUDART_INF_F, tdx = CUDART_INF_F, tdy = CUDART_INF_F;
-    if (active) {
-      const float gx = (ox - m.gx0) * m.inv_cell, gy = (oy - m.gy0) * m.inv_cell;
-      const float igx = dv.z * m.cell, igy = dv.w * m.cell;  // ray distance per grid unit along each axis
-      float t0 = 0.f, t1 = best.s;
-      if (!ry_.zx) {
-        const float ta = (0.f - gx) * igx, tb = ((float)m.nx - gx) * igx;
-        t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-      } else if (gx < 0.f || gx >= (float)m.nx) active = false;
-      if (!ry_.zy) {
-        const float ta = (0.f - gy) * igy, tb = ((float)m.ny - gy) * igy;
-        t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-      } else if (gy < 0.f || gy >= (float)m.ny) active = false;
-      if (!(t0 <= t1)) active = false;
-      if (active) {
-        const float sx = gx + dv.x * m.inv_cell * t0, sy = gy + dv.y * m.inv_cell * t0;
-        ix = min(max((int)floorf(sx), 0), m.nx - 1);
-        iy = min(max((int)floorf(sy), 0), m.ny - 1);
-        stepx = dv.x > 0.f ? 1 : -1; stepy = dv.y > 0.f ? 1 : -1;
-        tdx = ry_.zx ? CUDART_INF_F : fabsf(igx);
-        tdy = ry_.zy ? CUDART_INF_F : fabsf(igy);
-        tmx = ry_.zx ? CUDART_INF_F : ((float)(ix + (stepx > 0 ? 1 : 0)) - gx) * igx;
-        tmy = ry_.zy ? CUDART_INF_F : ((float)(iy + (stepy > 0 ? 1 : 0)) - gy) * igy;
-        const int cell = iy * m.nx + ix;
-        q = m.ray_off[cell]; qe = m.ray_off[cell + 1];
-      }
-    }
-    // ---- converged traversal: fetch (divergent, cheap) then one edge test (converged)
-    for (;;) {
-      if (active && ei == ee) {
-        for (;;) {
-          if (q < qe) {
-            const int h = m.ray_list[q++];
-            if (h == last1 || h == last2) continue;
-            last2 = last1; last1 = h;
-            if (!thin_bb_hit(m.hull_bb[h], ox, oy, ry_.zx, ry_.zy, ry_.idx, ry_.idy)) continue;
-            const uint32_t eo = m.hull_eo[h];
-            ei = eo & 0xFFFF; ee = ei + (eo >> 16); hcur = h;
-            break;
+    // ---- (1) lanes = rays: seed the depth buffer with the dynamic shapes and the alpha = 0 rules
+#pragma unroll 1
+    for (int sub = 0; sub < nsub; ++sub) {
+      const int i = sub * 32 + lane;
+      if (i < R) {
+        const float4 dv = m.dir[i];
+        Ray r;
+        r.ox = ox; r.oy = oy; r.ux = dv.x; r.uy = dv.y; r.L = L;
+        r.zx = dv.x == 0.f; r.zy = dv.y == 0.f; r.idx = dv.z * inv_L; r.idy = dv.w * inv_L;
+        unsigned long long key = make_key(L, kNoFeature);
+        if (zero_agent >= 0) key = make_key(0.f, kAgentTag + zero_agent);
+        else {
+#pragma unroll 1
+          for (int j = 0; j < A; ++j) {   // the other agents' cached centres
+            if (j == a) continue;
+            const float sc = ray_circle(tc[2 * j], tc[2 * j + 1], reach, r);
+            if (sc < L) key = min(key, make_key(sc, kAgentTag + j));
           }
-          // next cell; stop once it starts beyond the best hit (or the sensor range) or leaves the grid
-          if (!(fminf(tmx, tmy) < best.s)) { active = false; break; }
-          if (tmx < tmy) { ix += stepx; tmx += tdx; } else { iy += stepy; tmy += tdy; }
-          if (ix < 0 || iy < 0 || ix >= m.nx || iy >= m.ny) { active = false; break; }
-          const int cell = iy * m.nx + ix;
-          q = m.ray_off[cell]; qe = m.ray_off[cell + 1];
         }
+        // static shapes with the origin inside their reach: alpha = 0, but only if the thin ray enters the bb
+#pragma unroll 1
+        for (uint32_t q = 0; q < ncnt; ++q) {
+          const int h = w.near[a * kNear + q];
+          if (thin_bb_hit(m.hull_bb[h], ox, oy, r.zx, r.zy, r.idx, r.idy)) key = min(key, make_key(0.f, 0u));
+        }
+        w.best[a * R + i] = key;
       }
-      if (!__any_sync(0xFFFFFFFFu, active)) break;
-      if (active) { ray_edge(m, ei, hcur, ry_, rsum, rs2, best); ++ei; }
     }
+    __syncwarp();
 
-    if (valid) {
-      // entity.py:200-215 — float16 chain, reproduced at each of its rounding points
-      uint16_t dbits;
-      uint8_t type;
-      float hx = ox + L * dv.x, hy = oy + L * dv.y;   // ray end: reported when nothing is hit or alpha = 0
-      if (best.id < 0) {
-        dbits = __half_as_ushort(__float2half_rn(L));
-        type = TYPE_EMPTY;
-      } else {
-        if (!zero_hit) {
-          float2 n;
-          if (best.id < m.H) n = wall_hit_normal(m, best, ry_, rsum);
-          else {
-            const int j = best.id - m.H;
-            const float inv = 1.f / reach;
-            n = make_float2((ox - tc[2 * j] + best.s * dv.x) * inv, (oy - tc[2 * j + 1] + best.s * dv.y) * inv);
-          }
-          hx = ox + best.s * dv.x - n.x * k.ray_r; hy = oy + best.s * dv.y - n.y * k.ray_r;
-        }
-        const float pxh = __half2float(__float2half_rn(hx)), pyh = __half2float(__float2half_rn(hy));
-        const float oxh = __half2float(__float2half_rn(ox)), oyh = __half2float(__float2half_rn(oy));
-        const float dxh = __half2float(__float2half_rn(pxh - oxh));
-        const float dyh = __half2float(__float2half_rn(pyh - oyh));
-        const float hyp = (float)sqrt((double)dxh * (double)dxh + (double)dyh * (double)dyh);
-        dbits = __half_as_ushort(__float2half_rn(hyp));
-        type = best.id < m.H ? TYPE_WALL : ((best.id - m.H) >= k.nc ? TYPE_THIEF : TYPE_COP);
-        // rewards need the nearest opponent seen by this agent (cop.py:66-70, thief.py:60-63)
-        const int want = (a < k.nc) ? TYPE_THIEF : TYPE_COP;
-        if (type == want) atomicMin(&w.minbits[a], (uint32_t)dbits);
+    // ---- (2) lanes = edges: candidates face the origin (plane i or the next plane, which share vertex v_i
+    //          and hence its bevel) and lie within sensor range of the origin
+    int ncand = 0;
+#pragma unroll 1
+    for (int base = 0; base < E; base += 32) {
+      const int e = base + lane;
+      bool is_cand = false;
+      if (e < E) {
+        const float4 ed = m.edge[e];
+        const float2 nn = m.next_n[e];
+        const float rx = ox - ed.x, ry = oy - ed.y;
+        const float pd = rx * ed.z + ry * ed.w;
+        const float pdn = rx * nn.x + ry * nn.y;
+        const float len = m.edge_len[e];
+        const float qa = fmaf(ry, ed.z, -rx * ed.w);       // position of o along A->B, relative to B
+        const float dq = qa - fminf(fmaxf(qa, -len), 0.f);
+        is_cand = (pd > 0.f || pdn > 0.f) && (fmaf(pd, pd, dq * dq) < range2);
       }
-      w.rdist[r] = dbits;
-      w.rtype[r] = type;
-      if (k.hit_point) {
-        float2* hp = reinterpret_cast<float2*>(k.hit_point) + (size_t)world * k.nrays + r;
-        *hp = make_float2(hx, hy);
+      const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
+      if (is_cand) w.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)e;
+      ncand += __popc(cmask);
+      __syncwarp();
+      if (ncand >= 32) {
+        raster_batch(w.blob, w.best + a * R, w.cand, 32, ox, oy, rsum, L, R);
+        __syncwarp();
+        uint16_t t = 0;
+        if (lane + 32 < ncand) t = w.cand[lane + 32];
+        __syncwarp();
+        if (lane + 32 < ncand) w.cand[lane] = t;
+        ncand -= 32;
+        __syncwarp();
+      }
+    }
+    if (ncand > 0) raster_batch(w.blob, w.best + a * R, w.cand, ncand, ox, oy, rsum, L, R);
+    __syncwarp();
+
+    // ---- (3) lanes = rays: entity.py:200-215 — hit point, float16 chain at each of its rounding points, type
+    const float oxh = __half2float(__float2half_rn(ox)), oyh = __half2float(__float2half_rn(oy));
+    const int want = (a < k.nc) ? TYPE_THIEF : TYPE_COP;
+#pragma unroll 1
+    for (int sub = 0; sub < nsub; ++sub) {
+      const int i = sub * 32 + lane;
+      if (i < R) {
+        const int r = a * R + i;
+        const unsigned long long key = w.best[r];
+        const uint32_t feat = (uint32_t)key;
+        const float sHit = __uint_as_float((uint32_t)(key >> 32));
+        const float4 dv = m.dir[i];
+        uint16_t dbits;
+        uint8_t type;
+        float hx = fmaf(L, dv.x, ox), hy = fmaf(L, dv.y, oy);   // ray end: reported when nothing is hit or alpha = 0
+        if (feat == kNoFeature) {
+          dbits = __half_as_ushort(__float2half_rn(L));
+          type = TYPE_EMPTY;
+        } else {
+          const bool is_agent = feat >= kAgentTag;
+          if (sHit > 0.f) {
+            float2 n;
+            if (!is_agent) {
+              Ray rr; rr.ox = ox; rr.oy = oy; rr.ux = dv.x; rr.uy = dv.y;
+              n = wall_hit_normal(m, feat, sHit, rr, rsum);
+            } else {
+              const int j = (int)(feat - kAgentTag);
+              n = make_float2((ox - tc[2 * j] + sHit * dv.x) * inv_reach, (oy - tc[2 * j + 1] + sHit * dv.y) * inv_reach);
+            }
+            hx = ox + sHit * dv.x - n.x * k.ray_r; hy = oy + sHit * dv.y - n.y * k.ray_r;
+          }
+          const float pxh = __half2float(__float2half_rn(hx)), pyh = __half2float(__float2half_rn(hy));
+          const float dxh = __half2float(__float2half_rn(pxh - oxh));
+          const float dyh = __half2float(__float2half_rn(pyh - oyh));
+          const float hyp = (float)sqrt((double)dxh * (double)dxh + (double)dyh * (double)dyh);
+          dbits = __half_as_ushort(__float2half_rn(hyp));
+          type = !is_agent ? TYPE_WALL : ((int)(feat - kAgentTag) >= k.nc ? TYPE_THIEF : TYPE_COP);
+          // rewards need the nearest opponent seen by this agent (cop.py:66-70, thief.py:60-63)
+          if (type == want) atomicMin(&w.minbits[a], (uint32_t)dbits);
+        }
+        w.rdist[r] = dbits;
+        w.rtype[r] = type;
+        if (k.hit_point) {
+          float2* hp = reinterpret_cast<float2*>(k.hit_point) + (size_t)world * k.nrays + r;
+          *hp = make_float2(hx, hy);
+        }
       }
     }
   }
   __syncwarp();
+}
+
+// Optional fp32 layouts (what skrl's wrapper would build on the host): per-agent flattened observation
+// and the flattened centralised-critic state.  Only called when the caller asked for them; kept out of
+// line so the native-dtype fast path stays small.
+__device__ __noinline__ void write_flat_layouts(const KParams& k, const uint16_t* rdist, const uint8_t* rtype,
+                                                const float* pos, long long world) {
+  const int A = k.A, R = k.R, lane = threadIdx.x & 31;
+  if (k.obs_f32) {  // [A][N][2R]: [distance | object_type] as skrl flattens the Dict (keys sorted)
+#pragma unroll 1
+    for (int a = 0; a < A; ++a) {
+      float* dst = k.obs_f32 + ((size_t)a * k.n_worlds + world) * (2 * R);
+#pragma unroll 1
+      for (int i = lane; i < 2 * R; i += 32)
+        dst[i] = i < R ? __half2float(__ushort_as_half(rdist[a * R + i])) : (float)rtype[a * R + i - R];
+    }
+  }
+  if (k.state_f32) {
+    // env.state(): per agent [distance_shared | object_type_shared | own_distances | own_obj_types | team_positions]
+    float* dst = k.state_f32 + (size_t)world * k.state_dim;
+    int base = 0;
+#pragma unroll 1
+    for (int a = 0; a < A; ++a) {
+      const int team = a < k.nc ? 0 : 1;
+      const int a0 = team == 0 ? 0 : k.nc, a1 = team == 0 ? k.nc : A;
+      const int blk = 4 * R + 2 * (a1 - a0);
+#pragma unroll 1
+      for (int i = lane; i < blk; i += 32) {
+        float v;
+        if (i < 2 * R) {
+          const int ri = i < R ? i : i - R;
+          uint8_t t = TYPE_EMPTY;
+          uint16_t d = 0;
+#pragma unroll 1
+          for (int b = a0; b < a1; ++b)
+            if (t == TYPE_EMPTY) { t = rtype[b * R + ri]; d = rdist[b * R + ri]; }
+          v = i < R ? __half2float(__ushort_as_half(d)) : (float)t;
+        } else if (i < 3 * R) v = __half2float(__ushort_as_half(rdist[a * R + i - 2 * R]));
+        else if (i < 4 * R) v = (float)rtype[a * R + i - 3 * R];
+        else v = __half2float(__float2half_rn(pos[2 * a0 + (i - 4 * R)]));
+        dst[base + i] = v;
+      }
+      base += blk;
+    }
+  }
 }
 
 // Write the observation-side outputs of one world from shared memory (coalesced).
@@ -489,8 +654,10 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
     if ((nrays & 1) == 0) {
       uint32_t* dst = reinterpret_cast<uint32_t*>(k.obs_dist + (size_t)world * nrays);
       const uint32_t* src = reinterpret_cast<const uint32_t*>(w.rdist);
+#pragma unroll 1
       for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
     } else {
+#pragma unroll 1
       for (int i = lane; i < nrays; i += 32) k.obs_dist[(size_t)world * nrays + i] = w.rdist[i];
     }
   }
@@ -498,60 +665,36 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
     if ((nrays & 1) == 0) {
       uint16_t* dst = reinterpret_cast<uint16_t*>(k.obs_type + (size_t)world * nrays);
       const uint16_t* src = reinterpret_cast<const uint16_t*>(w.rtype);
+#pragma unroll 1
       for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
     } else {
+#pragma unroll 1
       for (int i = lane; i < nrays; i += 32) k.obs_type[(size_t)world * nrays + i] = w.rtype[i];
     }
   }
   if (k.team_pos) {  // observation_spaces.py:92-95
+#pragma unroll 1
     for (int i = lane; i < 2 * A; i += 32)
       k.team_pos[(size_t)world * 2 * A + i] = __half_as_ushort(__float2half_rn(pos[i]));
   }
   // observation_spaces.py:97-121 net effect: first non-EMPTY (type, distance) in team order
   if (k.shared_dist || k.shared_type) {
-    for (int q = lane; q < 2 * R; q += 32) {
-      const int team = q / R, i = q - team * R;
+#pragma unroll 1
+    for (int team = 0; team < 2; ++team) {
       const int a0 = team == 0 ? 0 : k.nc, a1 = team == 0 ? k.nc : A;
-      uint8_t t = TYPE_EMPTY;
-      uint16_t d = 0;
-      for (int a = a0; a < a1; ++a)
-        if (t == TYPE_EMPTY) { t = w.rtype[a * R + i]; d = w.rdist[a * R + i]; }
-      if (k.shared_dist) k.shared_dist[(size_t)world * 2 * R + q] = d;
-      if (k.shared_type) k.shared_type[(size_t)world * 2 * R + q] = t;
-    }
-  }
-  if (k.obs_f32) {  // [A][N][2R]: [distance | object_type] as skrl flattens the Dict (keys sorted)
-    for (int a = 0; a < A; ++a) {
-      float* dst = k.obs_f32 + ((size_t)a * k.n_worlds + world) * (2 * R);
-      for (int i = lane; i < 2 * R; i += 32)
-        dst[i] = i < R ? __half2float(__ushort_as_half(w.rdist[a * R + i])) : (float)w.rtype[a * R + i - R];
-    }
-  }
-  if (k.state_f32) {
-    // env.state(): per agent [distance_shared | object_type_shared | own_distances | own_obj_types | team_positions]
-    float* dst = k.state_f32 + (size_t)world * k.state_dim;
-    int base = 0;
-    for (int a = 0; a < A; ++a) {
-      const int team = a < k.nc ? 0 : 1;
-      const int a0 = team == 0 ? 0 : k.nc, a1 = team == 0 ? k.nc : A;
-      const int blk = 4 * R + 2 * (a1 - a0);
-      for (int i = lane; i < blk; i += 32) {
-        float v;
-        if (i < 2 * R) {
-          const int ri = i < R ? i : i - R;
-          uint8_t t = TYPE_EMPTY;
-          uint16_t d = 0;
-          for (int b = a0; b < a1; ++b)
-            if (t == TYPE_EMPTY) { t = w.rtype[b * R + ri]; d = w.rdist[b * R + ri]; }
-          v = i < R ? __half2float(__ushort_as_half(d)) : (float)t;
-        } else if (i < 3 * R) v = __half2float(__ushort_as_half(w.rdist[a * R + i - 2 * R]));
-        else if (i < 4 * R) v = (float)w.rtype[a * R + i - 3 * R];
-        else v = __half2float(__float2half_rn(pos[2 * a0 + (i - 4 * R)]));
-        dst[base + i] = v;
+#pragma unroll 1
+      for (int i = lane; i < R; i += 32) {
+        uint8_t t = TYPE_EMPTY;
+        uint16_t d = 0;
+#pragma unroll 1
+        for (int a = a0; a < a1; ++a)
+          if (t == TYPE_EMPTY) { t = w.rtype[a * R + i]; d = w.rdist[a * R + i]; }
+        if (k.shared_dist) k.shared_dist[((size_t)world * 2 + team) * R + i] = d;
+        if (k.shared_type) k.shared_type[((size_t)world * 2 + team) * R + i] = t;
       }
-      base += blk;
     }
   }
+  if (k.obs_f32 || k.state_f32) write_flat_layouts(k, w.rdist, w.rtype, pos, world);
 }
 
 // cop.py:49-75 / thief.py:48-69 in fp32 from the f16 distance.
@@ -591,6 +734,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
     uint32_t cnt = 0, used = 0;
     const int cell = grid_cell(m, px, py);
     if (cell >= 0) {
+#pragma unroll 1
       for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && cnt < (uint32_t)kSlots; ++q) {
         const int h = m.con_list[q];
         const float4 bb = m.hull_bb[h];  // QueryReject: the shape bbs must overlap (hull bb already grown by wall_r)
@@ -600,6 +744,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
         if (d <= rsum_w) {  // CircleToPoly: d <= r_circle + r_poly
           // cpArbiterUpdate: reuse the cached arbiter of this (agent, hull) pair if any
           int slot = -1;
+#pragma unroll 1
           for (int s = 0; s < kSlots; ++s)
             if (wkey[lane * kSlots + s] != kEmpty && (wkey[lane * kSlots + s] & 0xFFFF) == (uint32_t)h) slot = s;
           float jn0 = 0.f;
@@ -610,6 +755,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
           } else {
             // free slot, else the oldest slot not used this step
             uint32_t oldest = 0;
+#pragma unroll 1
             for (int s = 0; s < kSlots; ++s) {
               if (used & (1u << s)) continue;
               const uint32_t key = wkey[lane * kSlots + s];
@@ -632,6 +778,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
       }
     }
     // cpSpaceArbiterSetFilter: arbiters not used this step age; dropped at collision_persistence
+#pragma unroll 1
     for (int s = 0; s < kSlots; ++s) {
       if (used & (1u << s)) continue;
       const uint32_t key = wkey[lane * kSlots + s];
@@ -642,10 +789,16 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
     }
     w.ccount[lane] = cnt;
   }
+  {
+    // agents with a wall inside contact reach are the only ones that can start a ray inside a wall's reach next step
+    const uint32_t near_mask = __ballot_sync(0xFFFFFFFFu, lane < A && w.ccount[lane] > 0);
+    if (lane == 0) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = near_mask;
+  }
   uint32_t pair_hit = 0;
   if (lane < P) {
     // pair index -> (i, j), i-major
     int i = 0, rem = lane;
+#pragma unroll 1
     while (rem >= A - 1 - i) { rem -= A - 1 - i; ++i; }
     const int j = i + 1 + rem;
     const float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1];
@@ -654,8 +807,9 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
     if (dsq < mind * mind) {  // CircleToCircle (strict)
       const float dist = sqrtf(dsq);
       float* c = w.con + (A * kSlots + lane) * 8;
-      c[0] = dist > 0.f ? dx / dist : 1.f;
-      c[1] = dist > 0.f ? dy / dist : 0.f;
+      const float invd = dist > 0.f ? 1.f / dist : 0.f;
+      c[0] = dist > 0.f ? dx * invd : 1.f;
+      c[1] = dy * invd;
       c[2] = -k.bias_coef * fminf(0.f, (dist - mind) + k.slop) * k.inv_dt;
       c[3] = age != kEmpty ? pjn[lane] : 0.f;
       c[4] = 0.f; c[5] = 1.f / (2.f * k.inv_mass);
@@ -674,12 +828,16 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
   // (7) warm start + (8) sequential impulses: serial by construction, lane 0
   if (lane == 0) {
     int n = 0;
+#pragma unroll 1
     for (int a = 0; a < A; ++a)
+#pragma unroll 1
       for (uint32_t q = 0; q < w.ccount[a]; ++q) w.order[n++] = (uint8_t)(a * kSlots + q);
+#pragma unroll 1
     for (int p = 0; p < P; ++p)
       if (pair_mask & (1u << p)) w.order[n++] = (uint8_t)(A * kSlots + p);
     if (n > 0) {
       const float minv = k.inv_mass;
+#pragma unroll 1
       for (int q = 0; q < n; ++q) {  // cpArbiterApplyCachedImpulse (dt_coef = 1)
         float* c = w.con + w.order[q] * 8;
         const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
@@ -689,7 +847,9 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
         vel[2 * a] -= jx; vel[2 * a + 1] -= jy;
         if (b != 0xFF) { vel[2 * b] += jx; vel[2 * b + 1] += jy; }
       }
+#pragma unroll 1
       for (int it = 0; it < k.iterations; ++it) {
+#pragma unroll 1
         for (int q = 0; q < n; ++q) {  // cpArbiterApplyImpulse, e = 0, u = 0
           float* c = w.con + w.order[q] * 8;
           const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
@@ -713,6 +873,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
           }
         }
       }
+#pragma unroll 1
       for (int q = 0; q < n; ++q) {  // persist jnAcc in the arbiter cache
         const float* c = w.con + w.order[q] * 8;
         const uint32_t meta = reinterpret_cast<const uint32_t*>(c)[6];
@@ -740,6 +901,7 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
       const uint32_t idx = cat_spawn_region_index(k.seed, gid, episode, (uint32_t)lane, (uint32_t)nr);
       const float4 reg = m.regions[r0 + (int)idx];
       nx_ = reg.x + reg.z / 2.f; ny_ = reg.y + reg.w / 2.f;  // base_env.py:163-166 fallback
+#pragma unroll 1
       for (uint32_t t = 0; t < 20; ++t) {
         float ux, uy;
         cat_spawn_uniforms(k.seed, gid, episode, (uint32_t)lane, t, &ux, &uy);
@@ -748,12 +910,14 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
         bool blocked = false;
         const int cell = grid_cell(m, px, py);
         if (cell >= 0) {
+#pragma unroll 1
           for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && !blocked; ++q) {
             float d, ax, ay;
             hull_closest(m, m.con_list[q], px, py, d, ax, ay);
             if (d - k.wall_r < k.agent_r) blocked = true;
           }
         }
+#pragma unroll 1
         for (int j = 0; j < A && !blocked; ++j) {
           if (j == lane) continue;
           const float dx = px - tc[2 * j], dy = py - tc[2 * j + 1];
@@ -775,6 +939,7 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
   if (lane == 0) {
     *ep = episode;
     reinterpret_cast<int32_t*>(w.rec)[k.o_sc] = 0;  // base_env.py:350
+    reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0xFFu;  // re-spawned bodies may sit next to a wall
   }
   __syncwarp();
 }
@@ -801,6 +966,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
   }
   {
     uint32_t done = 0;
+#pragma unroll 1
     while (!done) {
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
@@ -824,26 +990,33 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
   w.con = reinterpret_cast<float*>(scratch + k.s_con);
   w.ccount = reinterpret_cast<uint32_t*>(scratch + k.s_ccount);
   w.order = reinterpret_cast<uint8_t*>(scratch + k.s_order);
+  w.best = reinterpret_cast<unsigned long long*>(scratch + k.s_best);
+  w.cand = reinterpret_cast<uint16_t*>(scratch + k.s_cand);
+  w.blob = smem;
   w.lane = lane;
 
   const int A = k.A;
   const long long stride = (long long)gridDim.x * kWarpsPerCta;
+#pragma unroll 1
   for (long long world = (long long)blockIdx.x * kWarpsPerCta + warp; world < k.n_worlds; world += stride) {
     float* grec = k.state + (size_t)world * k.rec_words;
     int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
 
     if (k.mode == MODE_INIT) {  // fresh environment (entity.py:115,124): agents at map positions
+#pragma unroll 1
       for (int i = lane; i < k.rec_words; i += 32) {
         float v = 0.f;
         if (i < 2 * A) v = (i & 1) ? m.init_pos[i >> 1].y : m.init_pos[i >> 1].x;
         else if (i >= k.o_tc && i < k.o_tc + 2 * A) { const int q = i - k.o_tc; v = (q & 1) ? m.init_pos[q >> 1].y : m.init_pos[q >> 1].x; }
         else if ((i >= k.o_wkey && i < k.o_wkey + A * kSlots) || (i >= k.o_page && i < k.o_page + k.P)) v = __uint_as_float(kEmpty);
+        else if (i == k.o_flags) v = __uint_as_float(0xFFu);
         grec[i] = v;
       }
       continue;
     }
     if (k.mode == MODE_RESET && k.reset_mask && !k.reset_mask[world]) continue;
 
+#pragma unroll 1
     for (int i = lane; i < k.rec_words; i += 32) w.rec[i] = grec[i];
     __syncwarp();
 
@@ -856,7 +1029,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
       __syncwarp();
       if (lane == 0) reci[k.o_sc] = step_count;
       // _termination_criterion (:521-554): thief-major; LOS blocked by walls only; dist < radius (strict)
+#pragma unroll 1
       for (int t = k.nc; t < A && !captured; ++t)
+#pragma unroll 1
         for (int c = 0; c < k.nc && !captured; ++c) {
           const float tx = pos[2 * t], ty = pos[2 * t + 1], cx = pos[2 * c], cy = pos[2 * c + 1];
           const float dx = tx - cx, dy = ty - cy;
@@ -889,6 +1064,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
     //   STEP    : observe -> rewards/flags -> (write) -> physics -> [done: reset -> observe -> write]
     //   RESET   : reset -> observe -> write
     //   OBSERVE : observe -> write
+#pragma unroll 1
     for (;;) {
       if (do_reset) { reset_world(k, m, w, world); do_reset = false; }
       observe_world(k, m, w, world);  // entity.py:143 — pre-physics state
@@ -914,6 +1090,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
       break;
     }
     if (k.mode != MODE_OBSERVE) {
+#pragma unroll 1
       for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
     }
     __syncwarp();
@@ -924,7 +1101,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
 struct ViewParams {
   float* state;
   int rec_words, n_worlds, A, P;
-  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep;
+  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags;
   CatStateView v;
   int set;
 };
@@ -940,6 +1117,7 @@ __global__ void cat_state_view_kernel(const ViewParams p) {
     for (int i = 0; i < n; ++i) { if (p.set) rec[off + i] = ext[(size_t)w * n + i]; else ext[(size_t)w * n + i] = rec[off + i]; }
   };
   xfer(p.v.pos, 0, 2 * A);
+  if (p.set && p.v.pos) recu[p.o_flags] = 0xFFu;  // positions changed: re-evaluate the alpha = 0 candidates
   xfer(p.v.vel, p.o_vel, 2 * A);
   xfer(p.v.vbias, p.o_vb, 2 * A);
   xfer(p.v.tc, p.o_tc, 2 * A);
@@ -1055,10 +1233,10 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   if (n_worlds < 1) return fail(CAT_ERR_INVALID, "n_worlds must be >= 1");
   if (map->n_cops < 1 || map->n_thieves < 1) return fail(CAT_ERR_INVALID, "need at least one cop and one thief");
   if (A > CAT_MAX_AGENTS) return fail(CAT_ERR_LIMIT, "too many agents (CAT_MAX_AGENTS)");
-  if (R < 1 || R > CAT_MAX_RAYS) return fail(CAT_ERR_LIMIT, "n_rays out of range (CAT_MAX_RAYS)");
+  if (R < 2 || R > CAT_MAX_RAYS) return fail(CAT_ERR_LIMIT, "n_rays out of range (2..CAT_MAX_RAYS)");
   if (H < 1 || H > 65535 || E > 65535) return fail(CAT_ERR_LIMIT, "hull/edge count out of range");
   const int ncell = map->nx * map->ny;
-  if (ncell < 1 || map->ray_cell_off[ncell] > 65535 || map->con_cell_off[ncell] > 65535)
+  if (ncell < 1 || map->con_cell_off[ncell] > 65535)
     return fail(CAT_ERR_LIMIT, "grid lists too long for 16-bit offsets");
   for (int h = 0; h < H; ++h)
     if (map->hull_off[h + 1] - map->hull_off[h] > 65535) return fail(CAT_ERR_LIMIT, "hull too large");
@@ -1078,8 +1256,8 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   hd.off_len = take(E * 4);
   hd.off_hbb = take(H * 16);
   hd.off_heo = take(H * 4);
-  hd.off_rayoff = take((ncell + 1) * 2);
-  hd.off_raylist = take(map->ray_cell_off[ncell] * 2 + 2);
+  hd.off_nextn = take(E * 8);
+  hd.off_edgehull = take(E * 2 + 2);
   hd.off_conoff = take((ncell + 1) * 2);
   hd.off_conlist = take(map->con_cell_off[ncell] * 2 + 2);
   hd.off_dir = take(R * 16);
@@ -1107,11 +1285,18 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
       bb[4 * h + 3] = nextafterf((float)(map->hull_bb[4 * h + 3] + pr->wall_radius), INFINITY);
       eo[h] = (uint32_t)map->hull_off[h] | ((uint32_t)(map->hull_off[h + 1] - map->hull_off[h]) << 16);
     }
-    uint16_t* ro = reinterpret_cast<uint16_t*>(blob.data() + hd.off_rayoff);
     uint16_t* co = reinterpret_cast<uint16_t*>(blob.data() + hd.off_conoff);
-    for (int c = 0; c <= ncell; ++c) { ro[c] = (uint16_t)map->ray_cell_off[c]; co[c] = (uint16_t)map->con_cell_off[c]; }
-    uint16_t* rl = reinterpret_cast<uint16_t*>(blob.data() + hd.off_raylist);
-    for (int i = 0; i < map->ray_cell_off[ncell]; ++i) rl[i] = (uint16_t)map->ray_cell_hulls[i];
+    for (int c = 0; c <= ncell; ++c) co[c] = (uint16_t)map->con_cell_off[c];
+    uint16_t* eh = reinterpret_cast<uint16_t*>(blob.data() + hd.off_edgehull);
+    float* nn = reinterpret_cast<float*>(blob.data() + hd.off_nextn);
+    for (int h = 0; h < H; ++h) {
+      const int o = map->hull_off[h], e = map->hull_off[h + 1];
+      for (int i = o; i < e; ++i) {
+        const int nx_ = (i + 1 < e) ? i + 1 : o;
+        eh[i] = (uint16_t)h;
+        nn[2 * i] = (float)map->normal[2 * nx_]; nn[2 * i + 1] = (float)map->normal[2 * nx_ + 1];
+      }
+    }
     uint16_t* cl = reinterpret_cast<uint16_t*>(blob.data() + hd.off_conlist);
     for (int i = 0; i < map->con_cell_off[ncell]; ++i) cl[i] = (uint16_t)map->con_cell_hulls[i];
     float* dir = reinterpret_cast<float*>(blob.data() + hd.off_dir);
@@ -1143,10 +1328,11 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   k.n_worlds = n_worlds; k.gid0 = gid0;
   k.A = A; k.nc = map->n_cops; k.R = R; k.P = P; k.nrays = A * R; k.nrays_pad = align_up(A * R, 32);
   k.maxc = A * kSlots + P;
+  k.n_edges = E;
   // record layout (4-byte words)
   k.o_vel = 2 * A; k.o_vb = 4 * A; k.o_tc = 6 * A; k.o_wkey = 8 * A; k.o_wjn = 8 * A + A * kSlots;
-  k.o_page = 8 * A + 2 * A * kSlots; k.o_pjn = k.o_page + P; k.o_sc = k.o_pjn + P; k.o_ep = k.o_sc + 1;
-  k.rec_words = align_up(k.o_ep + 1, 32);
+  k.o_page = 8 * A + 2 * A * kSlots; k.o_pjn = k.o_page + P; k.o_sc = k.o_pjn + P; k.o_ep = k.o_sc + 1; k.o_flags = k.o_ep + 1;
+  k.rec_words = align_up(k.o_flags + 1, 32);
   // scratch layout (bytes)
   int so = k.rec_words * 4;
   auto stake = [&](int bytes) { int o = so; so = align_up(so + bytes, 16); return o; };
@@ -1158,6 +1344,8 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   k.s_con = stake(k.maxc * 32);
   k.s_ccount = stake(CAT_MAX_AGENTS * 4);
   k.s_order = stake(k.maxc);
+  k.s_best = stake(k.nrays_pad * 8);
+  k.s_cand = stake(64 * 2);
   k.scratch_bytes = align_up(so, 128);
   k.state_dim = 0;
   for (int a = 0; a < A; ++a) k.state_dim += 4 * R + 2 * (a < map->n_cops ? map->n_cops : map->n_thieves);
@@ -1255,7 +1443,7 @@ static int state_view(CatEnv* env, void* state_dev, const CatStateView* view, in
   p.state = reinterpret_cast<float*>(state_dev);
   p.rec_words = k.rec_words; p.n_worlds = k.n_worlds; p.A = k.A; p.P = k.P;
   p.o_vel = k.o_vel; p.o_vb = k.o_vb; p.o_tc = k.o_tc; p.o_wkey = k.o_wkey; p.o_wjn = k.o_wjn;
-  p.o_page = k.o_page; p.o_pjn = k.o_pjn; p.o_sc = k.o_sc; p.o_ep = k.o_ep;
+  p.o_page = k.o_page; p.o_pjn = k.o_pjn; p.o_sc = k.o_sc; p.o_ep = k.o_ep; p.o_flags = k.o_flags;
   p.v = *view; p.set = set;
   const int threads = 128, blocks = (k.n_worlds + threads - 1) / threads;
   cat_state_view_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -51,8 +51,6 @@ class CatWorlds:
             init_pos=np.ascontiguousarray(cmap.init_pos, np.float64),
             region_off=np.ascontiguousarray(cmap.region_off, np.int32),
             regions=np.ascontiguousarray(cmap.regions if len(cmap.regions) else np.zeros((1, 4)), np.float64),
-            ray_cell_off=np.ascontiguousarray(cmap.ray_cell_off, np.int32),
-            ray_cell_hulls=np.ascontiguousarray(np.append(cmap.ray_cell_hulls, 0), np.int32),
             con_cell_off=np.ascontiguousarray(cmap.con_cell_off, np.int32),
             con_cell_hulls=np.ascontiguousarray(np.append(cmap.con_cell_hulls, 0), np.int32),
         )
@@ -62,7 +60,6 @@ class CatWorlds:
             _lib.np_ptr(k["edge_len"]), _lib.np_ptr(k["hull_bb"]), cmap.n_cops, cmap.n_thieves,
             _lib.np_ptr(k["init_pos"]), _lib.np_ptr(k["region_off"]), _lib.np_ptr(k["regions"]),
             cmap.grid_x0, cmap.grid_y0, cmap.cell, cmap.nx, cmap.ny,
-            _lib.np_ptr(k["ray_cell_off"]), _lib.np_ptr(k["ray_cell_hulls"]),
             _lib.np_ptr(k["con_cell_off"]), _lib.np_ptr(k["con_cell_hulls"]))
         cp = CatParams(**{name: p[name] for name, _ in CatParams._fields_})
         handle = C.c_void_p()

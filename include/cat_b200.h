@@ -64,10 +64,8 @@ typedef struct {
   const double* init_pos;    /* [A][2] */
   const int32_t* region_off; /* [A+1] */
   const double* regions;     /* [n_regions][4] x,y,w,h */
-  double grid_x0, grid_y0, cell;
+  double grid_x0, grid_y0, cell; /* uniform grid used by contact / spawn / start-inside lookups */
   int32_t nx, ny;
-  const int32_t* ray_cell_off;   /* [nx*ny+1] hulls within ray reach of each cell (ascending ids) */
-  const int32_t* ray_cell_hulls;
   const int32_t* con_cell_off;   /* [nx*ny+1] hulls within contact reach of each cell */
   const int32_t* con_cell_hulls;
 } CatMapDesc;

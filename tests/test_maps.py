@@ -114,16 +114,24 @@ def test_grid_lists_are_conservative(name):
     pts = rng.uniform(lo, hi, size=(1500, 2))
     for p in pts:
         c = int((p[1] - cm.grid_y0) // cm.cell) * cm.nx + int((p[0] - cm.grid_x0) // cm.cell)
-        ray = set(cm.ray_cell_hulls[cm.ray_cell_off[c]:cm.ray_cell_off[c + 1]].tolist())
+        ray = set(cm.ray_cell_edges[cm.ray_cell_off[c]:cm.ray_cell_off[c + 1]].tolist())
         con = set(cm.con_cell_hulls[cm.con_cell_off[c]:cm.con_cell_off[c + 1]].tolist())
         for h in range(cm.n_hulls):
             d = orc.hull_distance(h, p)
-            if d <= 2.0:
-                assert h in ray
             if d <= 6.0:
                 assert h in con
+            if d <= 2.0 and d > 0:
+                # every edge whose segment is within ray reach of p must be listed (edge-granular lists)
+                o, e = cm.hull_off[h], cm.hull_off[h + 1]
+                for i in range(o, e):
+                    a = cm.vert[i - 1] if i > o else cm.vert[e - 1]
+                    b = cm.vert[i]
+                    t = np.clip(((p - a) @ (b - a)) / ((b - a) @ (b - a)), 0, 1)
+                    if np.hypot(*(p - (a + t * (b - a)))) <= 2.0:
+                        assert i in ray
+                        assert cm.edge_hull[i] == h
     # lists are sorted ascending (fixes the arbiter order)
-    for off, lst in ((cm.ray_cell_off, cm.ray_cell_hulls), (cm.con_cell_off, cm.con_cell_hulls)):
+    for off, lst in ((cm.ray_cell_off, cm.ray_cell_edges), (cm.con_cell_off, cm.con_cell_hulls)):
         for c in range(cm.nx * cm.ny):
             seg = lst[off[c]:off[c + 1]]
             assert np.all(np.diff(seg) > 0)

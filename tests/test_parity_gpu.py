@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances are the north star's: positions / velocities <= 1e-4 relative, ray hit
+point <= 0.04 (1e-4 of the 400 range) BEFORE the float16 chain, the float16 chain bit-exact given
+equal fp32 inputs, flags / types / indexing exact outside the ε-boundary class.  The ε class is
+computed, not hand-waved: a ray / world is excluded only if nudging every body by ±1e-3 changes the
+oracle's own answer (tangent rays, corner ties, contact / capture thresholds).
+"""
+import numpy as np
+import pytest
+import torch
+
+import parity_utils as pu
+from as_cops_and_thieves_b200.maps import compile_map
+from as_cops_and_thieves_b200.worlds import CatWorlds
+from oracle.cat_oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+VBIAS_ATOL = 2e-3   # v_bias = 6/s * penetration; penetration is resolved at fp32 position granularity (~6e-5 at x~1e3)
+
+
+def _acts(rng, N, A, dev):
+    a = rng.integers(0, 4, (N, A))
+    return a, torch.from_numpy(a.astype(np.uint8)).to(dev)
+
+
+def _physics_unstable(orc, base_state, actions, ref_state, n_pert=3, eps=1e-3, tol=2e-2, seed=1):
+    """Worlds whose oracle transition is discontinuous under a ±eps nudge (contact / capture thresholds,
+    multi-contact ordering) — the physics ε class."""
+    rng = np.random.default_rng(seed)
+    bad = np.zeros(base_state.N, bool)
+    for _ in range(n_pert):
+        q = pu.perturbed(base_state, rng, eps)
+        out = orc.step(q, actions)
+        bad |= np.abs(q.pos - ref_state.pos).max(axis=(1, 2)) > tol
+        bad |= np.abs(q.vel - ref_state.vel).max(axis=(1, 2)) > tol * 50
+        bad |= out.terminated != ref_state._terminated
+    return bad
+
+
+def _compare_transition(cw, orc, rng, label):
+    N, A = cw.n_worlds, cw.A
+    st = cw.get_state()
+    torch.cuda.synchronize()
+    base = pu.cuda_state_to_oracle(orc, st, gid0=cw.gid0)
+    acts_np, acts = _acts(rng, N, A, cw.device)
+    pre = orc.observe(base.copy())
+    cw.step(acts)
+    torch.cuda.synchronize()
+    ost = base.copy()
+    oout = orc.step(ost, acts_np)
+    ost._terminated = oout.terminated.copy()
+    st2 = cw.get_state()
+    torch.cuda.synchronize()
+
+    nd = ~oout.terminated.astype(bool)                  # worlds that did not re-spawn this step
+    ndr = nd[:, None, None]
+    otype, odist = cw.obs_type.cpu().numpy(), cw.obs_dist.cpu().numpy()
+    hp = cw.hit_point.cpu().numpy()
+    unstable = pu.ray_unstable_mask(orc, base, pre.hit_alpha, pre.obs_type)
+    assert unstable.mean() < 0.03, f"{label}: ε-class unexpectedly large ({unstable.mean():.3%})"
+    ok = ~unstable & ndr
+    # --- object types and hit points (pre-quantisation)
+    assert not ((otype != oout.obs_type) & ok).any(), f"{label}: object type mismatch on stable rays"
+    hit = (oout.obs_type != pu.TYPE_EMPTY) & ok
+    err = np.linalg.norm(hp - oout.hit_point, axis=-1)
+    assert err[hit].max(initial=0.0) <= pu.RAY_ATOL, f"{label}: hit point error {err[hit].max():.3e}"
+    # --- float16 chain: bit-exact w.r.t. numpy run on CUDA's own fp32 hit points
+    pos0 = st["pos"].cpu().numpy()
+    chain = pu.f16_chain_numpy(hp, pos0)
+    chain = np.where(otype == pu.TYPE_EMPTY, np.float16(orc.params["ray_length"]), chain)
+    assert np.array_equal(chain.view(np.uint16)[nd], odist.view(np.uint16)[nd]), f"{label}: f16 chain not bit-exact"
+    # ... and within one f16 step of the oracle's (quantisation can flip on a 1e-4 fp32/fp64 difference)
+    dq = np.abs(odist.astype(np.float32) - oout.obs_dist.astype(np.float32))
+    assert dq[ok].max(initial=0.0) <= 1.5, f"{label}: f16 distance far from oracle"
+    assert (dq[ok] > 0).mean() < 2e-3
+    # --- flags, winner, counters
+    phys_bad = _physics_unstable(orc, base, acts_np, ost)
+    good = ~phys_bad
+    for k in ("terminated", "truncated", "winner"):
+        assert np.array_equal(getattr(cw, k).cpu().numpy()[good], getattr(oout, k)[good]), f"{label}: {k}"
+    assert np.array_equal(st2["step_count"].cpu().numpy()[good], ost.step_count[good])
+    assert np.array_equal(st2["episode"].cpu().numpy().astype(np.uint32)[good], ost.episode[good])
+    # --- rewards: exact formula check from CUDA's own observations, and agreement with the oracle
+    term = cw.terminated.cpu().numpy().astype(bool)
+    trunc = cw.truncated.cpu().numpy().astype(bool)
+    cap = cw.winner.cpu().numpy() == 0
+    rw = cw.reward.cpu().numpy()
+    exp = pu.expected_rewards_numpy(odist, otype, cw.n_cops, cap, trunc)
+    np.testing.assert_allclose(rw[~term], exp[~term], atol=1e-5, err_msg=f"{label}: reward formula")
+    np.testing.assert_allclose(rw[term], exp[term], atol=0, err_msg=f"{label}: terminal rewards")
+    stable_worlds = good & ~unstable.any(axis=(1, 2))
+    np.testing.assert_allclose(rw[stable_worlds], oout.reward[stable_worlds], atol=pu.REWARD_ATOL)
+    # --- physics
+    sel = good & nd
+    assert sel.mean() > 0.9
+    for k in ("pos", "vel"):
+        c = st2[k].cpu().numpy().astype(np.float64)[sel]
+        o = getattr(ost, k)[sel]
+        rel = np.abs(c - o) / np.maximum(1.0, np.abs(o))
+        assert rel.max(initial=0.0) <= pu.POS_RTOL, f"{label}: {k} rel err {rel.max():.3e}"
+    np.testing.assert_allclose(st2["vbias"].cpu().numpy()[sel], ost.vbias[sel], atol=VBIAS_ATOL)
+    np.testing.assert_allclose(st2["tc"].cpu().numpy()[sel], ost.tc[sel], rtol=pu.POS_RTOL)
+    # --- worlds that re-spawned: same sampled positions (fp32 fma sampling is bit-reproducible)
+    rs = good & ~nd
+    if rs.any():
+        same = np.abs(st2["pos"].cpu().numpy()[rs] - ost.pos[rs]).max(axis=(1, 2)) <= 1e-4
+        assert same.mean() >= 0.98, f"{label}: re-spawn positions differ in {(~same).sum()} of {same.size} worlds"
+        assert np.all(st2["vel"].cpu().numpy()[rs] == 0)
+    # --- arbiter cache bookkeeping (same contacts cached, same ages)
+    wh = st2["wall_hull"].cpu().numpy()
+    assert (wh[sel] >= 0).sum() == (ost.wall_age[sel] >= 0).sum(), f"{label}: cached wall arbiters differ"
+    return dict(unstable=float(unstable.mean()), phys_bad=int(phys_bad.sum()), done=int((~nd).sum()),
+                max_hit_err=float(err[hit].max(initial=0.0)))
+
+
+CASES = [("squarinth", False, 4096, (0, 49, 150)),      # BASELINE config 2: all 4096 worlds at steps 1, 50, 200
+         ("lbirinth", False, 512, (0, 80)),
+         ("grandbyrinth", False, 512, (0, 120)),
+         ("labyrinth", True, 1024, (0, 100)),            # config 3 spot-check (1024 worlds)
+         ("agh-map", True, 1024, (0, 100)),              # config 4 large-segment case, free-space spawns
+         ("agh-map", False, 256, (0, 30))]               # file spawns: agents start INSIDE hulls
+
+
+@pytest.mark.parametrize("name,free,N,gaps", CASES, ids=[f"{c[0]}{'-free' if c[1] else ''}" for c in CASES])
+def test_single_step_transition_parity(cuda_device, name, free, N, gaps):
+    cmap = pu.named_cmap(name, free_spawn=free)
+    cw = CatWorlds(cmap, N, device=cuda_device, want_hits=True, seed=7)
+    orc = Oracle(cmap, seed=7)
+    rng = np.random.default_rng(123)
+    cw.reset()
+    for gap in gaps:
+        for _ in range(gap):
+            cw.step(_acts(rng, N, cw.A, cw.device)[1])
+        stats = _compare_transition(cw, orc, rng, f"{name}@+{gap}")
+        print(name, gap, stats)
+    cw.close()
+
+
+def test_analytic_golden_vectors_through_cuda(cuda_device):
+    m, vectors = pu.load_analytic()
+    cmap = compile_map(m, name="analytic")
+    for vec in vectors:
+        cw = CatWorlds(cmap, 1, device=cuda_device, want_hits=True, **pu.vector_params(vec))
+        pos = torch.tensor([vec["pos"]], dtype=torch.float32)
+        fields = dict(pos=pos, tc=pos, step_count=torch.tensor([int(vec.get("step_count", 0))]))
+        if "vel" in vec:
+            fields["vel"] = torch.tensor([vec["vel"]], dtype=torch.float32)
+        cw.set_state(**fields)
+        if vec["kind"] == "ray":
+            cw.observe()
+        else:
+            cw.step(torch.tensor([vec["actions"]], dtype=torch.uint8, device=cuda_device))
+        torch.cuda.synchronize()
+        st = cw.get_state()
+        res = dict(obs_type=cw.obs_type[0].cpu().numpy(), obs_dist=cw.obs_dist[0].cpu().numpy(),
+                   hit_point=cw.hit_point[0].cpu().numpy(), reward=cw.reward[0].cpu().numpy(),
+                   terminated=int(cw.terminated[0]), truncated=int(cw.truncated[0]), winner=int(cw.winner[0]),
+                   pos=st["pos"][0].cpu().numpy(), vel=st["vel"][0].cpu().numpy(), vbias=st["vbias"][0].cpu().numpy())
+        pu.check_vector(vec, res, pos_tol=2e-3, point_tol=2e-3)   # fp32 at |x|~1e3: ulp 6e-5, bias gain 6
+        cw.close()
+
+
+def test_reset_matches_oracle_and_is_invariant_to_sharding(cuda_device):
+    cmap = pu.named_cmap("squarinth")
+    N = 1000
+    full = CatWorlds(cmap, N, device=cuda_device, seed=99, want_f32=False)
+    full.reset()
+    pf = full.get_state()["pos"].cpu().numpy()
+    orc = Oracle(cmap, seed=99)
+    ost = orc.new_state(N)
+    oout = orc.reset(ost)
+    assert np.array_equal(pf.astype(np.float64), ost.pos), "Philox spawn positions must be bit-identical"
+    assert np.array_equal(full.obs_type.cpu().numpy(), oout.obs_type) or \
+        (full.obs_type.cpu().numpy() != oout.obs_type).mean() < 5e-3
+    # 3 shards with global ids reproduce the unsharded run
+    from as_cops_and_thieves_b200.sharding import shard_range
+    parts = []
+    for r in range(3):
+        g0, n = shard_range(N, r, 3)
+        w = CatWorlds(cmap, n, device=cuda_device, gid0=g0, seed=99, want_f32=False)
+        w.reset()
+        parts.append((w, g0, n))
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        a = torch.from_numpy(rng.integers(0, 4, (N, 3)).astype(np.uint8)).to(cuda_device)
+        full.step(a)
+        for w, g0, n in parts:
+            w.step(a[g0:g0 + n].contiguous())
+    torch.cuda.synchronize()
+    for w, g0, n in parts:
+        assert torch.equal(w.state.view(torch.int32), full.state.view(torch.int32).view(N, -1)[g0:g0 + n].reshape(-1))
+        assert torch.equal(w.obs_dist, full.obs_dist[g0:g0 + n])
+        w.close()
+    full.close()
+
+
+def test_mask_reset_only_touches_masked_worlds(cuda_device):
+    cmap = pu.named_cmap("lbirinth")
+    cw = CatWorlds(cmap, 64, device=cuda_device, seed=1)
+    cw.reset()
+    before = cw.get_state()
+    mask = torch.zeros(64, dtype=torch.uint8, device=cuda_device)
+    mask[::4] = 1
+    cw.reset(mask)
+    after = cw.get_state()
+    torch.cuda.synchronize()
+    m = mask.bool().cpu()
+    assert torch.equal(before["pos"].cpu()[~m], after["pos"].cpu()[~m])
+    assert not torch.equal(before["pos"].cpu()[m], after["pos"].cpu()[m])
+    assert torch.all(after["episode"].cpu()[m] == 2) and torch.all(after["episode"].cpu()[~m] == 1)
+    cw.close()
+
+
+def test_stale_shape_cache_flag(cuda_device):
+    """with the pymunk behaviour the first observations after a reset see the
+    other agents at their previous cached centres; with the sane variant at their true positions."""
+    m, _ = pu.load_analytic()
+    cmap = compile_map(m, name="analytic")
+    for stale in (1, 0):
+        cw = CatWorlds(cmap, 1, device=cuda_device, stale_shape_cache=stale, seed=3)
+        pos = torch.tensor([[[50.0, 50.0], [80.0, 50.0], [1000.0, 700.0]]])
+        cw.set_state(pos=pos, tc=pos)
+        cw.reset()
+        st = cw.get_state()
+        torch.cuda.synchronize()
+        if stale:
+            assert torch.equal(st["tc"].cpu(), pos)
+        else:
+            assert torch.equal(st["tc"].cpu(), st["pos"].cpu())
+        orc = Oracle(cmap, stale_shape_cache=stale, seed=3)
+        ost = orc.new_state(1)
+        ost.pos[0] = pos[0].numpy()
+        ost.tc[0] = pos[0].numpy()
+        oout = orc.reset(ost)
+        assert np.array_equal(st["pos"].cpu().numpy().astype(np.float64), ost.pos)
+        assert np.array_equal(cw.obs_type.cpu().numpy(), oout.obs_type)
+        cw.step(torch.tensor([[1, 1, 1]], dtype=torch.uint8, device=cuda_device))
+        st = cw.get_state()
+        torch.cuda.synchronize()
+        assert torch.equal(st["tc"].cpu(), st["pos"].cpu())   # space.step refreshed the caches
+        cw.close()
+
+
+def test_warm_start_cache_follows_chipmunk_persistence(cuda_device):
+    m, _ = pu.load_analytic()
+    cmap = compile_map(m, name="analytic")
+    cw = CatWorlds(cmap, 1, device=cuda_device, auto_reset=0)
+    pos = torch.tensor([[[94.2, 150.0], [900.0, 700.0], [1000.0, 700.0]]])
+    cw.set_state(pos=pos, tc=pos)
+    push = torch.tensor([[2, 1, 1]], dtype=torch.uint8, device=cuda_device)
+    away = torch.tensor([[0, 1, 1]], dtype=torch.uint8, device=cuda_device)
+    cw.step(push)
+    st = cw.get_state()
+    assert int(st["wall_hull"][0, 0, 0]) == 0 and int(st["wall_age"][0, 0, 0]) == 0
+    assert float(st["wall_jn"][0, 0, 0]) == pytest.approx(10.0, abs=1e-4)
+    cw.step(push)
+    st = cw.get_state()
+    assert float(st["wall_jn"][0, 0, 0]) == pytest.approx(10.0, abs=1e-4) and abs(float(st["vel"][0, 0, 0])) < 1e-5
+    ages = []
+    for _ in range(40):
+        cw.step(away)
+        st = cw.get_state()
+        ages.append(int(st["wall_age"][0, 0, 0]) if int(st["wall_hull"][0, 0, 0]) >= 0 else -1)
+    k = ages.index(-1)
+    assert ages[k - 2:k] == [1, 2]
+    cw.close()
