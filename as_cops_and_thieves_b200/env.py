@@ -122,7 +122,7 @@ class BaseEnv(_EnvCommon):
         self._cmap = compile_map(map)
         self._params = params
         self._setup_common(map, self._cmap, params)
-        self._w = CatWorlds(self._cmap, 1, device=device, params=params, want_f32=False)
+        self._w = CatWorlds(self._cmap, 1, device=device, params=params, want_f32=False, want_shared=True)
         self.agents: List[str] = []
         self._np_random_seed = None
 
@@ -137,13 +137,15 @@ class BaseEnv(_EnvCommon):
         sd = self._w.shared_dist[0].cpu().numpy()
         st = self._w.shared_type[0].cpu().numpy()
         tp = self._w.team_pos[0].cpu().numpy()
-        nc = self._cmap.n_cops
+        nc, na = self._cmap.n_cops, len(self.possible_agents)
+        team_sd, team_st = [sd[0], sd[1]], [st[0], st[1]]      # one array object per team, shared by its members
+        team_tp = [tp[0:nc], tp[nc:na]]
         out = {}
         for i, a in enumerate(self.possible_agents):
             team = 0 if i < nc else 1
-            lo, hi = (0, nc) if team == 0 else (nc, len(self.possible_agents))
             out[a] = {"own_obj_types": obs[a]["object_type"], "own_distances": obs[a]["distance"],
-                      "object_type_shared": st[team], "distance_shared": sd[team], "team_positions": tp[lo:hi]}
+                      "object_type_shared": team_st[team], "distance_shared": team_sd[team],
+                      "team_positions": team_tp[team]}
         return out
 
     # ------------------------------------------------------------------ PettingZoo API

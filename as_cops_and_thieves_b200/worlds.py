@@ -31,7 +31,7 @@ def _require_cuda(device: torch.device) -> None:
 class CatWorlds:
     def __init__(self, cmap: CompiledMap, n_worlds: int, *, device: Union[str, torch.device] = "cuda:0",
                  gid0: int = 0, params: Optional[EnvParams] = None, want_f32: bool = True,
-                 want_hits: bool = False, **overrides):
+                 want_shared: bool = True, want_hits: bool = False, **overrides):
         self.device = torch.device(device)
         _require_cuda(self.device)
         self.L = _lib.load()
@@ -76,18 +76,33 @@ class CatWorlds:
         N, A, R, dev = self.n_worlds, self.A, self.R, self.device
         nbytes = int(self.L.cat_env_state_bytes(self._h))
         self.state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)   # packed per-world records
-        self.obs_dist = torch.zeros((N, A, R), dtype=torch.float16, device=dev)
-        self.obs_type = torch.zeros((N, A, R), dtype=torch.uint8, device=dev)
-        self.reward = torch.zeros((N, A), dtype=torch.float32, device=dev)
-        self.terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self.truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self.winner = torch.full((N,), -1, dtype=torch.int8, device=dev)
-        self.shared_dist = torch.zeros((N, 2, R), dtype=torch.float16, device=dev)
-        self.shared_type = torch.zeros((N, 2, R), dtype=torch.uint8, device=dev)
-        self.team_pos = torch.zeros((N, A, 2), dtype=torch.float16, device=dev)
+        # The per-step results live in ONE device buffer so the host-facing path needs a single D2H copy.
+        def carve(nbytes_, off=[0]):
+            o = off[0]
+            off[0] = (o + nbytes_ + 255) // 256 * 256
+            return o
+        sizes = dict(obs_dist=N * A * R * 2, obs_type=N * A * R, reward=N * A * 4, terminated=N, truncated=N, winner=N)
+        offs = {k_: carve(v) for k_, v in sizes.items()}
+        total = carve(0)
+        self._out = torch.zeros(total, dtype=torch.uint8, device=dev)
+
+        def view(name, dtype, shape):
+            return self._out[offs[name]:offs[name] + sizes[name]].view(dtype).view(shape)
+        self._out_layout = (offs, sizes, total)
+        self.obs_dist = view("obs_dist", torch.float16, (N, A, R))
+        self.obs_type = view("obs_type", torch.uint8, (N, A, R))
+        self.reward = view("reward", torch.float32, (N, A))
+        self.terminated = view("terminated", torch.uint8, (N,))
+        self.truncated = view("truncated", torch.uint8, (N,))
+        self.winner = view("winner", torch.int8, (N,))
+        self.winner.fill_(-1)
+        self.shared_dist = torch.zeros((N, 2, R), dtype=torch.float16, device=dev) if want_shared else None
+        self.shared_type = torch.zeros((N, 2, R), dtype=torch.uint8, device=dev) if want_shared else None
+        self.team_pos = torch.zeros((N, A, 2), dtype=torch.float16, device=dev) if want_shared else None
         self.obs_f32 = torch.zeros((A, N, 2 * R), dtype=torch.float32, device=dev) if want_f32 else None
         self.state_f32 = torch.zeros((N, self.S), dtype=torch.float32, device=dev) if want_f32 else None
         self.hit_point = torch.zeros((N, A, R, 2), dtype=torch.float32, device=dev) if want_hits else None
+        self._host = None
         self._io = self._make_io()
         self._ptr_table = (C.c_void_p * 8)()
         _lib.check(self.L.cat_env_init_state(self._h, self.state.data_ptr(), self._stream()), "cat_env_init_state")
@@ -149,6 +164,41 @@ class CatWorlds:
                 self._ptr_table[a] = t.data_ptr()
             io.actions, io.actions_kind = C.cast(self._ptr_table, C.c_void_p), 3
         _lib.check(self.L.cat_env_step(self._h, self.state.data_ptr(), C.byref(io), self._stream()), "cat_env_step")
+
+    # ------------------------------------------------------------------ host-buffer face (what a CPU caller sees)
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self.n_worlds * self.A
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return int(self._out_layout[2])
+
+    def step_host(self, host_actions: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """``step`` for a caller whose buffers live in host memory (the reference's own calling
+        convention): uint8 actions ``(N, A)`` in (pinned for async copy), and the step's observations,
+        rewards and flags back in pinned host memory when the call returns.  One H2D copy, one launch,
+        one D2H copy, one stream synchronisation."""
+        if self._host is None:
+            offs, sizes, total = self._out_layout
+            N, A, R = self.n_worlds, self.A, self.R
+            hb = torch.zeros(total, dtype=torch.uint8).pin_memory()
+
+            def hview(name, dtype, shape):
+                return hb[offs[name]:offs[name] + sizes[name]].view(dtype).view(shape)
+            self._host = dict(blob=hb, actions_dev=torch.zeros((N, A), dtype=torch.uint8, device=self.device),
+                              obs_dist=hview("obs_dist", torch.float16, (N, A, R)),
+                              obs_type=hview("obs_type", torch.uint8, (N, A, R)),
+                              reward=hview("reward", torch.float32, (N, A)),
+                              terminated=hview("terminated", torch.uint8, (N,)),
+                              truncated=hview("truncated", torch.uint8, (N,)),
+                              winner=hview("winner", torch.int8, (N,)))
+        h = self._host
+        h["actions_dev"].copy_(host_actions, non_blocking=True)
+        self.step(h["actions_dev"])
+        h["blob"].copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h
 
     def observe(self) -> None:
         _lib.check(self.L.cat_env_observe(self._h, self.state.data_ptr(), C.byref(self._io), self._stream()),

@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the batched cops-and-thieves environment step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--worlds n]
+
+A "step" is one lockstep transition of every world on a rank: ONE launch of `cat_world_kernel`
+(termination test, action impulses, 90-ray sensor sweep per agent, float16 observation chain, rewards,
+rigid-body step, auto-reset).  Default workload = BASELINE.json configs[1]: squarinth, 4096 worlds per
+GPU, native observation dtypes.  Weak scaling: the worlds per GPU are fixed, ranks shard the global
+world range, there is no data-path collective.
+
+Prints ONE JSON line (rank 0).  `value` = agent-steps/s over all ranks with everything resident in
+HBM; `e2e` = the same metric through the host-buffer API (pinned actions in, observations / rewards /
+flags out, copies inside the timed region).  L2 is flushed between timed steps (the working set, a few
+MB, is far smaller than the 126 MB L2), so each step is timed separately with CUDA events and summed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ALG_BYTES_PER_AGENT_STEP = 336          # native dtypes, step + raycast obs
+FALLBACK_HBM_GBS = 6650.0               # /opt/skills/guides/B200_PROFILING.md fallback
+WORKLOADS = {                           # name -> (map, free-space spawns, worlds per GPU)
+    "squarinth-4096": ("squarinth", False, 4096),       # BASELINE.json configs[1]  (default)
+    "labyrinth-8192": ("labyrinth", True, 8192),        # configs[2] per-GPU share
+    "grandbyrinth-16384": ("grandbyrinth", False, 16384),  # configs[3]
+    "agh-map-16384": ("agh-map", True, 16384),          # the real large-segment case (496 edges)
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="squarinth-4096", choices=list(WORKLOADS))
+    ap.add_argument("--worlds", type=int, default=None, help="worlds per GPU (overrides the workload's)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other workloads / cpu baseline")
+    return ap.parse_args()
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+def build_cmap(name, free):
+    from as_cops_and_thieves_b200.maps import compile_map, free_space_regions, load_named_map
+    m = load_named_map(name)
+    return compile_map(m, name=name, spawn_override=free_space_regions(m) if free else None)
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port, host cores)
+def time_cpu_port(map_name, free, n_worlds, seconds=12.0, min_steps=3):
+    """The reference's algorithm on the host cores: the fp64 oracle port with OpenMP over worlds.
+    (Pymunk / PettingZoo are not installable here, SURVEY.md §8c, so the reference itself cannot run.)"""
+    import numpy as np
+    from oracle.cat_oracle import Oracle, num_threads
+    cmap = build_cmap(map_name, free)
+    orc = Oracle(cmap, seed=0)
+    st = orc.new_state(n_worlds)
+    out = orc.new_out(n_worlds)
+    orc.reset(st, out=out)
+    rng = np.random.default_rng(1)
+    acts = [rng.integers(0, 4, (n_worlds, orc.A)).astype(np.int32) for _ in range(8)]
+    orc.step(st, acts[0], out)  # warm-up
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < min_steps or time.perf_counter() - t0 < seconds:
+        orc.step(st, acts[steps % 8], out)
+        steps += 1
+    dt = time.perf_counter() - t0
+    return dict(value=n_worlds * orc.A * steps / dt, steps=steps, seconds=dt, cores=num_threads(),
+                worlds=n_worlds, A=orc.A)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    map_name, free, _ = WORKLOADS[args.workload]
+    sample_worlds = 512
+    K, W = max(1, args.steps), max(0, args.warmup)
+    import numpy as np
+    from oracle.cat_oracle import Oracle, num_threads
+    cmap = build_cmap(map_name, free)
+    orc = Oracle(cmap, seed=0)
+    st = orc.new_state(sample_worlds)
+    out = orc.new_out(sample_worlds)
+    orc.reset(st, out=out)
+    rng = np.random.default_rng(1)
+    acts = [rng.integers(0, 4, (sample_worlds, orc.A)).astype(np.int32) for _ in range(8)]
+    # bounded: cap the number of CPU steps so that the whole run ends within a few minutes
+    K = min(K, 400)
+    W = min(W, 20)
+    for i in range(W):
+        orc.step(st, acts[i % 8], out)
+    t0 = time.perf_counter()
+    for i in range(K):
+        orc.step(st, acts[i % 8], out)
+    dt = time.perf_counter() - t0
+    value = sample_worlds * orc.A * K / dt
+    sample = f"{sample_worlds} {map_name} worlds x {K} steps, OpenMP over worlds (oracle port of the Pymunk path)"
+    line = {
+        "impl": "reference", "metric": "agent-steps/s (physics+raycast obs)", "value": value, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "map": map_name, "worlds_per_step": sample_worlds,
+                   "note": "reference Pymunk/PettingZoo path is not installable offline; CPU port of the same algorithm"},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------ GPU arm
+def time_steps(torch, cw, acts, K, W, flush, dist=None):
+    """W warm-up steps, then K steps each timed with its own CUDA-event pair (L2 flushed in between,
+    outside the timed span).  Returns total timed milliseconds on this rank."""
+    for i in range(W):
+        cw.step(acts[i % len(acts)])
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for i in range(K):
+        if flush is not None:
+            flush.add_(1)                       # > L2-sized write: evicts state / outputs / actions from L2
+        starts[i].record()
+        cw.step(acts[i % len(acts)])
+        stops[i].record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+
+
+def time_e2e(torch, cw, K, W, dist=None):
+    """The host-buffer API: pinned uint8 actions -> H2D -> step -> D2H of observations, rewards, flags."""
+    N, A = cw.n_worlds, cw.A
+    host_acts = [torch.randint(0, 4, (N, A), dtype=torch.uint8).pin_memory() for _ in range(8)]
+    for i in range(W):
+        cw.step_host(host_acts[i % 8])
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        cw.step_host(host_acts[i % 8])          # synchronises: results are in host memory when it returns
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1), cw.h2d_bytes_per_step, cw.d2h_bytes_per_step
+
+
+def run_b200(args):
+    import torch
+    from as_cops_and_thieves_b200.sharding import dist_env, shard_range
+    from as_cops_and_thieves_b200.worlds import CatWorlds
+
+    rank, local_rank, world_size = dist_env()
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist = dist_mod
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+
+    map_name, free, per_gpu = WORKLOADS[args.workload]
+    per_gpu = args.worlds or per_gpu
+    n_global = per_gpu * world_size
+    gid0, n_local = shard_range(n_global, rank, world_size)
+    K, W = max(1, args.steps), max(3, args.warmup)
+
+    cmap = build_cmap(map_name, free)
+    cw = CatWorlds(cmap, n_local, device=dev, gid0=gid0, seed=0, want_f32=False, want_shared=False)
+    cw.reset()
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    acts = [torch.randint(0, 4, (n_local, cw.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(16)]
+    flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # 192 MiB > 126 MB L2
+
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
+    sampler.start()
+    ms_total = time_steps(torch, cw, acts, K, W, flush, dist)
+    clocks = sampler.stop()
+    e2e_ms, h2d, d2h = time_e2e(torch, cw, min(K, 1000), 5, dist)
+    e2e_steps = min(K, 1000)
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    A = cw.A
+    value = n_global * A * K / (ms_total * 1e-3)
+    e2e_value = n_global * A * e2e_steps / (e2e_ms * 1e-3)
+    peak, peak_kind = measured_hbm_peak()
+    launch_ms = ms_total / K
+    alg_bytes = n_local * A * ALG_BYTES_PER_AGENT_STEP
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"          # dram bytes per launch from the committed ncu --set full capture
+    if tf.exists():
+        try:
+            traffic = json.load(open(tf)).get(args.workload if not args.worlds else "", None)
+        except Exception:
+            traffic = None
+
+    line = {
+        "metric": "agent-steps/s (physics+raycast obs)", "value": value, "unit": "agent-steps/s",
+        "n_gpus": world_size, "steps": K, "warmup": W, "ms_per_step": launch_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "map": map_name, "hull_edges": int(cmap.n_edges), "worlds_per_gpu": per_gpu,
+                   "global_worlds": n_global, "agents_per_world": A, "rays_per_agent": cw.R, "dt": 1 / 60,
+                   "max_step_count": 400, "spawn": "free-space regions" if free else "map spawn regions",
+                   "outputs": "f16 distance + u8 type + f32 reward + u8 flags (native dtypes)",
+                   "l2": "flushed between timed steps (192 MiB write), each step timed with its own CUDA events",
+                   "parallelism": f"worlds sharded over {world_size} GPU(s), no data-path collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "api": "CatWorlds.step_host: pinned u8 actions in; f16/u8 observations, f32 rewards, u8 flags out"},
+        "gpu_launches": K,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                     "algorithmic_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP, "kernel": "cat_world_kernel",
+                     "note": "ALU/latency-bound path (SURVEY.md §8d): HBM fraction is reported as asked, not a target"},
+    }
+
+    if rank == 0 and world_size == 1 and not args.no_extras:
+        others = {}
+        for wl, (mn, fr, nw) in WORKLOADS.items():
+            if wl == args.workload:
+                continue
+            c2 = build_cmap(mn, fr)
+            w2 = CatWorlds(c2, nw, device=dev, seed=0, want_f32=False, want_shared=False)
+            w2.reset()
+            a2 = [torch.randint(0, 4, (nw, w2.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(8)]
+            ms = time_steps(torch, w2, a2, 300, 20, flush)
+            others[wl] = {"value": nw * w2.A * 300 / (ms * 1e-3), "ms_per_step": ms / 300, "hull_edges": int(c2.n_edges)}
+            w2.close()
+        # the skrl-facing layout: + team-shared observations + fp32 flattened obs (A,N,180) + state (N,1090)
+        w3 = CatWorlds(cmap, n_local, device=dev, seed=0, want_f32=True, want_shared=True)
+        w3.reset()
+        ms = time_steps(torch, w3, acts, 300, 20, flush)
+        others[args.workload + "+skrl-layouts"] = {"value": n_local * A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
+                                                   "bytes_per_agent_step": 786 + 1453}
+        w3.close()
+        line["other_workloads"] = others
+        cpu = time_cpu_port(map_name, free, 512, seconds=12.0)
+        line["cpu_baseline"] = {"value": cpu["value"], "unit": "agent-steps/s", "cores": cpu["cores"], "kind": "port",
+                                "sample": f"{cpu['worlds']} {map_name} worlds x {cpu['steps']} steps in {cpu['seconds']:.1f} s, "
+                                          "fp64 oracle port of the Pymunk path, OpenMP over worlds"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    cw.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
