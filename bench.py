@@ -70,6 +70,7 @@ def time_cpu_port(map_name, free, n_worlds, seconds=12.0, min_steps=3):
     """The reference's algorithm on the host cores: the fp64 oracle port with OpenMP over worlds.
     (Pymunk / PettingZoo are not installable here, SURVEY.md §8c, so the reference itself cannot run.)"""
     import numpy as np
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     from oracle.cat_oracle import Oracle, num_threads
     cmap = build_cmap(map_name, free)
     orc = Oracle(cmap, seed=0)
@@ -93,6 +94,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (libgomp reads this at load)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     map_name, free, _ = WORKLOADS[args.workload]
     sample_worlds = 512
     K, W = max(1, args.steps), max(0, args.warmup)
