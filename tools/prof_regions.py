@@ -39,6 +39,10 @@ for l in open(tmp / "dis.txt"):
     if m and cur_func and "cat_world_kernel" in cur_func:
         addr2line[int(m.group(1), 16)] = cur_line
 rows = list(csv.reader(open(tmp / "src.csv")))
+for _i in range(2, len(rows)):          # several launches in one report: keep the first
+    if rows[_i] and rows[_i][0] == "Kernel Name":
+        rows = rows[:_i]
+        break
 hdr = rows[1]
 ia, ii, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 src = (ROOT / "as_cops_and_thieves_b200/csrc/cat_b200.cu").read_text().split("\n")
