@@ -68,7 +68,8 @@ struct BlobHeader {
   int32_t off_edge, off_len, off_hbb, off_heo;
   int32_t off_nextn, off_edgehull, off_conoff, off_conlist;
   int32_t off_dir, off_regoff, off_regions, off_initpos;
-  int32_t pad[4];
+  int32_t off_batchbb;
+  int32_t pad[3];
 };
 static_assert(sizeof(BlobHeader) == 96, "header must stay 16-byte sized");
 
@@ -77,6 +78,7 @@ struct MapView {
   const float* edge_len;
   const float4* hull_bb;   // l,b,r,t grown by the wall radius (the shape's bb)
   const uint32_t* hull_eo; // edge offset | count << 16
+  const float4* batch_bb;    // bounding box of edges [32b, 32b+32) incl. both end points
   const float2* next_n;      // outward normal of the NEXT edge of the same hull (shares vertex v_i)
   const uint16_t* edge_hull; // hull of each edge
   const uint16_t* con_off;
@@ -138,6 +140,7 @@ __device__ __forceinline__ MapView make_view(const unsigned char* blob) {
   m.hull_bb = reinterpret_cast<const float4*>(blob + h->off_hbb);
   m.hull_eo = reinterpret_cast<const uint32_t*>(blob + h->off_heo);
   m.next_n = reinterpret_cast<const float2*>(blob + h->off_nextn);
+  m.batch_bb = reinterpret_cast<const float4*>(blob + h->off_batchbb);
   m.edge_hull = reinterpret_cast<const uint16_t*>(blob + h->off_edgehull);
   m.con_off = reinterpret_cast<const uint16_t*>(blob + h->off_conoff);
   m.con_list = reinterpret_cast<const uint16_t*>(blob + h->off_conlist);
@@ -483,34 +486,9 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
       if (ddx * ddx + ddy * ddy <= reach2) zero_agent = j;
     }
 
-    // ---- (1) lanes = rays: seed the depth buffer with the dynamic shapes and the alpha = 0 rules
+    // ---- (1) clear the depth buffer (the dynamic shapes and the alpha = 0 rules are merged in step 3)
 #pragma unroll 1
-    for (int sub = 0; sub < nsub; ++sub) {
-      const int i = sub * 32 + lane;
-      if (i < R) {
-        const float4 dv = m.dir[i];
-        Ray r;
-        r.ox = ox; r.oy = oy; r.ux = dv.x; r.uy = dv.y; r.L = L;
-        r.zx = dv.x == 0.f; r.zy = dv.y == 0.f; r.idx = dv.z * inv_L; r.idy = dv.w * inv_L;
-        unsigned long long key = make_key(L, kNoFeature);
-        if (zero_agent >= 0) key = make_key(0.f, kAgentTag + zero_agent);
-        else {
-#pragma unroll 1
-          for (int j = 0; j < A; ++j) {   // the other agents' cached centres
-            if (j == a) continue;
-            const float sc = ray_circle(tc[2 * j], tc[2 * j + 1], reach, r);
-            if (sc < L) key = min(key, make_key(sc, kAgentTag + j));
-          }
-        }
-        // static shapes with the origin inside their reach: alpha = 0, but only if the thin ray enters the bb
-#pragma unroll 1
-        for (uint32_t q = 0; q < ncnt; ++q) {
-          const int h = w.near[a * kNear + q];
-          if (thin_bb_hit(m.hull_bb[h], ox, oy, r.zx, r.zy, r.idx, r.idy)) key = min(key, make_key(0.f, 0u));
-        }
-        w.best[a * R + i] = key;
-      }
-    }
+    for (int i = lane; i < R; i += 32) w.best[a * R + i] = make_key(L, kNoFeature);
     __syncwarp();
 
     // ---- (2) lanes = edges: candidates face the origin (plane i or the next plane, which share vertex v_i
@@ -518,6 +496,11 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
     int ncand = 0;
 #pragma unroll 1
     for (int base = 0; base < E; base += 32) {
+      {  // warp-uniform reject of the whole batch (hulls are stored in Morton order, so batches are compact)
+        const float4 bb = m.batch_bb[base >> 5];
+        const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
+        if (fmaf(ddx, ddx, ddy * ddy) >= range2) continue;
+      }
       const int e = base + lane;
       bool is_cand = false;
       if (e < E) {
@@ -557,10 +540,31 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
       const int i = sub * 32 + lane;
       if (i < R) {
         const int r = a * R + i;
-        const unsigned long long key = w.best[r];
+        const float4 dv = m.dir[i];
+        unsigned long long key = w.best[r];     // nearest wall hit from the rasteriser
+        {
+          Ray rq;
+          rq.ox = ox; rq.oy = oy; rq.ux = dv.x; rq.uy = dv.y; rq.L = L;
+          rq.zx = dv.x == 0.f; rq.zy = dv.y == 0.f; rq.idx = dv.z * inv_L; rq.idy = dv.w * inv_L;
+          // dynamic shapes: the other agents' cached centres (keys order walls before agents at equal s)
+          if (zero_agent >= 0) key = min(key, make_key(0.f, kAgentTag + zero_agent));
+          else {
+#pragma unroll 1
+            for (int j = 0; j < A; ++j) {
+              if (j == a) continue;
+              const float sc = ray_circle(tc[2 * j], tc[2 * j + 1], reach, rq);
+              if (sc < L) key = min(key, make_key(sc, kAgentTag + j));
+            }
+          }
+          // static shapes with the origin inside their reach: alpha = 0, but only if the thin ray enters the bb
+#pragma unroll 1
+          for (uint32_t q = 0; q < ncnt; ++q) {
+            const int h = w.near[a * kNear + q];
+            if (thin_bb_hit(m.hull_bb[h], ox, oy, rq.zx, rq.zy, rq.idx, rq.idy)) key = min(key, make_key(0.f, 0u));
+          }
+        }
         const uint32_t feat = (uint32_t)key;
         const float sHit = __uint_as_float((uint32_t)(key >> 32));
-        const float4 dv = m.dir[i];
         uint16_t dbits;
         uint8_t type;
         float hx = fmaf(L, dv.x, ox), hy = fmaf(L, dv.y, oy);   // ray end: reported when nothing is hit or alpha = 0
@@ -1035,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
         for (int c = 0; c < k.nc && !captured; ++c) {
           const float tx = pos[2 * t], ty = pos[2 * t + 1], cx = pos[2 * c], cy = pos[2 * c + 1];
           const float dx = tx - cx, dy = ty - cy;
-          if (sqrtf(dx * dx + dy * dy) < k.term_r) {
+          if (dx * dx + dy * dy < k.term_r * k.term_r) {
             const bool blocked = los_blocked(smem, lane, tx, ty, cx, cy, k.wall_r);
             if (!__any_sync(0xFFFFFFFFu, blocked)) captured = true;
           }
@@ -1264,6 +1268,7 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   hd.off_regoff = take((A + 1) * 4);
   hd.off_regions = take((nreg > 0 ? nreg : 1) * 16);
   hd.off_initpos = take(A * 8);
+  hd.off_batchbb = take(((E + 31) / 32) * 16);
   const int blob_bytes = align_up(off, 16);
   std::vector<unsigned char> blob(blob_bytes, 0);
   memcpy(blob.data(), &hd, sizeof(hd));
@@ -1310,6 +1315,23 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
     for (int a = 0; a <= A; ++a) rg[a] = map->region_off[a];
     float* rr = reinterpret_cast<float*>(blob.data() + hd.off_regions);
     for (int i = 0; i < nreg * 4; ++i) rr[i] = (float)map->regions[i];
+    float* bbb = reinterpret_cast<float*>(blob.data() + hd.off_batchbb);
+    for (int b = 0; b * 32 < E; ++b) {
+      float l = INFINITY, bo = INFINITY, r = -INFINITY, t = -INFINITY;
+      for (int i = b * 32; i < E && i < b * 32 + 32; ++i) {
+        // edge i spans vert[prev(i)] -> vert[i]; prev = i - 1 within the hull, else the hull's last vertex
+        int h = 0;
+        while (map->hull_off[h + 1] <= i) ++h;
+        const int pi = (i > map->hull_off[h]) ? i - 1 : map->hull_off[h + 1] - 1;
+        const int idx[2] = {i, pi};
+        for (int q = 0; q < 2; ++q) {
+          const float x = (float)map->vert[2 * idx[q]], y = (float)map->vert[2 * idx[q] + 1];
+          l = fminf(l, x); r = fmaxf(r, x); bo = fminf(bo, y); t = fmaxf(t, y);
+        }
+      }
+      bbb[4 * b + 0] = nextafterf(l, -INFINITY); bbb[4 * b + 1] = nextafterf(bo, -INFINITY);
+      bbb[4 * b + 2] = nextafterf(r, INFINITY); bbb[4 * b + 3] = nextafterf(t, INFINITY);
+    }
     float* ip = reinterpret_cast<float*>(blob.data() + hd.off_initpos);
     for (int i = 0; i < 2 * A; ++i) ip[i] = (float)map->init_pos[i];
   }

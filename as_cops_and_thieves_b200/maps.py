@@ -285,6 +285,23 @@ def _cells_touching_segment(a, b, rho, gx0, gy0, cell, nx, ny) -> np.ndarray:
     return (iy[keep] * nx + ix[keep]).astype(np.int64)
 
 
+def _morton_sorted(hulls: List[np.ndarray]) -> List[np.ndarray]:
+    """Order hulls along a Z-curve of their centroids (stable for ties).  Hull ids are internal to the
+    compiled map (oracle and CUDA receive the same one), so any fixed order is as good as the file's."""
+    c = np.asarray([h.mean(axis=0) for h in hulls])
+    lo, span = c.min(axis=0), np.maximum(c.max(axis=0) - c.min(axis=0), 1e-9)
+    q = np.minimum(((c - lo) / span * 65535.0).astype(np.int64), 65535)
+
+    def spread(v):
+        out = 0
+        for b in range(16):
+            out |= ((int(v) >> b) & 1) << (2 * b)
+        return out
+    keys = [spread(x) | (spread(y) << 1) for x, y in q]
+    order = sorted(range(len(hulls)), key=lambda i: (keys[i], i))
+    return [hulls[i] for i in order]
+
+
 def choose_cell_size(hull_bb: np.ndarray, n_hulls: int) -> float:
     """Heuristic from the B200 sweeps (profiles/): ~4 cells per hull, clamped to [24, 200] units."""
     w = float(hull_bb[:, 2].max() - hull_bb[:, 0].min())
@@ -308,6 +325,7 @@ def compile_map(m: Map, *, cell: Optional[float] = None, ray_reach: float = 2.0,
     map file says (used for the synthetic free-space spawns of the agh-map/labyrinth benchmarks).
     """
     hulls = [convex_hull_ccw(ring) for ring in m.blocks]
+    hulls = _morton_sorted(hulls)      # spatially compact edge batches (the kernel culls 32 edges at a time)
     H = len(hulls)
     hull_off = np.zeros(H + 1, np.int32)
     for h, hv in enumerate(hulls):
