@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-CAT_ABI_VERSION = 1
+CAT_ABI_VERSION = 2
 CAT_MAX_AGENTS = 8
 CAT_MAX_RAYS = 128
 CAT_WALL_SLOTS = 4
@@ -56,6 +56,7 @@ class CatStepIO(C.Structure):
         ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("winner", C.c_void_p),
         ("shared_dist", C.c_void_p), ("shared_type", C.c_void_p), ("team_pos", C.c_void_p),
         ("obs_f32", C.c_void_p), ("state_f32", C.c_void_p), ("hit_point", C.c_void_p),
+        ("obs_dist_world_stride", C.c_int32), ("obs_type_world_stride", C.c_int32),
     ]
 
 

@@ -116,6 +116,8 @@ struct KParams {
   const uint8_t* reset_mask;
   uint16_t* obs_dist;
   uint8_t* obs_type;
+  int dist_stride, type_stride;   // bytes between worlds
+  int obs_vec;                    // 1: both strides and bases are 16-byte aligned -> uint4 stores
   float* reward;
   uint8_t* terminated;
   uint8_t* truncated;
@@ -243,6 +245,18 @@ __device__ __forceinline__ float fast_atan2(float y, float x) {
   if (ay > ax) r = 1.57079637f - r;
   if (x < 0.f) r = 3.14159274f - r;
   return copysignf(r, y);
+}
+
+// float16(npy_hypotf(dx, dy)) for float16-valued dx, dy: numpy evaluates hypotf (glibc: sqrt in double, rounded to
+// float) and then rounds to half.  dx*dx and dy*dy are exact in fp32 (11-bit significands), so
+// sqrt.rn.f32(fma(dx, dx, dy*dy)) is within 1.5 fp32 ulp of that float; the two can only round to different
+// halves when the low 13 bits sit within 2 ulp of the tie point (or in the half-subnormal range): only then is the
+// double-precision path taken (about 6 rays in 10^4).
+__device__ __forceinline__ uint16_t half_hypot_bits(float dxh, float dyh) {
+  float hyp = __fsqrt_rn(fmaf(dxh, dxh, dyh * dyh));
+  const uint32_t low = __float_as_uint(hyp) & 0x1FFFu;
+  if ((low - 0x0FFEu <= 4u) || hyp < 6.2e-5f) hyp = (float)sqrt((double)dxh * (double)dxh + (double)dyh * (double)dyh);
+  return __half_as_ushort(__float2half_rn(hyp));
 }
 
 struct Ray {
@@ -587,8 +601,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
           const float pxh = __half2float(__float2half_rn(hx)), pyh = __half2float(__float2half_rn(hy));
           const float dxh = __half2float(__float2half_rn(pxh - oxh));
           const float dyh = __half2float(__float2half_rn(pyh - oyh));
-          const float hyp = (float)sqrt((double)dxh * (double)dxh + (double)dyh * (double)dyh);
-          dbits = __half_as_ushort(__float2half_rn(hyp));
+          dbits = half_hypot_bits(dxh, dyh);
           type = !is_agent ? TYPE_WALL : ((int)(feat - kAgentTag) >= k.nc ? TYPE_THIEF : TYPE_COP);
           // rewards need the nearest opponent seen by this agent (cop.py:66-70, thief.py:60-63)
           if (type == want) atomicMin(&w.minbits[a], (uint32_t)dbits);
@@ -654,26 +667,45 @@ __device__ __noinline__ void write_flat_layouts(const KParams& k, const uint16_t
 __device__ __forceinline__ void write_observation(const KParams& k, const Warp& w, long long world) {
   const int A = k.A, R = k.R, lane = w.lane, nrays = k.nrays;
   const float* pos = w.rec;
-  if (k.obs_dist) {
-    if ((nrays & 1) == 0) {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(k.obs_dist + (size_t)world * nrays);
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(w.rdist);
+  if (k.obs_vec) {
+    // 16-byte aligned world blocks (mapped pinned host memory): one or two 512-byte warp stores per array
+    if (k.obs_dist) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(k.obs_dist) + (size_t)world * k.dist_stride);
+      const uint4* src = reinterpret_cast<const uint4*>(w.rdist);
 #pragma unroll 1
-      for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
-    } else {
-#pragma unroll 1
-      for (int i = lane; i < nrays; i += 32) k.obs_dist[(size_t)world * nrays + i] = w.rdist[i];
+      for (int i = lane; i < (nrays * 2 + 15) / 16; i += 32) dst[i] = src[i];
     }
-  }
-  if (k.obs_type) {
-    if ((nrays & 1) == 0) {
-      uint16_t* dst = reinterpret_cast<uint16_t*>(k.obs_type + (size_t)world * nrays);
-      const uint16_t* src = reinterpret_cast<const uint16_t*>(w.rtype);
+    if (k.obs_type) {
+      uint4* dst = reinterpret_cast<uint4*>(k.obs_type + (size_t)world * k.type_stride);
+      const uint4* src = reinterpret_cast<const uint4*>(w.rtype);
 #pragma unroll 1
-      for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
-    } else {
+      for (int i = lane; i < (nrays + 15) / 16; i += 32) dst[i] = src[i];
+    }
+  } else {
+    if (k.obs_dist) {
+      unsigned char* base = reinterpret_cast<unsigned char*>(k.obs_dist) + (size_t)world * k.dist_stride;
+      if (((nrays | (k.dist_stride >> 1)) & 1) == 0) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(base);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(w.rdist);
 #pragma unroll 1
-      for (int i = lane; i < nrays; i += 32) k.obs_type[(size_t)world * nrays + i] = w.rtype[i];
+        for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
+      } else {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(base);
+#pragma unroll 1
+        for (int i = lane; i < nrays; i += 32) dst[i] = w.rdist[i];
+      }
+    }
+    if (k.obs_type) {
+      uint8_t* base = k.obs_type + (size_t)world * k.type_stride;
+      if (((nrays | k.type_stride) & 1) == 0) {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(base);
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(w.rtype);
+#pragma unroll 1
+        for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
+      } else {
+#pragma unroll 1
+        for (int i = lane; i < nrays; i += 32) base[i] = w.rtype[i];
+      }
     }
   }
   if (k.team_pos) {  // observation_spaces.py:92-95
@@ -829,8 +861,52 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
   const uint32_t pair_mask = __ballot_sync(0xFFFFFFFFu, pair_hit != 0);
   __syncwarp();
 
-  // (7) warm start + (8) sequential impulses: serial by construction, lane 0
-  if (lane == 0) {
+  // (7) warm start + (8) sequential impulses.
+  // An iteration that changes no accumulated impulse leaves v / v_bias untouched too, so every later
+  // iteration would recompute exactly the same zeros: stopping there is bit-identical to running all of them.
+  if (pair_mask == 0) {
+    // No agent-agent contact: the wall contacts of different agents touch disjoint state, so their
+    // sequential-impulse sweeps are independent -> lane a solves agent a, velocities in registers.
+    const uint32_t n = lane < A ? w.ccount[lane] : 0u;
+    if (n > 0) {
+      const float minv = k.inv_mass;
+      float* cbase = w.con + lane * kSlots * 8;
+      float vx = vel[2 * lane], vy = vel[2 * lane + 1], bx = vb[2 * lane], by = vb[2 * lane + 1];
+#pragma unroll 1
+      for (uint32_t q = 0; q < n; ++q) {  // cpArbiterApplyCachedImpulse (dt_coef = 1)
+        const float* c = cbase + q * 8;
+        if (reinterpret_cast<const uint32_t*>(c)[6] & (1u << 16)) continue;  // first contact: nothing applied
+        vx -= c[0] * c[3] * minv; vy -= c[1] * c[3] * minv;
+      }
+#pragma unroll 1
+      for (int it = 0; it < k.iterations; ++it) {
+        bool changed = false;
+#pragma unroll 1
+        for (uint32_t q = 0; q < n; ++q) {  // cpArbiterApplyImpulse against a static body, e = 0, u = 0
+          float* c = cbase + q * 8;
+          const float nx = c[0], ny = c[1], nMass = c[5];
+          const float vbn = (-bx) * nx + (-by) * ny;
+          const float vrn = (-vx) * nx + (-vy) * ny;
+          const float jbnOld = c[4], jnOld = c[3];
+          const float jBias = fmaxf(jbnOld + (c[2] - vbn) * nMass, 0.f);
+          const float jnAcc = fmaxf(jnOld - vrn * nMass, 0.f);
+          c[4] = jBias; c[3] = jnAcc;
+          const float jb = (jBias - jbnOld) * minv, j = (jnAcc - jnOld) * minv;
+          bx -= nx * jb; by -= ny * jb;
+          vx -= nx * j; vy -= ny * j;
+          changed |= (jb != 0.f) | (j != 0.f);
+        }
+        if (!changed) break;
+      }
+      vel[2 * lane] = vx; vel[2 * lane + 1] = vy; vb[2 * lane] = bx; vb[2 * lane + 1] = by;
+#pragma unroll 1
+      for (uint32_t q = 0; q < n; ++q) {  // persist jnAcc in the arbiter cache
+        const float* c = cbase + q * 8;
+        wjn[reinterpret_cast<const uint32_t*>(c)[7]] = c[3];
+      }
+    }
+  } else if (lane == 0) {
+    // Agent-agent contacts couple the bodies: one fixed global order (wall contacts agent-major, then pairs), lane 0
     int n = 0;
 #pragma unroll 1
     for (int a = 0; a < A; ++a)
@@ -839,51 +915,52 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
 #pragma unroll 1
     for (int p = 0; p < P; ++p)
       if (pair_mask & (1u << p)) w.order[n++] = (uint8_t)(A * kSlots + p);
-    if (n > 0) {
-      const float minv = k.inv_mass;
+    const float minv = k.inv_mass;
 #pragma unroll 1
-      for (int q = 0; q < n; ++q) {  // cpArbiterApplyCachedImpulse (dt_coef = 1)
+    for (int q = 0; q < n; ++q) {  // cpArbiterApplyCachedImpulse (dt_coef = 1)
+      float* c = w.con + w.order[q] * 8;
+      const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
+      if (meta & (1u << 16)) continue;  // first contact: nothing applied
+      const int a = meta & 0xFF, b = (meta >> 8) & 0xFF;
+      const float jx = c[0] * c[3] * minv, jy = c[1] * c[3] * minv;
+      vel[2 * a] -= jx; vel[2 * a + 1] -= jy;
+      if (b != 0xFF) { vel[2 * b] += jx; vel[2 * b + 1] += jy; }
+    }
+#pragma unroll 1
+    for (int it = 0; it < k.iterations; ++it) {
+      bool changed = false;
+#pragma unroll 1
+      for (int q = 0; q < n; ++q) {  // cpArbiterApplyImpulse, e = 0, u = 0
         float* c = w.con + w.order[q] * 8;
         const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
-        if (meta & (1u << 16)) continue;  // first contact: nothing applied
         const int a = meta & 0xFF, b = (meta >> 8) & 0xFF;
-        const float jx = c[0] * c[3] * minv, jy = c[1] * c[3] * minv;
-        vel[2 * a] -= jx; vel[2 * a + 1] -= jy;
-        if (b != 0xFF) { vel[2 * b] += jx; vel[2 * b + 1] += jy; }
-      }
-#pragma unroll 1
-      for (int it = 0; it < k.iterations; ++it) {
-#pragma unroll 1
-        for (int q = 0; q < n; ++q) {  // cpArbiterApplyImpulse, e = 0, u = 0
-          float* c = w.con + w.order[q] * 8;
-          const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
-          const int a = meta & 0xFF, b = (meta >> 8) & 0xFF;
-          const float nx = c[0], ny = c[1], nMass = c[5];
-          float vbx = -vb[2 * a], vby = -vb[2 * a + 1], vrx = -vel[2 * a], vry = -vel[2 * a + 1];
-          if (b != 0xFF) { vbx += vb[2 * b]; vby += vb[2 * b + 1]; vrx += vel[2 * b]; vry += vel[2 * b + 1]; }
-          const float vbn = vbx * nx + vby * ny;
-          const float vrn = vrx * nx + vry * ny;
-          const float jbnOld = c[4];
-          const float jBias = fmaxf(jbnOld + (c[2] - vbn) * nMass, 0.f);
-          const float jnOld = c[3];
-          const float jnAcc = fmaxf(jnOld - vrn * nMass, 0.f);
-          c[4] = jBias; c[3] = jnAcc;
-          const float jb = (jBias - jbnOld) * minv, j = (jnAcc - jnOld) * minv;
-          vb[2 * a] -= nx * jb; vb[2 * a + 1] -= ny * jb;
-          vel[2 * a] -= nx * j; vel[2 * a + 1] -= ny * j;
-          if (b != 0xFF) {
-            vb[2 * b] += nx * jb; vb[2 * b + 1] += ny * jb;
-            vel[2 * b] += nx * j; vel[2 * b + 1] += ny * j;
-          }
+        const float nx = c[0], ny = c[1], nMass = c[5];
+        float vbx = -vb[2 * a], vby = -vb[2 * a + 1], vrx = -vel[2 * a], vry = -vel[2 * a + 1];
+        if (b != 0xFF) { vbx += vb[2 * b]; vby += vb[2 * b + 1]; vrx += vel[2 * b]; vry += vel[2 * b + 1]; }
+        const float vbn = vbx * nx + vby * ny;
+        const float vrn = vrx * nx + vry * ny;
+        const float jbnOld = c[4];
+        const float jBias = fmaxf(jbnOld + (c[2] - vbn) * nMass, 0.f);
+        const float jnOld = c[3];
+        const float jnAcc = fmaxf(jnOld - vrn * nMass, 0.f);
+        c[4] = jBias; c[3] = jnAcc;
+        const float jb = (jBias - jbnOld) * minv, j = (jnAcc - jnOld) * minv;
+        vb[2 * a] -= nx * jb; vb[2 * a + 1] -= ny * jb;
+        vel[2 * a] -= nx * j; vel[2 * a + 1] -= ny * j;
+        if (b != 0xFF) {
+          vb[2 * b] += nx * jb; vb[2 * b + 1] += ny * jb;
+          vel[2 * b] += nx * j; vel[2 * b + 1] += ny * j;
         }
+        changed |= (jb != 0.f) | (j != 0.f);
       }
+      if (!changed) break;
+    }
 #pragma unroll 1
-      for (int q = 0; q < n; ++q) {  // persist jnAcc in the arbiter cache
-        const float* c = w.con + w.order[q] * 8;
-        const uint32_t meta = reinterpret_cast<const uint32_t*>(c)[6];
-        const uint32_t slot = reinterpret_cast<const uint32_t*>(c)[7];
-        if (((meta >> 8) & 0xFF) == 0xFF) wjn[slot] = c[3]; else pjn[slot] = c[3];
-      }
+    for (int q = 0; q < n; ++q) {  // persist jnAcc in the arbiter cache
+      const float* c = w.con + w.order[q] * 8;
+      const uint32_t meta = reinterpret_cast<const uint32_t*>(c)[6];
+      const uint32_t slot = reinterpret_cast<const uint32_t*>(c)[7];
+      if (((meta >> 8) & 0xFF) == 0xFF) wjn[slot] = c[3]; else pjn[slot] = c[3];
     }
   }
   __syncwarp();
@@ -999,10 +1076,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
   w.blob = smem;
   w.lane = lane;
 
+  // the staging tails beyond A*R rays are shipped by the 16-byte store path: keep them zero
+  for (int i = k.nrays + lane; i < k.nrays_pad; i += 32) { w.rdist[i] = 0; w.rtype[i] = 0; }
   const int A = k.A;
-  const long long stride = (long long)gridDim.x * kWarpsPerCta;
+  const int wpc = blockDim.x >> 5;   // warps per CTA: chosen per environment by the host (pick_launch_shape)
+  const long long stride = (long long)gridDim.x * wpc;
 #pragma unroll 1
-  for (long long world = (long long)blockIdx.x * kWarpsPerCta + warp; world < k.n_worlds; world += stride) {
+  for (long long world = (long long)blockIdx.x * wpc + warp; world < k.n_worlds; world += stride) {
     float* grec = k.state + (size_t)world * k.rec_words;
     int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
 
@@ -1151,46 +1231,136 @@ __global__ void cat_state_view_kernel(const ViewParams p) {
 }
 
 // ------------------------------------------------------------------ GAE
-// One thread per (world, agent) column scans T backwards; loads of step t-1 are independent of
-// the recurrence so the compiler keeps several in flight.  Block partials of sum / sum^2 in fp64.
-__global__ void __launch_bounds__(256) cat_gae_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
-                                                      const float* __restrict__ values,
-                                                      const float* __restrict__ last_values, float* __restrict__ returns,
-                                                      float* __restrict__ advantages, double* __restrict__ stats, int T,
-                                                      int M, float gamma, float lam) {
-  const int mcol = blockIdx.x * blockDim.x + threadIdx.x;
+// adv_t = delta_t + c_t * adv_{t+1} with delta_t = r_t - V_t + gamma * nd_t * V_{t+1}, c_t = gamma * lambda * nd_t is a
+// first-order linear recurrence, i.e. a scan of affine maps, so it parallelises over T as well as over
+// the (world, agent) columns.  One CTA owns 32 columns (lanes: 128-B coalesced rows) and walks T backwards
+// in chunks of kGaeSegs segments x kGaeS steps: warp s loads segment s of the chunk (all 8 x {r, V, done}
+// loads issued up front), folds it into one affine map (A, B); the kGaeSegs maps of a column are combined
+// by a shuffle scan (through shared memory, kGaeSegs lanes per column), and every thread then replays its
+// steps from registers and writes advantages / returns.  Every input byte is read once and every output
+// byte written once: 9 B read + 8 B written per sample.  CTAs are small (256 threads, 4+ per SM) so the
+// load, scan and store phases of different CTAs overlap.  sum / sum^2 of the advantages are reduced per
+// CTA and added in fp64 for the normalisation pass.
+constexpr int kGaeCols = 32, kGaeSegs = 8, kGaeS = 8;
+constexpr int kGaeColsPerWarp = kGaeCols / kGaeSegs;  // scan phase: each warp scans 4 columns, 8 lanes per column
+
+struct GaeChunk {          // one thread's 8 steps of one chunk, as loaded
+  float r[kGaeS], v[kGaeS], vnext;
+  uint32_t done;           // bit i: done flag of step i
+};
+
+__device__ __forceinline__ void gae_load(GaeChunk& ck, const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
+                                         const float* __restrict__ values, int base, int seg, int M, int col, bool valid,
+                                         float carry_v) {
+  // Branch-free: every address is clamped into the array so that all 24 loads issue back to back (a predicated
+  // load per step would make the compiler wait for each step's `done` byte before issuing the next step's loads);
+  // steps before t = 0 / columns beyond M are masked afterwards.
+  const int ccol = valid ? col : 0;
+  uint32_t raw[kGaeS];
+#pragma unroll
+  for (int i = 0; i < kGaeS; ++i) {
+    const size_t idx = (size_t)max(base + i, 0) * M + ccol;
+    ck.r[i] = __ldcs(rewards + idx); ck.v[i] = __ldcs(values + idx); raw[i] = __ldcs(dones + idx);
+  }
+  ck.done = 0;
+#pragma unroll
+  for (int i = 0; i < kGaeS; ++i) ck.done |= (raw[i] ? 1u : 0u) << i;
+  ck.vnext = carry_v;  // V_{t+1} of this thread's last step: the first V of the later segment (seg 0: patched by the caller)
+  if (seg > 0) ck.vnext = __ldg(values + (size_t)max(base + kGaeS, 0) * M + ccol);
+}
+
+__global__ void __launch_bounds__(kGaeCols* kGaeSegs, 3)
+    cat_gae_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, const float* __restrict__ values,
+                   const float* __restrict__ last_values, float* __restrict__ returns, float* __restrict__ advantages,
+                   double* __restrict__ stats, int T, int M, float gamma, float lam) {
+  __shared__ float sA[kGaeSegs][kGaeCols + 1], sB[kGaeSegs][kGaeCols + 1];
+  __shared__ float sCarryAdv[kGaeCols], sCarryV[kGaeCols];
+  __shared__ double sh1[kGaeSegs], sh2[kGaeSegs];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int col = blockIdx.x * kGaeCols + lane;
+  const bool valid = col < M;
+  const float gl = gamma * lam;
+  constexpr int kChunk = kGaeSegs * kGaeS;
+  float carry_adv = 0.f, carry_v = valid ? last_values[col] : 0.f;
   double s1 = 0.0, s2 = 0.0;
-  if (mcol < M) {
-    float adv = 0.f;
-    float next_v = last_values[mcol];
-    for (int t = T - 1; t >= 0; --t) {
-      const size_t i = (size_t)t * M + mcol;
-      const float r = rewards[i], v = values[i];
-      const float nd = dones[i] ? 0.f : 1.f;
-      adv = r - v + gamma * nd * (next_v + lam * adv);
-      advantages[i] = adv;
-      returns[i] = adv + v;
-      next_v = v;
-      s1 += (double)adv;
-      s2 += (double)adv * (double)adv;
+  GaeChunk cur;
+  gae_load(cur, rewards, dones, values, T - (seg + 1) * kGaeS, seg, M, col, valid, carry_v);
+#pragma unroll 1
+  for (int t_hi = T; t_hi > 0; t_hi -= kChunk) {
+    const int base = t_hi - (seg + 1) * kGaeS;  // this thread's steps: base .. base + 7 (those >= 0)
+    if (seg == 0) cur.vnext = carry_v;            // known only now: V at the first step of the later chunk
+    // software pipeline: the next (earlier) chunk's loads are in flight during this chunk's scan and stores
+    GaeChunk nxt;
+    if (t_hi > kChunk) gae_load(nxt, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
+    float A = 1.f, B = 0.f;
+#pragma unroll
+    for (int i = kGaeS - 1; i >= 0; --i) {
+      if (base + i >= 0) {
+        const float nd = (cur.done >> i) & 1u ? 0.f : 1.f;
+        const float vn = (i == kGaeS - 1) ? cur.vnext : cur.v[i + 1];
+        cur.r[i] = cur.r[i] - cur.v[i] + gamma * nd * vn;  // delta_t
+        B = fmaf(gl * nd, B, cur.r[i]);
+        A *= gl * nd;
+      }
     }
+    sA[seg][lane] = A; sB[seg][lane] = B;
+    if (seg == kGaeSegs - 1) sCarryV[lane] = cur.v[0];  // V at the chunk's first step = V_{t+1} of the next chunk
+    if (seg == 0) sCarryAdv[lane] = carry_adv;
+    __syncthreads();
+    {  // lane group g of warp `seg` scans column seg * 4 + g: sub-lane l holds the map of segment l
+       // (x_{l+1} = B_l + A_l * x_l, x_0 = the advantage carried in from the later chunk)
+      const int sl = lane & (kGaeSegs - 1), scol = seg * kGaeColsPerWarp + lane / kGaeSegs;
+      float a = sA[sl][scol], b = sB[sl][scol];
+#pragma unroll
+      for (int d = 1; d < kGaeSegs; d <<= 1) {
+        const float ap = __shfl_up_sync(0xFFFFFFFFu, a, d, kGaeSegs), bp = __shfl_up_sync(0xFFFFFFFFu, b, d, kGaeSegs);
+        if (sl >= d) { b = fmaf(a, bp, b); a *= ap; }
+      }
+      const float x0 = sCarryAdv[scol];
+      const float xout = fmaf(a, x0, b);                                // advantage at the first step of segment l
+      float xin = __shfl_up_sync(0xFFFFFFFFu, xout, 1, kGaeSegs);       // = advantage entering segment l
+      if (sl == 0) xin = x0;
+      __syncwarp();
+      sA[sl][scol] = xin;
+      if (sl == kGaeSegs - 1) sB[0][scol] = xout;                       // advantage entering the next (earlier) chunk
+    }
+    __syncthreads();
+    float adv = sA[seg][lane];
+    carry_adv = sB[0][lane];
+    carry_v = sCarryV[lane];
+    float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int i = kGaeS - 1; i >= 0; --i) {
+      const int t = base + i;
+      if (valid && t >= 0) {
+        const float nd = (cur.done >> i) & 1u ? 0.f : 1.f;
+        adv = fmaf(gl * nd, adv, cur.r[i]);
+        const size_t idx = (size_t)t * M + col;
+        advantages[idx] = adv;
+        __stcs(returns + idx, adv + cur.v[i]);
+        p1 += adv; p2 = fmaf(adv, adv, p2);
+      }
+    }
+    s1 += (double)p1; s2 += (double)p2;
+    cur = nxt;
+    __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1) {
     s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
     s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
   }
-  __shared__ double sh1[8], sh2[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { sh1[warp] = s1; sh2[warp] = s2; }
+  if (lane == 0) { sh1[seg] = s1; sh2[seg] = s2; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0, b = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh1[i]; b += sh2[i]; }
+    for (int i = 0; i < kGaeSegs; ++i) { a += sh1[i]; b += sh2[i]; }
     atomicAdd(&stats[0], a);
     atomicAdd(&stats[1], b);
   }
 }
 
+// In-place (adv - mean) / (std + 1e-8): 4 B read + 4 B written per sample, four independent 16-B loads in
+// flight per thread.
 __global__ void __launch_bounds__(256) cat_adv_normalize_kernel(float* __restrict__ adv, long long n,
                                                                 const double* __restrict__ stats, long long count) {
   const double mean = stats[0] / (double)count;
@@ -1200,13 +1370,24 @@ __global__ void __launch_bounds__(256) cat_adv_normalize_kernel(float* __restric
   const long long n4 = n >> 2;
   float4* a4 = reinterpret_cast<float4*>(adv);
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = a4[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u].x = (v[u].x - fm) * inv; v[u].y = (v[u].y - fm) * inv; v[u].z = (v[u].z - fm) * inv; v[u].w = (v[u].w - fm) * inv;
+      a4[i + u * stride] = v[u];
+    }
+  }
+  for (; i < n4; i += stride) {
     float4 v = a4[i];
     v.x = (v.x - fm) * inv; v.y = (v.y - fm) * inv; v.z = (v.z - fm) * inv; v.w = (v.w - fm) * inv;
     a4[i] = v;
   }
-  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    adv[i] = (adv[i] - fm) * inv;
+  for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    adv[j] = (adv[j] - fm) * inv;
 }
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -1222,6 +1403,7 @@ struct CatEnv {
   CatEnvInfo info{};
   int smem_bytes = 0;
   int grid = 0;
+  int threads = kThreads;
 };
 
 extern "C" {
@@ -1379,26 +1561,42 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   k.iterations = pr->iterations; k.persistence = pr->collision_persistence; k.max_steps = pr->max_step_count;
   k.stale = pr->stale_shape_cache; k.auto_reset = pr->auto_reset; k.seed = pr->seed;
 
-  env->smem_bytes = align_up(blob_bytes, 128) + kWarpsPerCta * k.scratch_bytes;
-  int max_optin = 0;
+  // Launch shape.  A warp owns a world, so with few worlds (one resident wave) the step takes as long as the
+  // SM holding the most warps: smaller CTAs spread N warps more evenly over the SMs (4096 worlds = 27.7 warps per
+  // SM: 8-warp CTAs put 32 on some SMs, 4-warp CTAs at most 28).  With many worlds the grid is persistent and the
+  // shape with the most resident warps wins (ties: the larger CTA, fewer copies of the map).
+  int max_optin = 0, n_sm = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  if (env->smem_bytes > max_optin) {
-    cudaFree(env->blob_dev); delete env;
-    return fail(CAT_ERR_LIMIT, "map does not fit in shared memory (" + std::to_string(env->smem_bytes) + " B)");
-  }
-  ce = cudaFuncSetAttribute(cat_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_bytes);
-  if (ce != cudaSuccess) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
-  int n_sm = 0, occ = 0;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_world_kernel, kThreads, env->smem_bytes);
-  if (ce != cudaSuccess || occ < 1) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, "occupancy query failed"); }
-  const int need = (n_worlds + kWarpsPerCta - 1) / kWarpsPerCta;
-  env->grid = need < n_sm * occ ? need : n_sm * occ;  // persistent: at most one resident wave
+  const int smem_max = align_up(blob_bytes, 128) + kWarpsPerCta * k.scratch_bytes;
+  if (align_up(blob_bytes, 128) + 2 * k.scratch_bytes > max_optin) {
+    cudaFree(env->blob_dev); delete env;
+    return fail(CAT_ERR_LIMIT, "map does not fit in shared memory (" + std::to_string(smem_max) + " B)");
+  }
+  ce = cudaFuncSetAttribute(cat_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max < max_optin ? smem_max : max_optin);
+  if (ce != cudaSuccess) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
+  long long best_score = -1;
+  for (int wpc = kWarpsPerCta; wpc >= 2; wpc >>= 1) {
+    const int smem = align_up(blob_bytes, 128) + wpc * k.scratch_bytes;
+    if (smem > max_optin) continue;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_world_kernel, wpc * 32, smem) != cudaSuccess || occ < 1) continue;
+    const int need = (n_worlds + wpc - 1) / wpc;
+    const bool one_wave = need <= n_sm * occ;
+    // one wave: fewest warps on the fullest SM; persistent: most resident warps per SM
+    const int key = one_wave ? 4096 - ((need + n_sm - 1) / n_sm) * wpc : occ * wpc;
+    const long long score = ((long long)(one_wave ? 1 : 0) << 40) + ((long long)key << 8) + wpc;
+    if (score > best_score) {
+      best_score = score;
+      env->threads = wpc * 32; env->smem_bytes = smem; env->grid = one_wave ? need : n_sm * occ;
+    }
+  }
+  if (best_score < 0) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, "occupancy query failed"); }
 
   CatEnvInfo& inf = env->info;
   inf.n_worlds = n_worlds; inf.n_agents = A; inf.n_cops = map->n_cops; inf.n_thieves = map->n_thieves;
   inf.n_rays = R; inf.n_hulls = H; inf.n_edges = E; inf.state_dim = k.state_dim; inf.record_words = k.rec_words;
-  inf.map_blob_bytes = blob_bytes; inf.smem_bytes_per_cta = env->smem_bytes; inf.warps_per_cta = kWarpsPerCta;
+  inf.map_blob_bytes = blob_bytes; inf.smem_bytes_per_cta = env->smem_bytes; inf.warps_per_cta = env->threads / 32;
   inf.grid = env->grid; inf.n_pairs = P;
   *out = env;
   return CAT_OK;
@@ -1442,13 +1640,20 @@ static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, v
       else k.actions[0] = io->actions;
     }
     k.reset_mask = io->reset_mask;
-    k.obs_dist = io->obs_dist; k.obs_type = io->obs_type; k.reward = io->reward; k.terminated = io->terminated;
+    k.obs_dist = io->obs_dist; k.obs_type = io->obs_type; k.reward = io->reward;
+    k.dist_stride = io->obs_dist_world_stride ? io->obs_dist_world_stride : k.nrays * 2;
+    k.type_stride = io->obs_type_world_stride ? io->obs_type_world_stride : k.nrays;
+    if (k.dist_stride < k.nrays * 2 || (k.dist_stride & 1) || k.type_stride < k.nrays)
+      return fail(CAT_ERR_INVALID, "observation world strides are smaller than one world's block");
+    k.obs_vec = ((k.dist_stride | k.type_stride) & 15) == 0 &&
+                ((reinterpret_cast<uintptr_t>(io->obs_dist) | reinterpret_cast<uintptr_t>(io->obs_type)) & 15) == 0 &&
+                k.dist_stride >= (k.nrays * 2 + 15) / 16 * 16 && k.type_stride >= (k.nrays + 15) / 16 * 16; k.terminated = io->terminated;
     k.truncated = io->truncated; k.winner = io->winner; k.shared_dist = io->shared_dist; k.shared_type = io->shared_type;
     k.team_pos = io->team_pos; k.obs_f32 = io->obs_f32; k.state_f32 = io->state_f32; k.hit_point = io->hit_point;
   } else if (mode == MODE_STEP) {
     return fail(CAT_ERR_INVALID, "step needs a CatStepIO");
   }
-  cat_world_kernel<<<env->grid, kThreads, env->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(k);
+  cat_world_kernel<<<env->grid, env->threads, env->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(k);
   CUDA_TRY(cudaGetLastError());
   return CAT_OK;
 }
@@ -1487,7 +1692,7 @@ int cat_gae(const float* rewards, const uint8_t* dones, const float* values, con
   if (T < 1 || M < 1) return fail(CAT_ERR_INVALID, "T and M must be >= 1");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(double), s));
-  const int threads = 256, blocks = (M + threads - 1) / threads;
+  const int threads = kGaeCols * kGaeSegs, blocks = (M + kGaeCols - 1) / kGaeCols;
   cat_gae_kernel<<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M,
                                              gamma, lam);
   CUDA_TRY(cudaGetLastError());
@@ -1501,7 +1706,7 @@ int cat_adv_normalize(float* advantages, int64_t n, const double* stats_dev, int
   const int threads = 256;
   long long blocks = (n / 4 + threads - 1) / threads;
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   cat_adv_normalize_kernel<<<(int)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(advantages, n, stats_dev, count);
   CUDA_TRY(cudaGetLastError());
   return CAT_OK;

@@ -116,7 +116,7 @@ class CatWorlds:
             return None if t is None else t.data_ptr()
         return CatStepIO(None, 0, None, dp(self.obs_dist), dp(self.obs_type), dp(self.reward), dp(self.terminated),
                          dp(self.truncated), dp(self.winner), dp(self.shared_dist), dp(self.shared_type),
-                         dp(self.team_pos), dp(self.obs_f32), dp(self.state_f32), dp(self.hit_point))
+                         dp(self.team_pos), dp(self.obs_f32), dp(self.state_f32), dp(self.hit_point), 0, 0)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -172,31 +172,95 @@ class CatWorlds:
 
     @property
     def d2h_bytes_per_step(self) -> int:
-        return int(self._out_layout[2])
+        """Bytes of results that cross to the host per ``step_host`` (observations, rewards, flags)."""
+        return self.n_worlds * (self.A * self.R * 3 + self.A * 4 + 3)
 
-    def step_host(self, host_actions: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """``step`` for a caller whose buffers live in host memory (the reference's own calling
-        convention): uint8 actions ``(N, A)`` in (pinned for async copy), and the step's observations,
-        rewards and flags back in pinned host memory when the call returns.  One H2D copy, one launch,
-        one D2H copy, one stream synchronisation."""
+    def _host_buffers(self, zero_copy: bool) -> Dict[str, torch.Tensor]:
+        key = "zc" if zero_copy else "staged"
         if self._host is None:
+            self._host = {}
+        if key in self._host:
+            return self._host[key]
+        N, A, R = self.n_worlds, self.A, self.R
+        if not zero_copy:
             offs, sizes, total = self._out_layout
-            N, A, R = self.n_worlds, self.A, self.R
             hb = torch.zeros(total, dtype=torch.uint8).pin_memory()
 
             def hview(name, dtype, shape):
                 return hb[offs[name]:offs[name] + sizes[name]].view(dtype).view(shape)
-            self._host = dict(blob=hb, actions_dev=torch.zeros((N, A), dtype=torch.uint8, device=self.device),
-                              obs_dist=hview("obs_dist", torch.float16, (N, A, R)),
-                              obs_type=hview("obs_type", torch.uint8, (N, A, R)),
-                              reward=hview("reward", torch.float32, (N, A)),
-                              terminated=hview("terminated", torch.uint8, (N,)),
-                              truncated=hview("truncated", torch.uint8, (N,)),
-                              winner=hview("winner", torch.int8, (N,)))
-        h = self._host
-        h["actions_dev"].copy_(host_actions, non_blocking=True)
-        self.step(h["actions_dev"])
-        h["blob"].copy_(self._out, non_blocking=True)
+            h = dict(blob=hb, actions_dev=torch.zeros((N, A), dtype=torch.uint8, device=self.device),
+                     obs_dist=hview("obs_dist", torch.float16, (N, A, R)),
+                     obs_type=hview("obs_type", torch.uint8, (N, A, R)),
+                     reward=hview("reward", torch.float32, (N, A)),
+                     terminated=hview("terminated", torch.uint8, (N,)),
+                     truncated=hview("truncated", torch.uint8, (N,)),
+                     winner=hview("winner", torch.int8, (N,)))
+        else:
+            # Pinned host memory is mapped into the device's address space (unified virtual addressing), so the
+            # kernel can read the actions from it and store its results straight into it.  Each world's
+            # observation block starts on a 16-byte boundary (world stride rounded up), so the kernel ships it
+            # with 512-byte warp stores, which the PCIe root port sees as full-size writes; the (N, A, R)
+            # tensors handed back are strided views of that buffer.
+            layout = getattr(self, "_zc_layout", "record128")
+            d16, t16 = (A * R * 2 + 15) // 16 * 16, (A * R + 15) // 16 * 16
+            if layout.startswith("record"):
+                # one record per world: [distance f16 | type u8 | pad], record size a multiple of 128 B
+                al = int(layout[6:] or 128)
+                ds = ts = (d16 + t16 + al - 1) // al * al
+                sizes = dict(obs=N * ds, reward=N * A * 4, terminated=N, truncated=N, winner=N)
+            else:                                        # "split<align>": two arrays, world stride rounded up
+                al = int(layout[5:] or 16)
+                ds, ts = (d16 + al - 1) // al * al, (t16 + al - 1) // al * al
+                sizes = dict(obs_dist=N * ds, obs_type=N * ts, reward=N * A * 4, terminated=N, truncated=N, winner=N)
+            offs, total = {}, 0
+            for name, nb in sizes.items():
+                offs[name] = total
+                total = (total + nb + 255) // 256 * 256
+            hb = torch.zeros(total, dtype=torch.uint8).pin_memory()
+
+            def flat(name, dtype, skip=0):
+                return hb[offs[name] + skip:offs[name] + sizes[name]].view(dtype)
+            if layout.startswith("record"):
+                od = hb[offs["obs"]:offs["obs"] + sizes["obs"]].view(torch.float16).as_strided((N, A, R), (ds // 2, R, 1))
+                ot = hb[offs["obs"]:offs["obs"] + sizes["obs"]].as_strided((N, A, R), (ts, R, 1), d16)
+            else:
+                od = flat("obs_dist", torch.float16).as_strided((N, A, R), (ds // 2, R, 1))
+                ot = flat("obs_type", torch.uint8).as_strided((N, A, R), (ts, R, 1))
+            h = dict(blob=hb, actions_pinned=torch.zeros((N, A), dtype=torch.uint8).pin_memory(),
+                     obs_dist=od, obs_type=ot,
+                     reward=flat("reward", torch.float32).view(N, A),
+                     terminated=flat("terminated", torch.uint8), truncated=flat("truncated", torch.uint8),
+                     winner=flat("winner", torch.int8))
+            h["io"] = CatStepIO(None, 0, None, h["obs_dist"].data_ptr(), h["obs_type"].data_ptr(), h["reward"].data_ptr(),
+                                h["terminated"].data_ptr(), h["truncated"].data_ptr(), h["winner"].data_ptr(),
+                                None, None, None, None, None, None, ds, ts)
+        self._host[key] = h
+        return h
+
+    def step_host(self, host_actions: torch.Tensor, zero_copy: bool = True) -> Dict[str, torch.Tensor]:
+        """``step`` for a caller whose buffers live in host memory (the reference's own calling
+        convention): uint8 actions ``(N, A)`` in, and the step's observations, rewards and flags in pinned
+        host memory when the call returns.
+
+        ``zero_copy=True`` (default): ONE kernel launch and one stream synchronisation — the kernel reads
+        the actions from, and stores every result directly into, mapped pinned host memory, so the
+        device-to-host transfer of a world's outputs overlaps the computation of the other worlds
+        instead of following the kernel as a separate copy.  ``zero_copy=False``: H2D copy, launch into
+        device buffers, one D2H copy of the output blob (the device-side outputs stay valid too)."""
+        h = self._host_buffers(zero_copy)
+        if zero_copy:
+            if not host_actions.is_pinned():
+                h["actions_pinned"].copy_(host_actions)
+                host_actions = h["actions_pinned"]
+            if host_actions.dtype != torch.uint8 or not host_actions.is_contiguous() or host_actions.numel() != self.n_worlds * self.A:
+                raise ValueError("host actions must be a contiguous uint8 (N, A) tensor")
+            io = h["io"]
+            io.actions, io.actions_kind = host_actions.data_ptr(), 0
+            _lib.check(self.L.cat_env_step(self._h, self.state.data_ptr(), C.byref(io), self._stream()), "cat_env_step")
+        else:
+            h["actions_dev"].copy_(host_actions, non_blocking=True)
+            self.step(h["actions_dev"])
+            h["blob"].copy_(self._out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return h
 

@@ -205,24 +205,68 @@ def time_steps(torch, cw, acts, K, W, flush, dist=None):
     return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
 
 
-def time_e2e(torch, cw, K, W, dist=None):
-    """The host-buffer API: pinned uint8 actions -> H2D -> step -> D2H of observations, rewards, flags."""
+def time_e2e(torch, cw, K, W, dist=None, zero_copy=True):
+    """The host-buffer API: pinned uint8 actions in, observations / rewards / flags back in pinned host memory
+    when each call returns.  zero_copy: the kernel reads / writes the mapped pinned buffers itself (transfers
+    overlap compute); otherwise H2D copy -> launch -> one D2H copy."""
     N, A = cw.n_worlds, cw.A
     host_acts = [torch.randint(0, 4, (N, A), dtype=torch.uint8).pin_memory() for _ in range(8)]
     for i in range(W):
-        cw.step_host(host_acts[i % 8])
+        cw.step_host(host_acts[i % 8], zero_copy=zero_copy)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        cw.step_host(host_acts[i % 8])          # synchronises: results are in host memory when it returns
+        cw.step_host(host_acts[i % 8], zero_copy=zero_copy)   # synchronises: results are in host memory on return
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     return e0.elapsed_time(e1), cw.h2d_bytes_per_step, cw.d2h_bytes_per_step
+
+
+def time_gae(torch, dev, flush, T=256, M=49152, iters=30):
+    """north-star item 4: the GAE scan (9 B read + 8 B written per sample) and the in-place advantage
+    normalisation (4 B + 4 B), each timed with its own CUDA events.  L2 is flushed before every launch by READING a 192 MiB buffer
+    (a write flush would leave 126 MB of dirty lines whose write-back then competes with the timed kernel)."""
+    from as_cops_and_thieves_b200 import _lib
+    L = _lib.load()
+    g = torch.Generator(device=dev).manual_seed(7)
+    r = torch.randn((T, M), device=dev, generator=g)
+    v = torch.randn((T, M), device=dev, generator=g)
+    d = (torch.rand((T, M), device=dev, generator=g) < 0.01).to(torch.uint8)
+    lv = torch.randn((M,), device=dev, generator=g)
+    ret, adv = torch.empty_like(r), torch.empty_like(r)
+    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    t_gae, t_norm = [], []
+    for i in range(-3, iters):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        flush.sum()      # read-only L2 flush: leaves clean lines, so no write-back of flush data inside the timed span
+        e[0].record()
+        _lib.check(L.cat_gae(r.data_ptr(), d.data_ptr(), v.data_ptr(), lv.data_ptr(), ret.data_ptr(), adv.data_ptr(),
+                             stats.data_ptr(), T, M, 0.99, 0.95, stream), "cat_gae")
+        e[1].record()
+        flush.sum()
+        e[2].record()
+        _lib.check(L.cat_adv_normalize(adv.data_ptr(), adv.numel(), stats.data_ptr(), T * M, stream), "cat_adv_normalize")
+        e[3].record()
+        torch.cuda.synchronize()
+        if i >= 0:
+            t_gae.append(e[0].elapsed_time(e[1]))       # includes the 16-B stats memset
+            t_norm.append(e[2].elapsed_time(e[3]))
+    ms_gae, ms_norm = sorted(t_gae)[iters // 2], sorted(t_norm)[iters // 2]     # medians
+    n = T * M
+    peak, _ = measured_hbm_peak()
+    gbs_gae, gbs_norm = 17 * n / ms_gae / 1e6, 8 * n / ms_norm / 1e6
+    return {"T": T, "columns": M, "samples": n, "timing": f"median of {iters} launches, CUDA events, inputs > L2 and L2 read-flushed",
+            "gae_ms": ms_gae, "normalize_ms": ms_norm,
+            "gae_gbs": gbs_gae, "gae_frac_of_hbm_peak": gbs_gae / peak, "normalize_gbs": gbs_norm,
+            "normalize_frac_of_hbm_peak": gbs_norm / peak, "combined_gbs": 25 * n / (ms_gae + ms_norm) / 1e6,
+            "combined_frac_of_hbm_peak": 25 * n / (ms_gae + ms_norm) / 1e6 / peak,
+            "bytes_per_sample": {"gae": 17, "normalize": 8}, "samples_per_s": n / (ms_gae + ms_norm) * 1e3}
 
 
 def run_b200(args):
@@ -258,13 +302,14 @@ def run_b200(args):
     sampler.start()
     ms_total = time_steps(torch, cw, acts, K, W, flush, dist)
     clocks = sampler.stop()
-    e2e_ms, h2d, d2h = time_e2e(torch, cw, min(K, 1000), 5, dist)
     e2e_steps = min(K, 1000)
+    e2e_ms, h2d, d2h = time_e2e(torch, cw, e2e_steps, 5, dist, zero_copy=True)
+    e2e_staged_ms, _, _ = time_e2e(torch, cw, e2e_steps, 5, dist, zero_copy=False)
 
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, e2e_staged_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, e2e_staged_ms = float(t[0]), float(t[1]), float(t[2])
 
     A = cw.A
     value = n_global * A * K / (ms_total * 1e-3)
@@ -294,7 +339,11 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "CatWorlds.step_host: pinned u8 actions in; f16/u8 observations, f32 rewards, u8 flags out"},
+                "api": "CatWorlds.step_host(zero_copy=True): the kernel reads pinned u8 actions and stores f16/u8 "
+                       "observations, f32 rewards, u8 flags straight into mapped pinned host memory (transfer overlaps "
+                       "compute); one launch + one stream sync per step",
+                "staged_copy": {"value": n_global * A * e2e_steps / (e2e_staged_ms * 1e-3), "ms_per_step": e2e_staged_ms / e2e_steps,
+                                "api": "step_host(zero_copy=False): H2D copy, launch, one D2H copy of the output blob"}},
         "gpu_launches": K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
@@ -322,6 +371,7 @@ def run_b200(args):
                                                    "bytes_per_agent_step": 786 + 1453}
         w3.close()
         line["other_workloads"] = others
+        line["gae"] = time_gae(torch, dev, flush)
         cpu = time_cpu_port(map_name, free, 512, seconds=12.0)
         line["cpu_baseline"] = {"value": cpu["value"], "unit": "agent-steps/s", "cores": cpu["cores"], "kind": "port",
                                 "sample": f"{cpu['worlds']} {map_name} worlds x {cpu['steps']} steps in {cpu['seconds']:.1f} s, "

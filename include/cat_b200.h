@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CAT_ABI_VERSION 1
+#define CAT_ABI_VERSION 2
 #define CAT_MAX_AGENTS 8
 #define CAT_MAX_RAYS 128
 #define CAT_WALL_SLOTS 4 /* cached wall arbiters kept per agent */
@@ -104,6 +104,12 @@ typedef struct {
   float* obs_f32;
   float* state_f32;
   float* hit_point;
+  /* bytes between consecutive worlds in obs_dist / obs_type; 0 = dense (A*R*2 and A*R).  A stride that is a
+   * multiple of 16 (with a 16-byte aligned base) lets the kernel store each world's observation with 16-byte
+   * vector stores (the world's block is then written up to the next multiple of 16 bytes, padding included):
+   * the layout CatWorlds.step_host uses for mapped pinned host memory, where wide stores make wide PCIe writes. */
+  int32_t obs_dist_world_stride;
+  int32_t obs_type_world_stride;
 } CatStepIO;
 
 typedef struct {

@@ -138,6 +138,29 @@ def test_action_input_forms_are_equivalent(cuda_device):
         e.close()
 
 
+def test_host_buffer_step_zero_copy_equals_staged_copy(cuda_device):
+    """CatWorlds.step_host: the kernel storing straight into mapped pinned host memory must deliver exactly
+    what the H2D copy -> launch -> D2H copy path delivers (and what the device-resident outputs hold)."""
+    cmap = pu.named_cmap("squarinth")
+    N = 777
+    zc = CatWorlds(cmap, N, device=cuda_device, seed=5, want_f32=False, want_shared=False)
+    st = CatWorlds(cmap, N, device=cuda_device, seed=5, want_f32=False, want_shared=False)
+    zc.reset()
+    st.reset()
+    g = torch.Generator().manual_seed(3)
+    for i in range(60):
+        a = torch.randint(0, 4, (N, 3), dtype=torch.uint8, generator=g)
+        hz = zc.step_host(a.pin_memory() if i % 2 else a, zero_copy=True)
+        hs = st.step_host(a.pin_memory(), zero_copy=False)
+        for k in ("obs_dist", "obs_type", "reward", "terminated", "truncated", "winner"):
+            assert hz[k].shape == hs[k].shape
+            assert torch.equal(hz[k].contiguous().view(torch.uint8), hs[k].contiguous().view(torch.uint8)), (i, k)
+            assert torch.equal(hs[k].contiguous().view(torch.uint8), getattr(st, k).cpu().view(torch.uint8)), (i, k)
+    assert torch.equal(zc.state, st.state)
+    zc.close()
+    st.close()
+
+
 def test_auto_reset_emits_terminal_reward_and_new_episode_observation(cuda_device):
     m = load_named_map("squarinth")
     N = 256
@@ -164,7 +187,8 @@ def test_auto_reset_emits_terminal_reward_and_new_episode_observation(cuda_devic
 
 def test_gae_kernels_match_oracle_and_torch(cuda_device):
     g = torch.Generator().manual_seed(0)
-    for T, shape in ((64, (300, 3)), (16, (1000,)), (5, (7, 1))):
+    # T spans: one partial segment, one chunk (256 = 32 segments x 8 steps), ragged multi-chunk carries
+    for T, shape in ((64, (300, 3)), (16, (1000,)), (5, (7, 1)), (1, (33,)), (256, (40,)), (257, (31, 3)), (600, (65,))):
         r = torch.randn((T,) + shape, generator=g)
         v = torch.randn((T,) + shape, generator=g)
         d = torch.rand((T,) + shape, generator=g) < 0.08

@@ -61,13 +61,13 @@ ob = find("__device__ __forceinline__ void observe_world")
 marks = [("hull_closest", find("__device__ __noinline__ float3 hull_closest_impl")),
          ("thin_bb_hit", find("__device__ __forceinline__ bool thin_bb_hit")),
          ("fast_sqrt", find("__device__ __forceinline__ float fast_sqrt")),
-         ("ray_edge", find("__device__ __forceinline__ void ray_edge")),
+         ("ray_edge", find("__device__ __forceinline__ float ray_edge")),
          ("wall_hit_normal", find("__device__ __forceinline__ float2 wall_hit_normal")),
-         ("ray_circle", find("__device__ __forceinline__ void ray_circle")),
+         ("ray_circle", find("__device__ __forceinline__ float ray_circle")),
          ("make_ray/los", find("__device__ __forceinline__ Ray make_ray")),
          ("grid_cell", find("__device__ __forceinline__ int grid_cell")),
-         ("raster_batch", find("__device__ __forceinline__ void raster_batch")), ("observe:near", ob),
-         ("observe:agent-uniform", find("// ---- warp-uniform, per agent", ob)), ("observe:seed", find("// ---- (1) lanes = rays", ob)), ("observe:candidates", find("// ---- (2) lanes = edges", ob)), ("observe:epilogue3", find("// ---- (3) lanes = rays", ob)),
+         ("raster_batch", find("__device__ __noinline__ void raster_batch")), ("raster:pairs", find("for (int p0 = 0; p0 < total; p0 += 32)")), ("observe:near", ob),
+         ("observe:agent-uniform", find("// ---- warp-uniform, per agent", ob)), ("observe:clear", find("// ---- (1) clear the depth buffer", ob)), ("observe:candidates", find("// ---- (2) lanes = edges", ob)), ("observe:epilogue3", find("// ---- (3) lanes = rays", ob)),
          ("observe:rayinit", find("for (int sub = 0; sub < nsub; ++sub)", ob)),
          ("observe:gridsetup", find("// ---- uniform-grid walk set-up", ob)),
          ("observe:traverse", find("// ---- converged traversal", ob)),

@@ -34,4 +34,4 @@ for i in range(50):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 50
-print(f"{a.map} N={a.worlds} cell={cmap.cell:.1f}: {ms*1e3:.1f} us/step {a.worlds*cw.A/ms*1e3:.3e} agent-steps/s grid {cw.info.grid}")
+print(f"{a.map} N={a.worlds} cell={cmap.cell:.1f}: {ms*1e3:.1f} us/step {a.worlds*cw.A/ms*1e3:.3e} agent-steps/s grid {cw.info.grid} x {cw.info.warps_per_cta} warps")
