@@ -75,7 +75,7 @@ class CatStateView(C.Structure):
 #: every symbol ``include/cat_b200.h`` declares
 EXPORTS = (
     "cat_abi_version", "cat_last_error", "cat_env_create", "cat_env_destroy", "cat_env_info",
-    "cat_env_set_seed", "cat_env_state_bytes", "cat_env_init_state", "cat_env_reset", "cat_env_step", "cat_env_observe",
+    "cat_env_set_seed", "cat_env_state_bytes", "cat_env_init_state", "cat_env_reset", "cat_env_step", "cat_env_step_host", "cat_env_observe",
     "cat_env_get_state", "cat_env_set_state", "cat_gae", "cat_adv_normalize",
 )
 
@@ -112,6 +112,7 @@ def load():
     L.cat_env_init_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     for fn in (L.cat_env_reset, L.cat_env_step, L.cat_env_observe):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStepIO), C.c_void_p]
+    L.cat_env_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStepIO), C.POINTER(CatStepIO), C.c_int32, C.c_void_p]
     for fn in (L.cat_env_get_state, L.cat_env_set_state):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStateView), C.c_void_p]
     L.cat_gae.argtypes = [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p]

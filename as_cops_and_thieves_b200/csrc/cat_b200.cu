@@ -97,6 +97,7 @@ struct KParams {
   float* state;
   int rec_words;
   int n_worlds;
+  int world_begin, world_end;   // the slice of worlds this launch steps (chunked host path); default [0, n_worlds)
   long long gid0;
   int A, nc, R, P, nrays, nrays_pad, maxc, n_edges;
   int mode;
@@ -1082,7 +1083,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
   const int wpc = blockDim.x >> 5;   // warps per CTA: chosen per environment by the host (pick_launch_shape)
   const long long stride = (long long)gridDim.x * wpc;
 #pragma unroll 1
-  for (long long world = (long long)blockIdx.x * wpc + warp; world < k.n_worlds; world += stride) {
+  for (long long world = k.world_begin + (long long)blockIdx.x * wpc + warp; world < k.world_end; world += stride) {
     float* grec = k.state + (size_t)world * k.rec_words;
     int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
 
@@ -1404,7 +1405,34 @@ struct CatEnv {
   int smem_bytes = 0;
   int grid = 0;
   int threads = kThreads;
+  int blob_bytes = 0, max_optin = 0, n_sm = 0;
+  // chunked host path: a second stream for the device-to-host copies and one event per chunk
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  cudaEvent_t copies_done = nullptr;
 };
+
+struct LaunchShape { int threads, smem, grid; };
+
+static bool pick_launch_shape(const CatEnv* env, int n_worlds, LaunchShape* out) {
+  long long best_score = -1;
+  for (int wpc = kWarpsPerCta; wpc >= 2; wpc >>= 1) {
+    const int smem = align_up(env->blob_bytes, 128) + wpc * env->kp.scratch_bytes;
+    if (smem > env->max_optin) continue;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_world_kernel, wpc * 32, smem) != cudaSuccess || occ < 1) continue;
+    const int need = (n_worlds + wpc - 1) / wpc;
+    const bool one_wave = need <= env->n_sm * occ;
+    // one wave: fewest warps on the fullest SM; persistent: most resident warps per SM
+    const int key = one_wave ? 4096 - ((need + env->n_sm - 1) / env->n_sm) * wpc : occ * wpc;
+    const long long score = ((long long)(one_wave ? 1 : 0) << 40) + ((long long)key << 8) + wpc;
+    if (score > best_score) {
+      best_score = score;
+      out->threads = wpc * 32; out->smem = smem; out->grid = one_wave ? need : env->n_sm * occ;
+    }
+  }
+  return best_score >= 0;
+}
 
 extern "C" {
 
@@ -1575,23 +1603,11 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   }
   ce = cudaFuncSetAttribute(cat_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max < max_optin ? smem_max : max_optin);
   if (ce != cudaSuccess) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
-  long long best_score = -1;
-  for (int wpc = kWarpsPerCta; wpc >= 2; wpc >>= 1) {
-    const int smem = align_up(blob_bytes, 128) + wpc * k.scratch_bytes;
-    if (smem > max_optin) continue;
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_world_kernel, wpc * 32, smem) != cudaSuccess || occ < 1) continue;
-    const int need = (n_worlds + wpc - 1) / wpc;
-    const bool one_wave = need <= n_sm * occ;
-    // one wave: fewest warps on the fullest SM; persistent: most resident warps per SM
-    const int key = one_wave ? 4096 - ((need + n_sm - 1) / n_sm) * wpc : occ * wpc;
-    const long long score = ((long long)(one_wave ? 1 : 0) << 40) + ((long long)key << 8) + wpc;
-    if (score > best_score) {
-      best_score = score;
-      env->threads = wpc * 32; env->smem_bytes = smem; env->grid = one_wave ? need : n_sm * occ;
-    }
-  }
-  if (best_score < 0) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, "occupancy query failed"); }
+  env->blob_bytes = blob_bytes; env->max_optin = max_optin; env->n_sm = n_sm;
+  LaunchShape shp;
+  if (!pick_launch_shape(env, n_worlds, &shp)) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, "occupancy query failed"); }
+  env->threads = shp.threads; env->smem_bytes = shp.smem; env->grid = shp.grid;
+  k.world_begin = 0; k.world_end = n_worlds;
 
   CatEnvInfo& inf = env->info;
   inf.n_worlds = n_worlds; inf.n_agents = A; inf.n_cops = map->n_cops; inf.n_thieves = map->n_thieves;
@@ -1606,6 +1622,9 @@ int cat_env_destroy(CatEnv* env) {
   if (!env) return CAT_OK;
   cudaSetDevice(env->device);
   if (env->blob_dev) cudaFree(env->blob_dev);
+  for (cudaEvent_t e : env->chunk_events) cudaEventDestroy(e);
+  if (env->copies_done) cudaEventDestroy(env->copies_done);
+  if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
   delete env;
   return CAT_OK;
 }
@@ -1626,7 +1645,7 @@ size_t cat_env_state_bytes(const CatEnv* env) {
   return env ? (size_t)env->n_worlds * env->kp.rec_words * 4 : 0;
 }
 
-static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, void* stream) {
+static int prepare(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, KParams* out) {
   if (!env || !state_dev) return fail(CAT_ERR_INVALID, "null env/state");
   KParams k = env->kp;
   k.state = reinterpret_cast<float*>(state_dev);
@@ -1647,12 +1666,21 @@ static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, v
       return fail(CAT_ERR_INVALID, "observation world strides are smaller than one world's block");
     k.obs_vec = ((k.dist_stride | k.type_stride) & 15) == 0 &&
                 ((reinterpret_cast<uintptr_t>(io->obs_dist) | reinterpret_cast<uintptr_t>(io->obs_type)) & 15) == 0 &&
-                k.dist_stride >= (k.nrays * 2 + 15) / 16 * 16 && k.type_stride >= (k.nrays + 15) / 16 * 16; k.terminated = io->terminated;
+                k.dist_stride >= (k.nrays * 2 + 15) / 16 * 16 && k.type_stride >= (k.nrays + 15) / 16 * 16;
+    k.terminated = io->terminated;
     k.truncated = io->truncated; k.winner = io->winner; k.shared_dist = io->shared_dist; k.shared_type = io->shared_type;
     k.team_pos = io->team_pos; k.obs_f32 = io->obs_f32; k.state_f32 = io->state_f32; k.hit_point = io->hit_point;
   } else if (mode == MODE_STEP) {
     return fail(CAT_ERR_INVALID, "step needs a CatStepIO");
   }
+  *out = k;
+  return CAT_OK;
+}
+
+static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, void* stream) {
+  KParams k;
+  const int rc = prepare(env, state_dev, io, mode, &k);
+  if (rc != CAT_OK) return rc;
   cat_world_kernel<<<env->grid, env->threads, env->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(k);
   CUDA_TRY(cudaGetLastError());
   return CAT_OK;
@@ -1662,6 +1690,64 @@ int cat_env_init_state(CatEnv* env, void* state_dev, void* stream) { return laun
 int cat_env_reset(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream) { return launch(env, state_dev, io, MODE_RESET, stream); }
 int cat_env_step(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream) { return launch(env, state_dev, io, MODE_STEP, stream); }
 int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream) { return launch(env, state_dev, io, MODE_OBSERVE, stream); }
+
+// BaseEnv.step for a caller whose buffers are pinned HOST memory, pipelined: the worlds are stepped in
+// `n_chunks` consecutive launches on `stream`; as soon as a chunk's launch has finished, its slice of every
+// output array is copied to the host arrays on an internal copy stream (DMA engine, full PCIe rate) while
+// the next chunk computes.  `stream` finally waits for the copies, so one cudaStreamSynchronize(stream) by
+// the caller makes every result visible.  dev: the dense device outputs; host: the same arrays in pinned
+// host memory (dense); host->actions: u8 [N][A] in pinned host memory, read by the kernel directly.
+int cat_env_step_host(CatEnv* env, void* state_dev, const CatStepIO* dev, const CatStepIO* host, int32_t n_chunks,
+                      void* stream_) {
+  if (!env || !dev || !host) return fail(CAT_ERR_INVALID, "null argument");
+  if (!host->actions || host->actions_kind != 0) return fail(CAT_ERR_INVALID, "host actions must be u8 [N][A] (kind 0)");
+  if (dev->obs_dist_world_stride || dev->obs_type_world_stride || host->obs_dist_world_stride || host->obs_type_world_stride)
+    return fail(CAT_ERR_INVALID, "the chunked host path uses dense observation arrays");
+  const int N = env->n_worlds;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > N) n_chunks = N;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(env->device));
+  if (!env->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
+  if (!env->copies_done) CUDA_TRY(cudaEventCreateWithFlags(&env->copies_done, cudaEventDisableTiming));
+  while ((int)env->chunk_events.size() < n_chunks) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    env->chunk_events.push_back(e);
+  }
+  CatStepIO io = *dev;
+  io.actions = host->actions; io.actions_kind = 0;
+  KParams k;
+  const int rc = prepare(env, state_dev, &io, MODE_STEP, &k);
+  if (rc != CAT_OK) return rc;
+  const int A = k.A, nrays = k.nrays;
+  const int per = ((N + n_chunks - 1) / n_chunks + 7) / 8 * 8;   // worlds per chunk, a multiple of the CTA's 8 warps
+  int c = 0;
+  for (int w0 = 0; w0 < N; w0 += per, ++c) {
+    const int w1 = w0 + per < N ? w0 + per : N, n = w1 - w0;
+    LaunchShape shp;
+    if (!pick_launch_shape(env, n, &shp)) return fail(CAT_ERR_CUDA, "occupancy query failed");
+    k.world_begin = w0; k.world_end = w1;
+    cat_world_kernel<<<shp.grid, shp.threads, shp.smem, stream>>>(k);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(env->chunk_events[c], stream));
+    CUDA_TRY(cudaStreamWaitEvent(env->copy_stream, env->chunk_events[c], 0));
+    auto copy = [&](void* h, const void* d, size_t elem_bytes) -> cudaError_t {
+      if (!h || !d) return cudaSuccess;
+      return cudaMemcpyAsync(static_cast<char*>(h) + (size_t)w0 * elem_bytes, static_cast<const char*>(d) + (size_t)w0 * elem_bytes,
+                             (size_t)n * elem_bytes, cudaMemcpyDeviceToHost, env->copy_stream);
+    };
+    CUDA_TRY(copy(host->obs_dist, dev->obs_dist, (size_t)nrays * 2));
+    CUDA_TRY(copy(host->obs_type, dev->obs_type, (size_t)nrays));
+    CUDA_TRY(copy(host->reward, dev->reward, (size_t)A * 4));
+    CUDA_TRY(copy(host->terminated, dev->terminated, 1));
+    CUDA_TRY(copy(host->truncated, dev->truncated, 1));
+    CUDA_TRY(copy(host->winner, dev->winner, 1));
+  }
+  CUDA_TRY(cudaEventRecord(env->copies_done, env->copy_stream));
+  CUDA_TRY(cudaStreamWaitEvent(stream, env->copies_done, 0));
+  return CAT_OK;
+}
 
 static int state_view(CatEnv* env, void* state_dev, const CatStateView* view, int set, void* stream) {
   if (!env || !state_dev || !view) return fail(CAT_ERR_INVALID, "null argument");

@@ -13,7 +13,7 @@ skrl is not installable in this image, so this module restates the part of
   ``cat_adv_normalize``);
 * PPO-clip surrogate, entropy bonus, scaled value loss, KL early stop, grad-norm clip (skrl's ``_update``);
 * under ``torchrun`` the gradients of every minibatch are all-reduced over NCCL in one flat bucket
-  (``sharding.allreduce_gradients``) — the only collective in the system besides the optional advantage
+  (every parameter's ``.grad`` is a view into it) — the only collective in the system besides the optional advantage
   statistics.
 
 Differences from the reference that batching forces (documented, not hidden):
@@ -37,7 +37,6 @@ from typing import Dict, Iterable, List, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from .sharding import allreduce_gradients
 
 N_RAYS = 90
 
@@ -275,6 +274,17 @@ class MAPPOLearner:
         self.models = build_models(self.agents, self.n_obs, self.n_state, self.cfg.model, self.device)
         self.optimizers = {a: torch.optim.Adam(self.parameters(a), lr=self.cfg.learning_rate) for a in self.agents}
         self.frozen: Dict[str, Dict[str, bool]] = {a: {"policy": False, "value": False} for a in self.agents}
+        # One flat fp32 gradient bucket per agent; every parameter's .grad is a view into it, so the minibatch
+        # all-reduce is a single NCCL call on memory autograd already wrote — no gather / scatter copies.
+        self._flat_grad: Dict[str, torch.Tensor] = {}
+        for a in self.agents:
+            ps = self.parameters(a)
+            flat = torch.zeros(sum(p.numel() for p in ps), device=self.device)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self._flat_grad[a] = flat
         T, N, dev = self.cfg.rollouts, env.num_envs, self.device
         nseg = T // self.cfg.sequence_length
         self.mem = {}
@@ -312,8 +322,21 @@ class MAPPOLearner:
         self.frozen[agent][role] = frozen
         for p in self.models[agent][role].parameters():
             p.requires_grad_(not frozen)
-            if frozen:
-                p.grad = None          # Adam skips parameters without a gradient (no momentum drift while frozen)
+        self._rebind_grads(agent)
+
+    def _rebind_grads(self, agent: str) -> None:
+        """Frozen parameters get no gradient (Adam then skips them: no momentum drift while frozen); trainable
+        ones (re)attach to their slice of the agent's flat bucket."""
+        flat, off = self._flat_grad[agent], 0
+        for role in ("policy", "value"):
+            for p in self.models[agent][role].parameters():
+                n = p.numel()
+                if self.frozen[agent][role]:
+                    p.grad = None
+                else:
+                    flat[off:off + n].zero_()
+                    p.grad = flat[off:off + n].view_as(p)
+                off += n
 
     def state_dict(self) -> Dict[str, Dict[str, dict]]:
         """What ``agent.save`` writes (orchestration.py:225-228): per agent policy / value / optimizer."""
@@ -493,7 +516,7 @@ class MAPPOLearner:
             act_seq, logp_seq = self._sequences(mem["act"]), self._sequences(mem["logp"])
             ret_seq, adv_seq = self._sequences(returns), self._sequences(advantages)
             params = [p for p in self.parameters(a) if p.requires_grad]
-            ar_ms = 0.0
+            ar_events = []
             for _epoch in range(cfg.learning_epochs):
                 perm = torch.randperm(n_seq, device=self.device)
                 for idx in perm.chunk(cfg.mini_batches):
@@ -509,12 +532,13 @@ class MAPPOLearner:
                     self.optimizers[a].zero_grad(set_to_none=False)
                     loss.backward()
                     if cfg.distributed:
+                        import torch.distributed as dist
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                        allreduce_gradients(params, cfg.world_size)
+                        dist.all_reduce(self._flat_grad[a])          # frozen slices are zero on every rank
+                        self._flat_grad[a].div_(cfg.world_size)
                         e1.record()
-                        e1.synchronize()
-                        ar_ms += e0.elapsed_time(e1)
+                        ar_events.append((e0, e1))
                     if cfg.grad_norm_clip > 0:
                         nn.utils.clip_grad_norm_(params, cfg.grad_norm_clip)
                     self.optimizers[a].step()
@@ -522,7 +546,8 @@ class MAPPOLearner:
                     st.minibatches += 1
             ev2.record()
             ev2.synchronize()
-            st.gae_ms, st.update_ms, st.allreduce_ms = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2), ar_ms
+            st.gae_ms, st.update_ms = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)
+            st.allreduce_ms = sum(e0.elapsed_time(e1) for e0, e1 in ar_events)
             stats[a] = st
         return stats
 

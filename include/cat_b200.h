@@ -160,6 +160,14 @@ int cat_env_init_state(CatEnv* env, void* state_dev, void* stream);
 int cat_env_reset(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);
 /* BaseEnv.step (base_env.py:354-413) for every world, one launch */
 int cat_env_step(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);
+/* BaseEnv.step for a caller whose buffers live in pinned HOST memory (the reference's own calling convention:
+ * numpy in, numpy out), pipelined: the worlds are stepped in n_chunks consecutive launches on `stream`, and
+ * each chunk's slice of obs_dist / obs_type / reward / terminated / truncated / winner is copied from the
+ * dense device arrays in `dev` to the dense pinned host arrays in `host` on an internal copy stream while the
+ * next chunk computes.  host->actions: u8 [N][A] in pinned host memory (actions_kind 0), read by the kernel
+ * directly.  `stream` waits for the copies: one cudaStreamSynchronize(stream) makes every result visible. */
+int cat_env_step_host(CatEnv* env, void* state_dev, const CatStepIO* dev, const CatStepIO* host, int32_t n_chunks,
+                      void* stream);
 /* Entity.get_observation + get_shared_observations of the current state (entity.py:159-220,
  * observation_spaces.py:67-131) without stepping */
 int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);

@@ -138,27 +138,34 @@ def test_action_input_forms_are_equivalent(cuda_device):
         e.close()
 
 
-def test_host_buffer_step_zero_copy_equals_staged_copy(cuda_device):
-    """CatWorlds.step_host: the kernel storing straight into mapped pinned host memory must deliver exactly
-    what the H2D copy -> launch -> D2H copy path delivers (and what the device-resident outputs hold)."""
+def test_host_buffer_step_modes_are_equivalent(cuda_device):
+    """CatWorlds.step_host: the pipelined path (chunked launches + DMA on a second stream, cat_env_step_host), the
+    zero-copy path (kernel stores into mapped pinned host memory) and the staged path (H2D copy -> launch -> D2H
+    copy) must deliver exactly the same bytes, equal to what the device-resident outputs hold."""
     cmap = pu.named_cmap("squarinth")
     N = 777
-    zc = CatWorlds(cmap, N, device=cuda_device, seed=5, want_f32=False, want_shared=False)
-    st = CatWorlds(cmap, N, device=cuda_device, seed=5, want_f32=False, want_shared=False)
-    zc.reset()
-    st.reset()
+    envs = {m: CatWorlds(cmap, N, device=cuda_device, seed=5, want_f32=False, want_shared=False)
+            for m in ("pipelined", "pipelined5", "zero_copy", "staged")}
+    for w in envs.values():
+        w.reset()
     g = torch.Generator().manual_seed(3)
     for i in range(60):
         a = torch.randint(0, 4, (N, 3), dtype=torch.uint8, generator=g)
-        hz = zc.step_host(a.pin_memory() if i % 2 else a, zero_copy=True)
-        hs = st.step_host(a.pin_memory(), zero_copy=False)
+        out = {"pipelined": envs["pipelined"].step_host(a.pin_memory(), mode="pipelined", chunks=2),
+               "pipelined5": envs["pipelined5"].step_host(a, mode="pipelined", chunks=5),
+               "zero_copy": envs["zero_copy"].step_host(a.pin_memory() if i % 2 else a, mode="zero_copy"),
+               "staged": envs["staged"].step_host(a.pin_memory(), mode="staged")}
+        ref = envs["staged"]
         for k in ("obs_dist", "obs_type", "reward", "terminated", "truncated", "winner"):
-            assert hz[k].shape == hs[k].shape
-            assert torch.equal(hz[k].contiguous().view(torch.uint8), hs[k].contiguous().view(torch.uint8)), (i, k)
-            assert torch.equal(hs[k].contiguous().view(torch.uint8), getattr(st, k).cpu().view(torch.uint8)), (i, k)
-    assert torch.equal(zc.state, st.state)
-    zc.close()
-    st.close()
+            want = getattr(ref, k).cpu().view(torch.uint8)
+            for m, h in out.items():
+                assert h[k].shape == getattr(ref, k).shape
+                assert torch.equal(h[k].contiguous().view(torch.uint8), want), (i, k, m)
+    for w in envs.values():
+        assert torch.equal(w.state, envs["staged"].state)
+        w.close()
+    with pytest.raises(ValueError):
+        CatWorlds(cmap, 8, device=cuda_device).step_host(torch.zeros((8, 3), dtype=torch.uint8), mode="carrier-pigeon")
 
 
 def test_auto_reset_emits_terminal_reward_and_new_episode_observation(cuda_device):
