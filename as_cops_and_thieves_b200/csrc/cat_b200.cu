@@ -547,6 +547,12 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
     if (ncand > 0) raster_batch(w.blob, w.best + a * R, w.cand, ncand, ox, oy, rsum, L, R);
     __syncwarp();
 
+    // the other agents' cached centres relative to this origin, compacted (the candidate queue is free now)
+    float4* others = reinterpret_cast<float4*>(w.cand);
+    if (lane < A && lane != a)
+      others[lane < a ? lane : lane - 1] = make_float4(ox - tc[2 * lane], oy - tc[2 * lane + 1], __uint_as_float(kAgentTag + lane), 0.f);
+    __syncwarp();
+
     // ---- (3) lanes = rays: entity.py:200-215 — hit point, float16 chain at each of its rounding points, type
     const float oxh = __half2float(__float2half_rn(ox)), oyh = __half2float(__float2half_rn(oy));
     const int want = (a < k.nc) ? TYPE_THIEF : TYPE_COP;
@@ -565,10 +571,14 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
           if (zero_agent >= 0) key = min(key, make_key(0.f, kAgentTag + zero_agent));
           else {
 #pragma unroll 1
-            for (int j = 0; j < A; ++j) {
-              if (j == a) continue;
-              const float sc = ray_circle(tc[2 * j], tc[2 * j + 1], reach, rq);
-              if (sc < L) key = min(key, make_key(sc, kAgentTag + j));
+            for (int q = 0; q < A - 1; ++q) {   // CircleSegmentQuery, perpendicular-offset form (as ray_circle)
+              const float4 o4 = others[q];
+              const float cp = fmaf(o4.x, dv.y, -o4.y * dv.x);
+              const float disc = fmaf(-cp, cp, reach2);
+              if (disc >= 0.f) {
+                const float sc = -fmaf(o4.x, dv.x, o4.y * dv.y) - fast_sqrt(disc);
+                if (sc >= 0.f && sc < L) key = min(key, make_key(sc, __float_as_uint(o4.z)));
+              }
             }
           }
           // static shapes with the origin inside their reach: alpha = 0, but only if the thin ray enters the bb
@@ -615,6 +625,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
         }
       }
     }
+    __syncwarp();   // `others` aliases the candidate queue of the next agent
   }
   __syncwarp();
 }
@@ -766,52 +777,94 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
   __syncwarp();
 
   // (3) narrow phase.  Entry: {nx, ny, bias, jn, jBias, nMass, meta, slot}
-  if (lane < A) {
-    const float px = pos[2 * lane], py = pos[2 * lane + 1];
-    uint32_t cnt = 0, used = 0;
-    const int cell = grid_cell(m, px, py);
-    if (cell >= 0) {
+  // (3a) lanes = (agent, hull of the agent's grid cell) pairs: bounding-box reject + closest feature, all
+  //      pairs of the world in one pass; hits are staged per agent in list order ({nx, ny, d, hull}).
+  {
+    int q0 = 0, len = 0;
+    if (lane < A) {
+      const int cell = grid_cell(m, pos[2 * lane], pos[2 * lane + 1]);
+      if (cell >= 0) { q0 = m.con_off[cell]; len = m.con_off[cell + 1] - q0; }
+      w.ccount[lane] = 0;
+    }
+    int incl = len;   // inclusive scan over the (at most 8) agent lanes
+#pragma unroll
+    for (int d = 1; d < CAT_MAX_AGENTS; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, A - 1);
+    __syncwarp();
 #pragma unroll 1
-      for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && cnt < (uint32_t)kSlots; ++q) {
-        const int h = m.con_list[q];
+    for (int p0 = 0; p0 < total; p0 += 32) {
+      const int p = p0 + lane;
+      int a = 0;
+#pragma unroll 1
+      for (int j = 0; j < A - 1; ++j) a += (p >= __shfl_sync(0xFFFFFFFFu, incl, j)) ? 1 : 0;
+      const int q0a = __shfl_sync(0xFFFFFFFFu, q0, a), excl = __shfl_sync(0xFFFFFFFFu, incl - len, a);
+      bool hit = false;
+      float d = 0.f, nx = 0.f, ny = 0.f;
+      int h = 0;
+      if (p < total) {
+        h = m.con_list[q0a + (p - excl)];
+        const float px = pos[2 * a], py = pos[2 * a + 1];
         const float4 bb = m.hull_bb[h];  // QueryReject: the shape bbs must overlap (hull bb already grown by wall_r)
-        if (px + k.agent_r < bb.x || bb.z < px - k.agent_r || py + k.agent_r < bb.y || bb.w < py - k.agent_r) continue;
-        float d, nx, ny;
-        hull_closest(m, h, px, py, d, nx, ny);
-        if (d <= rsum_w) {  // CircleToPoly: d <= r_circle + r_poly
-          // cpArbiterUpdate: reuse the cached arbiter of this (agent, hull) pair if any
-          int slot = -1;
-#pragma unroll 1
-          for (int s = 0; s < kSlots; ++s)
-            if (wkey[lane * kSlots + s] != kEmpty && (wkey[lane * kSlots + s] & 0xFFFF) == (uint32_t)h) slot = s;
-          float jn0 = 0.f;
-          bool first = true;
-          if (slot >= 0) {
-            jn0 = wjn[lane * kSlots + slot];
-            first = (wkey[lane * kSlots + slot] >> 16) != 0;  // used in the previous step -> not first
-          } else {
-            // free slot, else the oldest slot not used this step
-            uint32_t oldest = 0;
-#pragma unroll 1
-            for (int s = 0; s < kSlots; ++s) {
-              if (used & (1u << s)) continue;
-              const uint32_t key = wkey[lane * kSlots + s];
-              const uint32_t age = key == kEmpty ? 0x10000u : (key >> 16) + 1u;
-              if (age > oldest) { oldest = age; slot = s; }
-            }
-          }
-          if (slot >= 0) {
-            used |= 1u << slot;
-            wkey[lane * kSlots + slot] = (uint32_t)h;  // age 0 = used this step
-            float* c = w.con + (lane * kSlots + cnt) * 8;
-            c[0] = nx; c[1] = ny;
-            c[2] = -k.bias_coef * fminf(0.f, (d - rsum_w) + k.slop) * k.inv_dt;  // cpArbiterPreStep
-            c[3] = jn0; c[4] = 0.f; c[5] = 1.f / k.inv_mass;
-            reinterpret_cast<uint32_t*>(c)[6] = (uint32_t)lane | (0xFFu << 8) | (first ? 1u << 16 : 0u);
-            reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)(lane * kSlots + slot);
-            ++cnt;
-          }
+        if (!(px + k.agent_r < bb.x || bb.z < px - k.agent_r || py + k.agent_r < bb.y || bb.w < py - k.agent_r)) {
+          hull_closest(m, h, px, py, d, nx, ny);
+          hit = d <= rsum_w;  // CircleToPoly: d <= r_circle + r_poly
         }
+      }
+      const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
+      const uint32_t same = __match_any_sync(0xFFFFFFFFu, a);
+      if (hit) {
+        const uint32_t rank = w.ccount[a] + __popc(hits & same & ((1u << lane) - 1u));
+        if (rank < (uint32_t)kSlots) {
+          float* c = w.con + (a * kSlots + rank) * 8;
+          c[0] = nx; c[1] = ny; c[2] = d;
+          reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)h;
+        }
+      }
+      __syncwarp();
+      if (hit && (hits & same & ((1u << lane) - 1u)) == 0) w.ccount[a] += __popc(hits & same);   // first hit lane of each agent
+      __syncwarp();
+    }
+  }
+  // (3b) lanes = agents: arbiter cache look-up for the staged contacts, in list order (cpArbiterUpdate)
+  if (lane < A) {
+    const uint32_t nstaged = min(w.ccount[lane], (uint32_t)kSlots);
+    uint32_t cnt = 0, used = 0;
+#pragma unroll 1
+    for (uint32_t idx = 0; idx < nstaged; ++idx) {
+      float* cs = w.con + (lane * kSlots + idx) * 8;
+      const float nx = cs[0], ny = cs[1], d = cs[2];
+      const int h = (int)reinterpret_cast<uint32_t*>(cs)[7];
+      // reuse the cached arbiter of this (agent, hull) pair if any
+      int slot = -1;
+#pragma unroll 1
+      for (int s = 0; s < kSlots; ++s)
+        if (wkey[lane * kSlots + s] != kEmpty && (wkey[lane * kSlots + s] & 0xFFFF) == (uint32_t)h) slot = s;
+      float jn0 = 0.f;
+      bool first = true;
+      if (slot >= 0) {
+        jn0 = wjn[lane * kSlots + slot];
+        first = (wkey[lane * kSlots + slot] >> 16) != 0;  // used in the previous step -> not first
+      } else {
+        // free slot, else the oldest slot not used this step
+        uint32_t oldest = 0;
+#pragma unroll 1
+        for (int s = 0; s < kSlots; ++s) {
+          if (used & (1u << s)) continue;
+          const uint32_t key = wkey[lane * kSlots + s];
+          const uint32_t age = key == kEmpty ? 0x10000u : (key >> 16) + 1u;
+          if (age > oldest) { oldest = age; slot = s; }
+        }
+      }
+      if (slot >= 0) {
+        used |= 1u << slot;
+        wkey[lane * kSlots + slot] = (uint32_t)h;  // age 0 = used this step
+        float* c = w.con + (lane * kSlots + cnt) * 8;   // cnt <= idx: never overwrites an unread staged entry
+        c[0] = nx; c[1] = ny;
+        c[2] = -k.bias_coef * fminf(0.f, (d - rsum_w) + k.slop) * k.inv_dt;  // cpArbiterPreStep
+        c[3] = jn0; c[4] = 0.f; c[5] = 1.f / k.inv_mass;
+        reinterpret_cast<uint32_t*>(c)[6] = (uint32_t)lane | (0xFFu << 8) | (first ? 1u << 16 : 0u);
+        reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)(lane * kSlots + slot);
+        ++cnt;
       }
     }
     // cpSpaceArbiterSetFilter: arbiters not used this step age; dropped at collision_persistence
@@ -1038,6 +1091,16 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // Prefetch this warp's first record while the map copy is in flight (with one world per warp, the usual case
+  // at a few thousand worlds, both latencies would otherwise add up on the critical path).
+  const long long first_world = k.world_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const bool prefetched = k.rec_words <= 64 && k.mode != MODE_INIT && first_world < k.world_end;
+  float pf0 = 0.f, pf1 = 0.f;
+  if (prefetched) {
+    const float* g = k.state + (size_t)first_world * k.rec_words;
+    if (lane < k.rec_words) pf0 = g[lane];
+    if (lane + 32 < k.rec_words) pf1 = g[lane + 32];
+  }
   if (tid == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(k.blob_bytes)
                  : "memory");
@@ -1101,8 +1164,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
     }
     if (k.mode == MODE_RESET && k.reset_mask && !k.reset_mask[world]) continue;
 
+    if (prefetched && world == first_world) {
+      if (lane < k.rec_words) w.rec[lane] = pf0;
+      if (lane + 32 < k.rec_words) w.rec[lane + 32] = pf1;
+    } else {
 #pragma unroll 1
-    for (int i = lane; i < k.rec_words; i += 32) w.rec[i] = grec[i];
+      for (int i = lane; i < k.rec_words; i += 32) w.rec[i] = grec[i];
+    }
     __syncwarp();
 
     bool do_step = k.mode == MODE_STEP, do_reset = k.mode == MODE_RESET;

@@ -21,7 +21,7 @@ ap.add_argument("--cell", type=float, default=None)
 a = ap.parse_args()
 kw = {} if a.cell is None else {"cell": a.cell}
 cmap = pu.named_cmap(a.map, free_spawn=bool(a.free), **kw)
-cw = CatWorlds(cmap, a.worlds, want_f32=False)
+cw = CatWorlds(cmap, a.worlds, want_f32=False, want_shared=False)
 cw.reset()
 acts = [torch.randint(0, 4, (a.worlds, cw.A), dtype=torch.uint8, device="cuda") for _ in range(8)]
 for i in range(a.steps):
