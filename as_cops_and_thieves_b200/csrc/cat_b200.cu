@@ -1307,10 +1307,20 @@ __global__ void cat_state_view_kernel(const ViewParams p) {
 // loads issued up front), folds it into one affine map (A, B); the kGaeSegs maps of a column are combined
 // by a shuffle scan (through shared memory, kGaeSegs lanes per column), and every thread then replays its
 // steps from registers and writes advantages / returns.  Every input byte is read once and every output
-// byte written once: 9 B read + 8 B written per sample.  CTAs are small (256 threads, 4+ per SM) so the
-// load, scan and store phases of different CTAs overlap.  sum / sum^2 of the advantages are reduced per
+// byte written once: 9 B read + 8 B written per sample.  CTAs are small (128 threads, 6 per SM) and the next
+// chunk's loads are issued before the scan (software pipeline), so loads stay in flight during the scan and
+// store phases.  sum / sum^2 of the advantages are reduced per
 // CTA and added in fp64 for the normalisation pass.
-constexpr int kGaeCols = 32, kGaeSegs = 8, kGaeS = 8;
+#ifndef CAT_GAE_SEGS
+#define CAT_GAE_SEGS 4   // measured on B200 (gpurun_out/prof_gae4.log): 4 segments x 32 columns, 6 CTAs per SM is the fastest shape
+#endif
+#ifndef CAT_GAE_PREFETCH
+#define CAT_GAE_PREFETCH 1
+#endif
+#ifndef CAT_GAE_MIN_CTAS
+#define CAT_GAE_MIN_CTAS 6
+#endif
+constexpr int kGaeCols = 32, kGaeSegs = CAT_GAE_SEGS, kGaeS = 8;
 constexpr int kGaeColsPerWarp = kGaeCols / kGaeSegs;  // scan phase: each warp scans 4 columns, 8 lanes per column
 
 struct GaeChunk {          // one thread's 8 steps of one chunk, as loaded
@@ -1338,7 +1348,7 @@ __device__ __forceinline__ void gae_load(GaeChunk& ck, const float* __restrict__
   if (seg > 0) ck.vnext = __ldg(values + (size_t)max(base + kGaeS, 0) * M + ccol);
 }
 
-__global__ void __launch_bounds__(kGaeCols* kGaeSegs, 3)
+__global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
     cat_gae_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, const float* __restrict__ values,
                    const float* __restrict__ last_values, float* __restrict__ returns, float* __restrict__ advantages,
                    double* __restrict__ stats, int T, int M, float gamma, float lam) {
@@ -1359,8 +1369,10 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, 3)
     const int base = t_hi - (seg + 1) * kGaeS;  // this thread's steps: base .. base + 7 (those >= 0)
     if (seg == 0) cur.vnext = carry_v;            // known only now: V at the first step of the later chunk
     // software pipeline: the next (earlier) chunk's loads are in flight during this chunk's scan and stores
+#if CAT_GAE_PREFETCH
     GaeChunk nxt;
     if (t_hi > kChunk) gae_load(nxt, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
+#endif
     float A = 1.f, B = 0.f;
 #pragma unroll
     for (int i = kGaeS - 1; i >= 0; --i) {
@@ -1411,7 +1423,11 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, 3)
       }
     }
     s1 += (double)p1; s2 += (double)p2;
+#if CAT_GAE_PREFETCH
     cur = nxt;
+#else
+    if (t_hi > kChunk) gae_load(cur, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
+#endif
     __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1) {
