@@ -1220,7 +1220,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
 #pragma unroll 1
     for (;;) {
       if (do_reset) { reset_world(k, m, w, world); do_reset = false; }
-      observe_world(k, m, w, world);  // entity.py:143 — pre-physics state
+      // entity.py:143 — observation of the pre-physics state.  A world that ends on this step and
+      // is re-spawned in it emits the NEW episode's observation (C-10) and a terminal reward that does not depend
+      // on what is seen, so its terminal sensor sweep would be thrown away: skip it.  With one world per warp the
+      // launch lasts as long as its slowest warp, and a second sweep made every finishing world that warp.
+      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world(k, m, w, world);
       bool again = false;
       if (do_step) {
         if (lane < A && k.reward)

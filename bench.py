@@ -135,6 +135,7 @@ def run_reference(args):
 class ClockSampler:
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.period = float(os.environ.get("CAT_BENCH_CLOCK_PERIOD", "0.01"))
         self._thread = None
         try:
             import pynvml
@@ -164,7 +165,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.period)
 
     def start(self):
         if self.nv is not None:

@@ -18,6 +18,7 @@ ap.add_argument("--worlds", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=60)
 ap.add_argument("--free", type=int, default=0)
 ap.add_argument("--cell", type=float, default=None)
+ap.add_argument("--flush", default="none", choices=["none", "read", "write"])
 a = ap.parse_args()
 kw = {} if a.cell is None else {"cell": a.cell}
 cmap = pu.named_cmap(a.map, free_spawn=bool(a.free), **kw)
@@ -27,11 +28,24 @@ acts = [torch.randint(0, 4, (a.worlds, cw.A), dtype=torch.uint8, device="cuda") 
 for i in range(a.steps):
     cw.step(acts[i % 8])
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for i in range(50):
-    cw.step(acts[i % 8])
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 50
+if a.flush == "none":
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(50):
+        cw.step(acts[i % 8])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+else:
+    flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
+    ev = []
+    for i in range(50):
+        flush.add_(1) if a.flush == "write" else flush.sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); cw.step(acts[i % 8]); e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = sorted(x.elapsed_time(y) for x, y in ev)
+    ms = sum(ts) / len(ts)
+    print(f"flush={a.flush}: min {ts[0]*1e3:.1f} median {ts[25]*1e3:.1f} max {ts[-1]*1e3:.1f} us")
 print(f"{a.map} N={a.worlds} cell={cmap.cell:.1f}: {ms*1e3:.1f} us/step {a.worlds*cw.A/ms*1e3:.3e} agent-steps/s grid {cw.info.grid} x {cw.info.warps_per_cta} warps")
