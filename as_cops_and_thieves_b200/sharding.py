@@ -29,6 +29,32 @@ def dist_env() -> Tuple[int, int, int]:
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Tuple[int, ...]:
+    """Pin this process to the CPU cores local to GPU ``device_index`` (best effort; returns the cores, () if
+    unknown).  Call it BEFORE allocating pinned host buffers: with one process per GPU on a two-socket box, the
+    first-touch policy then places the pinned pages on the GPU's own NUMA node, so the kernel's zero-copy
+    stores (``CatWorlds.step_host``) and the DMA copies do not cross the socket interconnect."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+        return tuple(sorted(cpus))
+    except Exception:
+        return ()
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], world_size: int, group=None) -> torch.Tensor:
     """MAPPO minibatch gradient all-reduce (skrl does the same when launched distributed;
     SURVEY.md §2.1, Appendix D): one flat fp32 bucket, one ``all_reduce``, mean over ranks.

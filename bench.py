@@ -286,6 +286,10 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    numa_cpus = ()
+    if world_size > 1 and os.environ.get("CAT_BENCH_NUMA_BIND", "1") == "1":
+        from as_cops_and_thieves_b200.sharding import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation (first touch)
 
     map_name, free, per_gpu = WORKLOADS[args.workload]
     per_gpu = args.worlds or per_gpu
@@ -338,7 +342,8 @@ def run_b200(args):
                    "max_step_count": 400, "spawn": "free-space regions" if free else "map spawn regions",
                    "outputs": "f16 distance + u8 type + f32 reward + u8 flags (native dtypes)",
                    "l2": "flushed between timed steps (192 MiB write), each step timed with its own CUDA events",
-                   "parallelism": f"worlds sharded over {world_size} GPU(s), no data-path collective"},
+                   "parallelism": f"worlds sharded over {world_size} GPU(s), no data-path collective",
+                   "cpu_affinity": f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus else "unbound"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,

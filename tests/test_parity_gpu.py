@@ -138,6 +138,62 @@ def test_single_step_transition_parity(cuda_device, name, free, N, gaps):
     cw.close()
 
 
+RAGGED_MAP = {
+    "window": {"w_px": 900, "h_px": 700}, "canvas": {"w": 900, "h": 700},
+    "objects": {"blocks": [
+        {"type": "rect", "x": 50, "y": 50, "w": 800, "h": 6}, {"type": "rect", "x": 50, "y": 644, "w": 800, "h": 6},
+        {"type": "rect", "x": 50, "y": 50, "w": 6, "h": 600}, {"type": "rect", "x": 844, "y": 50, "w": 6, "h": 600},
+        {"type": "poly", "vs": [{"x": 300, "y": 250}, {"x": 420, "y": 260}, {"x": 380, "y": 380}]},       # triangle
+        {"type": "poly", "vs": [{"x": 560, "y": 300}, {"x": 640, "y": 280}, {"x": 700, "y": 340},
+                                {"x": 660, "y": 420}, {"x": 580, "y": 400}]},                         # pentagon
+        {"type": "rect", "x": 200, "y": 480, "w": -60, "h": 40}]},                            # negative extent
+    "agents": [
+        {"type": "cop", "x": 120, "y": 120, "spawn_region": {"x": 80, "y": 80, "w": 200, "h": 120}},
+        {"type": "thief", "x": 780, "y": 580, "spawn_regions": [{"x": 700, "y": 500, "w": 120, "h": 120},
+                                                                  {"x": 450, "y": 80, "w": 150, "h": 100}]},
+        {"type": "cop", "x": 160, "y": 560, "spawn_region": {"x": 80, "y": 500, "w": 200, "h": 120}},
+        {"type": "thief", "x": 760, "y": 120, "spawn_region": {"x": 700, "y": 80, "w": 120, "h": 120}},
+        {"type": "cop", "x": 450, "y": 560, "spawn_region": {"x": 400, "y": 480, "w": 160, "h": 140}}]}
+
+
+@pytest.mark.parametrize("n_rays,dt", [(45, 1 / 15), (64, 1 / 60), (128, 1 / 30)], ids=["R45-dt15", "R64-dt60", "R128-dt30"])
+def test_ragged_configuration_parity(cuda_device, tmp_path, n_rays, dt):
+    """Not the 2-cops-1-thief / 90-ray shape everything else uses: 3 cops + 2 thieves (10 agent pairs, two
+    thief x three cop capture tests), odd / non-multiple-of-32 / maximum ray counts (the scalar and the
+    vector store paths), a triangle, a pentagon and a negative-extent rectangle, and BaseEnv's own 1/15 s
+    step (base_env.py:57) besides SimpleEnv's 1/60."""
+    import json
+    from as_cops_and_thieves_b200.maps import Map
+    path = tmp_path / "ragged.json"
+    path.write_text(json.dumps(RAGGED_MAP))
+    cmap = compile_map(Map(str(path)), name="ragged")
+    assert (cmap.n_cops, cmap.n_thieves) == (3, 2)
+    N = 512
+    cw = CatWorlds(cmap, N, device=cuda_device, want_hits=True, seed=11, n_rays=n_rays, dt=dt, max_step_count=60)
+    orc = Oracle(cmap, seed=11, n_rays=n_rays, dt=dt, max_step_count=60)
+    assert cw.A == 5 and cw.P == 10 and cw.R == n_rays
+    rng = np.random.default_rng(5)
+    cw.reset()
+    for gap in (0, 25, 45):          # the last comparison lands after worlds timed out (60 steps) and re-spawned
+        for _ in range(gap):
+            cw.step(_acts(rng, N, cw.A, cw.device)[1])
+        print(n_rays, gap, _compare_transition(cw, orc, rng, f"ragged-R{n_rays}@+{gap}"))
+    # shared observation: first non-EMPTY of (cop_0, cop_1, cop_2) / (thief_0, thief_1), from CUDA's own rays
+    ot, od = cw.obs_type.cpu().numpy(), cw.obs_dist.cpu().numpy()
+    for team, (a0, a1) in enumerate(((0, 3), (3, 5))):
+        t = np.full((N, n_rays), pu.TYPE_EMPTY, np.uint8)
+        d = np.zeros((N, n_rays), np.float16)
+        for a in range(a1 - 1, a0 - 1, -1):
+            seen = ot[:, a] != pu.TYPE_EMPTY
+            t = np.where(seen, ot[:, a], t)
+            d = np.where(seen, od[:, a], d)
+        d = np.where(t == pu.TYPE_EMPTY, od[:, a0], d)
+        assert np.array_equal(cw.shared_type.cpu().numpy()[:, team], t)
+        assert np.array_equal(cw.shared_dist.cpu().numpy()[:, team].view(np.uint16), d.view(np.uint16))
+    assert cw.state_f32.shape == (N, 3 * (4 * n_rays + 6) + 2 * (4 * n_rays + 4))
+    cw.close()
+
+
 def test_analytic_golden_vectors_through_cuda(cuda_device):
     m, vectors = pu.load_analytic()
     cmap = compile_map(m, name="analytic")
