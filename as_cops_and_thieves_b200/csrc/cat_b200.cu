@@ -1318,9 +1318,6 @@ __global__ void cat_state_view_kernel(const ViewParams p) {
 #ifndef CAT_GAE_SEGS
 #define CAT_GAE_SEGS 4   // measured on B200 (gpurun_out/prof_gae4.log): 4 segments x 32 columns, 6 CTAs per SM is the fastest shape
 #endif
-#ifndef CAT_GAE_PREFETCH
-#define CAT_GAE_PREFETCH 1
-#endif
 #ifndef CAT_GAE_MIN_CTAS
 #define CAT_GAE_MIN_CTAS 6
 #endif
@@ -1332,26 +1329,64 @@ struct GaeChunk {          // one thread's 8 steps of one chunk, as loaded
   uint32_t done;           // bit i: done flag of step i
 };
 
+// kFull: every step of the chunk exists (t >= 0) and every column of the CTA is < M, so nothing is clamped or
+// predicated.  Index: element offsets are formed in 32 bits when T*M < 2^31 (one IMAD.WIDE per access instead of
+// 64-bit multiply-adds — address arithmetic was a third of the kernel's instructions and the kernel is close to
+// issue-bound once the loads are batched).
+template <bool kFull, typename Index>
 __device__ __forceinline__ void gae_load(GaeChunk& ck, const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
                                          const float* __restrict__ values, int base, int seg, int M, int col, bool valid,
                                          float carry_v) {
   // Branch-free: every address is clamped into the array so that all 24 loads issue back to back (a predicated
   // load per step would make the compiler wait for each step's `done` byte before issuing the next step's loads);
   // steps before t = 0 / columns beyond M are masked afterwards.
-  const int ccol = valid ? col : 0;
+  const int ccol = kFull ? col : (valid ? col : 0);
   uint32_t raw[kGaeS];
 #pragma unroll
   for (int i = 0; i < kGaeS; ++i) {
-    const size_t idx = (size_t)max(base + i, 0) * M + ccol;
+    const Index idx = (Index)(kFull ? base + i : max(base + i, 0)) * (Index)M + (Index)ccol;
     ck.r[i] = __ldcs(rewards + idx); ck.v[i] = __ldcs(values + idx); raw[i] = __ldcs(dones + idx);
   }
   ck.done = 0;
 #pragma unroll
   for (int i = 0; i < kGaeS; ++i) ck.done |= (raw[i] ? 1u : 0u) << i;
   ck.vnext = carry_v;  // V_{t+1} of this thread's last step: the first V of the later segment (seg 0: patched by the caller)
-  if (seg > 0) ck.vnext = __ldg(values + (size_t)max(base + kGaeS, 0) * M + ccol);
+  if (seg > 0) ck.vnext = __ldg(values + (Index)(kFull ? base + kGaeS : max(base + kGaeS, 0)) * (Index)M + (Index)ccol);
 }
 
+template <bool kFull>
+__device__ __forceinline__ void gae_fold(GaeChunk& ck, int base, float gamma, float gl, float& A, float& B) {
+  A = 1.f; B = 0.f;
+#pragma unroll
+  for (int i = kGaeS - 1; i >= 0; --i) {
+    if (kFull || base + i >= 0) {
+      const float nd = (ck.done >> i) & 1u ? 0.f : 1.f;
+      const float vn = (i == kGaeS - 1) ? ck.vnext : ck.v[i + 1];
+      ck.r[i] = ck.r[i] - ck.v[i] + gamma * nd * vn;  // delta_t
+      B = fmaf(gl * nd, B, ck.r[i]);
+      A *= gl * nd;
+    }
+  }
+}
+
+template <bool kFull, typename Index>
+__device__ __forceinline__ void gae_store(const GaeChunk& ck, float adv, int base, int M, int col, bool valid, float gl,
+                                          float* __restrict__ returns, float* __restrict__ advantages, float& p1, float& p2) {
+#pragma unroll
+  for (int i = kGaeS - 1; i >= 0; --i) {
+    const int t = base + i;
+    if (kFull || (valid && t >= 0)) {
+      const float nd = (ck.done >> i) & 1u ? 0.f : 1.f;
+      adv = fmaf(gl * nd, adv, ck.r[i]);
+      const Index idx = (Index)t * (Index)M + (Index)col;
+      advantages[idx] = adv;
+      __stcs(returns + idx, adv + ck.v[i]);
+      p1 += adv; p2 = fmaf(adv, adv, p2);
+    }
+  }
+}
+
+template <typename Index>
 __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
     cat_gae_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, const float* __restrict__ values,
                    const float* __restrict__ last_values, float* __restrict__ returns, float* __restrict__ advantages,
@@ -1362,32 +1397,27 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
   const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
   const int col = blockIdx.x * kGaeCols + lane;
   const bool valid = col < M;
+  const bool cols_full = blockIdx.x * kGaeCols + kGaeCols <= M;   // CTA-uniform
   const float gl = gamma * lam;
   constexpr int kChunk = kGaeSegs * kGaeS;
   float carry_adv = 0.f, carry_v = valid ? last_values[col] : 0.f;
   double s1 = 0.0, s2 = 0.0;
   GaeChunk cur;
-  gae_load(cur, rewards, dones, values, T - (seg + 1) * kGaeS, seg, M, col, valid, carry_v);
+  if (cols_full && T >= kChunk) gae_load<true, Index>(cur, rewards, dones, values, T - (seg + 1) * kGaeS, seg, M, col, valid, carry_v);
+  else gae_load<false, Index>(cur, rewards, dones, values, T - (seg + 1) * kGaeS, seg, M, col, valid, carry_v);
 #pragma unroll 1
   for (int t_hi = T; t_hi > 0; t_hi -= kChunk) {
     const int base = t_hi - (seg + 1) * kGaeS;  // this thread's steps: base .. base + 7 (those >= 0)
+    const bool full = cols_full && t_hi >= kChunk;
     if (seg == 0) cur.vnext = carry_v;            // known only now: V at the first step of the later chunk
     // software pipeline: the next (earlier) chunk's loads are in flight during this chunk's scan and stores
-#if CAT_GAE_PREFETCH
     GaeChunk nxt;
-    if (t_hi > kChunk) gae_load(nxt, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
-#endif
-    float A = 1.f, B = 0.f;
-#pragma unroll
-    for (int i = kGaeS - 1; i >= 0; --i) {
-      if (base + i >= 0) {
-        const float nd = (cur.done >> i) & 1u ? 0.f : 1.f;
-        const float vn = (i == kGaeS - 1) ? cur.vnext : cur.v[i + 1];
-        cur.r[i] = cur.r[i] - cur.v[i] + gamma * nd * vn;  // delta_t
-        B = fmaf(gl * nd, B, cur.r[i]);
-        A *= gl * nd;
-      }
+    if (t_hi > kChunk) {
+      if (cols_full && t_hi >= 2 * kChunk) gae_load<true, Index>(nxt, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
+      else gae_load<false, Index>(nxt, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
     }
+    float A, B;
+    if (full) gae_fold<true>(cur, base, gamma, gl, A, B); else gae_fold<false>(cur, base, gamma, gl, A, B);
     sA[seg][lane] = A; sB[seg][lane] = B;
     if (seg == kGaeSegs - 1) sCarryV[lane] = cur.v[0];  // V at the chunk's first step = V_{t+1} of the next chunk
     if (seg == 0) sCarryAdv[lane] = carry_adv;
@@ -1410,28 +1440,14 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
       if (sl == kGaeSegs - 1) sB[0][scol] = xout;                       // advantage entering the next (earlier) chunk
     }
     __syncthreads();
-    float adv = sA[seg][lane];
+    const float adv = sA[seg][lane];
     carry_adv = sB[0][lane];
     carry_v = sCarryV[lane];
     float p1 = 0.f, p2 = 0.f;
-#pragma unroll
-    for (int i = kGaeS - 1; i >= 0; --i) {
-      const int t = base + i;
-      if (valid && t >= 0) {
-        const float nd = (cur.done >> i) & 1u ? 0.f : 1.f;
-        adv = fmaf(gl * nd, adv, cur.r[i]);
-        const size_t idx = (size_t)t * M + col;
-        advantages[idx] = adv;
-        __stcs(returns + idx, adv + cur.v[i]);
-        p1 += adv; p2 = fmaf(adv, adv, p2);
-      }
-    }
+    if (full) gae_store<true, Index>(cur, adv, base, M, col, valid, gl, returns, advantages, p1, p2);
+    else gae_store<false, Index>(cur, adv, base, M, col, valid, gl, returns, advantages, p1, p2);
     s1 += (double)p1; s2 += (double)p2;
-#if CAT_GAE_PREFETCH
     cur = nxt;
-#else
-    if (t_hi > kChunk) gae_load(cur, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
-#endif
     __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -1867,8 +1883,10 @@ int cat_gae(const float* rewards, const uint8_t* dones, const float* values, con
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(double), s));
   const int threads = kGaeCols * kGaeSegs, blocks = (M + kGaeCols - 1) / kGaeCols;
-  cat_gae_kernel<<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M,
-                                             gamma, lam);
+  if ((long long)(T + kGaeS) * M < (1ll << 31))
+    cat_gae_kernel<uint32_t><<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+  else
+    cat_gae_kernel<size_t><<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
   CUDA_TRY(cudaGetLastError());
   return CAT_OK;
 }
