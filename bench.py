@@ -31,6 +31,7 @@ ALG_BYTES_PER_AGENT_STEP = 336          # native dtypes, step 
 FALLBACK_HBM_GBS = 6650.0               # /opt/skills/guides/B200_PROFILING.md fallback
 WORKLOADS = {                           # name -> (map, free-space spawns, worlds per GPU)
     "squarinth-4096": ("squarinth", False, 4096),       # BASELINE.json configs[1]  (default)
+    "lbirinth-4096": ("lbirinth", False, 4096),         # the fifth named map
     "labyrinth-8192": ("labyrinth", True, 8192),        # configs[2] per-GPU share
     "grandbyrinth-16384": ("grandbyrinth", False, 16384),  # configs[3]
     "agh-map-16384": ("agh-map", True, 16384),          # the real large-segment case (496 edges)
@@ -359,34 +360,49 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                      "algorithmic_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP, "kernel": "cat_world_kernel",
-                     "note": "ALU/latency-bound path (SURVEY.md §8d): HBM fraction is reported as asked, not a target"},
+                     "note": "ALU/latency-bound path (SURVEY.md §8d): HBM fraction is reported as asked, not a target; "
+                             "what bounds the kernel is instruction issue (ncu: 68-76 % of issue slots busy, 23-25 of 32 "
+                             "lanes active; profiles/r1_cat_world_kernel_*.txt)"},
     }
 
-    if rank == 0 and world_size == 1 and not args.no_extras:
+    if not args.no_extras:
+        # every named map, on every rank (weak scaling: the same worlds per GPU), max over ranks like the headline
         others = {}
         for wl, (mn, fr, nw) in WORKLOADS.items():
             if wl == args.workload:
                 continue
             c2 = build_cmap(mn, fr)
-            w2 = CatWorlds(c2, nw, device=dev, seed=0, want_f32=False, want_shared=False)
+            g0, nl = shard_range(nw * world_size, rank, world_size)
+            w2 = CatWorlds(c2, nl, device=dev, gid0=g0, seed=0, want_f32=False, want_shared=False)
             w2.reset()
-            a2 = [torch.randint(0, 4, (nw, w2.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(8)]
-            ms = time_steps(torch, w2, a2, 300, 20, flush)
-            others[wl] = {"value": nw * w2.A * 300 / (ms * 1e-3), "ms_per_step": ms / 300, "hull_edges": int(c2.n_edges)}
+            a2 = [torch.randint(0, 4, (nl, w2.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(8)]
+            ms = time_steps(torch, w2, a2, 300, 20, flush, dist)
+            if dist is not None:
+                tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt[0])
+            others[wl] = {"value": nw * world_size * w2.A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
+                          "hull_edges": int(c2.n_edges), "worlds_per_gpu": nw}
             w2.close()
+        line["other_workloads"] = others
+    if rank == 0 and world_size == 1 and not args.no_extras:
         # the skrl-facing layout: + team-shared observations + fp32 flattened obs (A,N,180) + state (N,1090)
         w3 = CatWorlds(cmap, n_local, device=dev, seed=0, want_f32=True, want_shared=True)
         w3.reset()
         ms = time_steps(torch, w3, acts, 300, 20, flush)
-        others[args.workload + "+skrl-layouts"] = {"value": n_local * A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
-                                                   "bytes_per_agent_step": 786 + 1453}
+        line["other_workloads"][args.workload + "+skrl-layouts"] = {"value": n_local * A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
+                                                                    "bytes_per_agent_step": 786 + 1453}
         w3.close()
-        line["other_workloads"] = others
         line["gae"] = time_gae(torch, dev, flush)
         cpu = time_cpu_port(map_name, free, 512, seconds=12.0)
         line["cpu_baseline"] = {"value": cpu["value"], "unit": "agent-steps/s", "cores": cpu["cores"], "kind": "port",
                                 "sample": f"{cpu['worlds']} {map_name} worlds x {cpu['steps']} steps in {cpu['seconds']:.1f} s, "
                                           "fp64 oracle port of the Pymunk path, OpenMP over worlds"}
+        # BASELINE.json configs[0]: agh-map, ONE environment, one host thread — what a reference user runs today
+        cpu1 = time_cpu_port("agh-map", False, 1, seconds=3.0)       # one world = one loop iteration = one thread
+        line["cpu_baseline"]["config0_agh-map_single_env"] = {
+            "value": cpu1["value"], "unit": "agent-steps/s", "worlds": 1,
+            "sample": f"1 agh-map world (file spawn positions) x {cpu1['steps']} steps in {cpu1['seconds']:.1f} s, oracle port"}
     elif rank == 0:
         line["cpu_baseline"] = None
     cw.close()
