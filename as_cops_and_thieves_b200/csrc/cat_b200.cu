@@ -50,6 +50,13 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2, MODE_INIT = 3 };
 
 thread_local std::string g_last_error;
 
+#ifdef CAT_STATS   // developer build only (tools/raster_stats.py): rasteriser work counters
+__device__ unsigned long long g_stats[8];
+#define CAT_COUNT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#else
+#define CAT_COUNT(i, v)
+#endif
+
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
@@ -409,7 +416,26 @@ __device__ __noinline__ void raster_batch(const unsigned char* blob, unsigned lo
       if (i0 < 0) i0 += R;
       if (i0 < 0) i0 += R;
       if (i0 >= R) i0 -= R;
+      if (cnt > 0 && cnt <= 3) {
+        // Occlusion: a narrow (far) edge whose every ray already holds a strictly nearer hit cannot win the
+        // depth test.  Any hit on this edge or its bevel has s >= dist(origin, raw segment) - rsum.
+        const float len = m.edge_len[e];
+        const float qa = fmaf(-by, ed.z, bx * ed.w);        // position of o along A->B, relative to B
+        const float dq = qa - fminf(fmaxf(qa, -len), 0.f);
+        const float smin = fast_sqrt(fmaf(pd, pd, dq * dq)) * 0.9999f - rsum - 1e-3f;
+        bool occluded = true;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          int i = i0 + q;
+          if (i >= R) i -= R;
+          if (q < cnt) occluded = occluded && __uint_as_float((uint32_t)(best[i] >> 32)) < smin;
+        }
+        CAT_COUNT(2, 1);
+        if (occluded) { cnt = 0; CAT_COUNT(3, 1); }
+      }
     }
+    CAT_COUNT(0, 1);
+    CAT_COUNT(1, cnt);
   }
   int scan = cnt;
 #pragma unroll
@@ -508,11 +534,37 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
 
     // ---- (2) lanes = edges: candidates face the origin (plane i or the next plane, which share vertex v_i
     //          and hence its bevel) and lie within sensor range of the origin
+    //          Batches of 32 edges (hulls are stored in Morton order, so a batch is compact) are visited NEAR TO FAR:
+    //          lane b measures the distance of batch b's bounding box once, a counting rank orders them, and
+    //          the walk stops at the first batch beyond sensor range.  Near walls are then already in the depth
+    //          buffer when the far edges are set up, which lets the rasteriser drop occluded edges.
     int ncand = 0;
+    const int nb = (E + 31) >> 5;
+    const bool ordered = nb <= 32;
+    float bdist = CUDART_INF_F;
+    int brank = 0;
+    if (ordered) {
+      if (lane < nb) {
+        const float4 bb = m.batch_bb[lane];
+        const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
+        bdist = fmaf(ddx, ddx, ddy * ddy);
+      }
 #pragma unroll 1
-    for (int base = 0; base < E; base += 32) {
-      {  // warp-uniform reject of the whole batch (hulls are stored in Morton order, so batches are compact)
-        const float4 bb = m.batch_bb[base >> 5];
+      for (int j = 0; j < nb; ++j) {
+        const float dj = __shfl_sync(0xFFFFFFFFu, bdist, j);
+        brank += (dj < bdist || (dj == bdist && j < lane)) ? 1 : 0;
+      }
+    }
+#pragma unroll 1
+    for (int it = 0; it < nb; ++it) {
+      int base;
+      if (ordered) {
+        const int b = __ffs(__ballot_sync(0xFFFFFFFFu, lane < nb && brank == it)) - 1;
+        if (__shfl_sync(0xFFFFFFFFu, bdist, b) >= range2) break;   // this and every later batch is out of range
+        base = b << 5;
+      } else {
+        base = it << 5;
+        const float4 bb = m.batch_bb[it];
         const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
         if (fmaf(ddx, ddx, ddy * ddy) >= range2) continue;
       }
@@ -1539,6 +1591,15 @@ static bool pick_launch_shape(const CatEnv* env, int n_worlds, LaunchShape* out)
 }
 
 extern "C" {
+
+#ifdef CAT_STATS
+int cat_debug_stats(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_stats, sizeof(g_stats));
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_stats, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int cat_abi_version(void) { return CAT_ABI_VERSION; }
 const char* cat_last_error(void) { return g_last_error.c_str(); }
