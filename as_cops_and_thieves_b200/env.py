@@ -122,21 +122,28 @@ class BaseEnv(_EnvCommon):
         self._cmap = compile_map(map)
         self._params = params
         self._setup_common(map, self._cmap, params)
-        self._w = CatWorlds(self._cmap, 1, device=device, params=params, want_f32=False, want_shared=True)
+        # One world, consumed on the CPU every step: every output lives in mapped pinned host memory, so a step
+        # is one kernel launch + one stream synchronisation, and the dicts below are built from numpy views.
+        self._w = CatWorlds(self._cmap, 1, device=device, params=params, want_f32=False, want_shared=True,
+                            pinned_outputs=True)
+        self._acts = torch.zeros((1, len(self.possible_agents)), dtype=torch.uint8).pin_memory()
+        self._acts_np = self._acts.numpy()
+        w = self._w
+        self._np = {k: getattr(w, k).numpy() for k in ("obs_dist", "obs_type", "reward", "terminated", "truncated",
+                                                         "winner", "shared_dist", "shared_type", "team_pos")}
         self.agents: List[str] = []
         self._np_random_seed = None
 
     # ------------------------------------------------------------------ helpers
     def _observations(self) -> Dict[str, dict]:
-        d = self._w.obs_dist[0].cpu().numpy()
-        t = self._w.obs_type[0].cpu().numpy()
+        d, t = self._np["obs_dist"][0], self._np["obs_type"][0]
         return {a: {"distance": d[i].copy(), "object_type": t[i].copy()} for i, a in enumerate(self.possible_agents)}
 
     def _shared(self, obs: Dict[str, dict]) -> Dict[str, dict]:
         # observation_spaces.py:123-129 — team-mates share (alias) the merged arrays
-        sd = self._w.shared_dist[0].cpu().numpy()
-        st = self._w.shared_type[0].cpu().numpy()
-        tp = self._w.team_pos[0].cpu().numpy()
+        sd = self._np["shared_dist"][0].copy()
+        st = self._np["shared_type"][0].copy()
+        tp = self._np["team_pos"][0].copy()
         nc, na = self._cmap.n_cops, len(self.possible_agents)
         team_sd, team_st = [sd[0], sd[1]], [st[0], st[1]]      # one array object per team, shared by its members
         team_tp = [tp[0:nc], tp[nc:na]]
@@ -155,6 +162,7 @@ class BaseEnv(_EnvCommon):
             self._w.set_seed(seed)
         self.agents = self.possible_agents[:]
         self._w.reset()
+        self._w.synchronize()
         observations = self._observations()
         infos = {a: {} for a in self.agents}
         self._state = self._shared(observations)
@@ -166,14 +174,15 @@ class BaseEnv(_EnvCommon):
         if not action:
             self.agents = []
             return {}, {}, {}, {}, {}
-        acts = torch.tensor([[int(action[a]) for a in self.possible_agents]], dtype=torch.uint8,
-                            device=self._w.device)
-        self._w.step(acts)
+        for i, a in enumerate(self.possible_agents):
+            self._acts_np[0, i] = int(action[a])
+        self._w.step(self._acts)
+        self._w.synchronize()
         observations = self._observations()
-        rew = self._w.reward[0].cpu().numpy()
-        terminated = bool(self._w.terminated[0].item())
-        truncated = bool(self._w.truncated[0].item())
-        winner_code = int(self._w.winner[0].item())
+        rew = self._np["reward"][0]
+        terminated = bool(self._np["terminated"][0])
+        truncated = bool(self._np["truncated"][0])
+        winner_code = int(self._np["winner"][0])
         agents = self.agents
         rewards = {a: float(rew[self._agent_index[a]]) for a in agents}
         terminations = {a: terminated for a in agents}

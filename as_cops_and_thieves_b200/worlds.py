@@ -31,7 +31,10 @@ def _require_cuda(device: torch.device) -> None:
 class CatWorlds:
     def __init__(self, cmap: CompiledMap, n_worlds: int, *, device: Union[str, torch.device] = "cuda:0",
                  gid0: int = 0, params: Optional[EnvParams] = None, want_f32: bool = True,
-                 want_shared: bool = True, want_hits: bool = False, **overrides):
+                 want_shared: bool = True, want_hits: bool = False, pinned_outputs: bool = False, **overrides):
+        """``pinned_outputs=True`` places every output tensor in mapped pinned HOST memory: the kernel stores its
+        results there directly and the host reads them (``tensor.numpy()``) after one stream synchronisation —
+        the layout for callers that consume every step on the CPU, like the single-world PettingZoo face."""
         self.device = torch.device(device)
         _require_cuda(self.device)
         self.L = _lib.load()
@@ -84,7 +87,13 @@ class CatWorlds:
         sizes = dict(obs_dist=N * A * R * 2, obs_type=N * A * R, reward=N * A * 4, terminated=N, truncated=N, winner=N)
         offs = {k_: carve(v) for k_, v in sizes.items()}
         total = carve(0)
-        self._out = torch.zeros(total, dtype=torch.uint8, device=dev)
+        self.pinned_outputs = bool(pinned_outputs)
+
+        def alloc(shape, dtype):
+            if self.pinned_outputs:
+                return torch.zeros(shape, dtype=dtype).pin_memory()
+            return torch.zeros(shape, dtype=dtype, device=dev)
+        self._out = alloc(total, torch.uint8)
 
         def view(name, dtype, shape):
             return self._out[offs[name]:offs[name] + sizes[name]].view(dtype).view(shape)
@@ -96,12 +105,12 @@ class CatWorlds:
         self.truncated = view("truncated", torch.uint8, (N,))
         self.winner = view("winner", torch.int8, (N,))
         self.winner.fill_(-1)
-        self.shared_dist = torch.zeros((N, 2, R), dtype=torch.float16, device=dev) if want_shared else None
-        self.shared_type = torch.zeros((N, 2, R), dtype=torch.uint8, device=dev) if want_shared else None
-        self.team_pos = torch.zeros((N, A, 2), dtype=torch.float16, device=dev) if want_shared else None
-        self.obs_f32 = torch.zeros((A, N, 2 * R), dtype=torch.float32, device=dev) if want_f32 else None
-        self.state_f32 = torch.zeros((N, self.S), dtype=torch.float32, device=dev) if want_f32 else None
-        self.hit_point = torch.zeros((N, A, R, 2), dtype=torch.float32, device=dev) if want_hits else None
+        self.shared_dist = alloc((N, 2, R), torch.float16) if want_shared else None
+        self.shared_type = alloc((N, 2, R), torch.uint8) if want_shared else None
+        self.team_pos = alloc((N, A, 2), torch.float16) if want_shared else None
+        self.obs_f32 = alloc((A, N, 2 * R), torch.float32) if want_f32 else None
+        self.state_f32 = alloc((N, self.S), torch.float32) if want_f32 else None
+        self.hit_point = alloc((N, A, R, 2), torch.float32) if want_hits else None
         self._host = None
         self._io = self._make_io()
         self._ptr_table = (C.c_void_p * 8)()
@@ -148,8 +157,9 @@ class CatWorlds:
         """``BaseEnv.step`` for every world: one kernel launch on the current stream."""
         io = self._io
         if isinstance(actions, torch.Tensor):
-            if actions.device != self.device or not actions.is_contiguous() or actions.numel() != self.n_worlds * self.A:
-                raise ValueError("actions must be a contiguous (N, A) tensor on the env's device")
+            on_device = actions.device == self.device or (actions.device.type == "cpu" and actions.is_pinned())
+            if not on_device or not actions.is_contiguous() or actions.numel() != self.n_worlds * self.A:
+                raise ValueError("actions must be a contiguous (N, A) tensor on the env's device (or in pinned host memory)")
             kind = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}.get(actions.dtype)
             if kind is None:
                 raise ValueError(f"unsupported action dtype {actions.dtype}")
@@ -291,6 +301,10 @@ class CatWorlds:
             h["blob"].copy_(self._out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return h
+
+    def synchronize(self) -> None:
+        """Wait for the launches enqueued so far (needed before reading ``pinned_outputs`` tensors on the host)."""
+        torch.cuda.current_stream(self.device).synchronize()
 
     def observe(self) -> None:
         _lib.check(self.L.cat_env_observe(self._h, self.state.data_ptr(), C.byref(self._io), self._stream()),
