@@ -279,8 +279,7 @@ def run_b200(args):
     dist = None
     if world_size > 1:
         import torch.distributed as dist_mod
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on STDOUT; stdout carries one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries ONE JSON line
         dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         dist = dist_mod
     if not torch.cuda.is_available():

@@ -43,7 +43,9 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if world_size > 1:
+        import os
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     m = load_named_map(a.map)
     gid0, n_local = shard_range(a.worlds * world_size, rank, world_size)
