@@ -279,8 +279,20 @@ def run_b200(args):
     dist = None
     if world_size > 1:
         import torch.distributed as dist_mod
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries ONE JSON line
-        dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # NCCL prints its version banner (this image sets NCCL_DEBUG=VERSION) with printf on fd 1 and ignores
+        # NCCL_DEBUG_FILE for it; stdout must carry ONE JSON line, so fd 1 points at stderr while the communicator
+        # is created (init + first collective).
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         dist = dist_mod
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
