@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-CAT_ABI_VERSION = 2
+CAT_ABI_VERSION = 3
 CAT_MAX_AGENTS = 8
 CAT_MAX_RAYS = 128
 CAT_WALL_SLOTS = 4
@@ -33,6 +33,7 @@ class CatMapDesc(C.Structure):
         ("grid_x0", C.c_double), ("grid_y0", C.c_double), ("cell", C.c_double),
         ("nx", C.c_int32), ("ny", C.c_int32),
         ("con_cell_off", C.c_void_p), ("con_cell_hulls", C.c_void_p),
+        ("view_cell_off", C.c_void_p), ("view_cell_edges", C.c_void_p), ("view_range", C.c_double),
     ]
 
 

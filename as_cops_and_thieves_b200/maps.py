@@ -214,6 +214,12 @@ class CompiledMap:
     edge_hull: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))        # hull of each edge
     con_cell_off: np.ndarray = field(default_factory=lambda: np.zeros(2, np.int32))
     con_cell_hulls: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    # per grid cell: the edges a sensor sweep from ANY point of the cell can have as candidates (facing the
+    # point and within view_range of it), nearest first — a conservative superset, the kernel still runs the
+    # exact per-origin test on each listed edge
+    view_cell_off: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    view_cell_edges: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    view_range: float = 0.0
 
     @property
     def n_hulls(self) -> int:
@@ -310,9 +316,64 @@ def choose_cell_size(hull_bb: np.ndarray, n_hulls: int) -> float:
     return float(min(200.0, max(24.0, c)))
 
 
+def view_lists(vert: np.ndarray, normal: np.ndarray, hull_off: np.ndarray, gx0: float, gy0: float, cell: float,
+               nx: int, ny: int, view_range: float, eps: float = 1e-2) -> Tuple[np.ndarray, np.ndarray]:
+    """Per grid cell, the edges that can be sensor candidates for SOME origin inside the cell.
+
+    The kernel's per-origin candidate test is ``(pd > 0 or pdn > 0) and dist(origin, segment) < range`` with
+    pd / pdn the signed distances to the edge's plane and to the next plane of the hull (they share the
+    bevelled vertex).  Over a rectangular cell the first part is a union of two half-planes (a linear function
+    is maximal at a corner) and the second is the distance between two convex sets (attained at a vertex of
+    one of them), so both are evaluated exactly here, with ``eps`` of slack for the kernel's fp32.  Each list is
+    ordered by distance from the cell centre, nearest first, so that near walls reach the depth buffer first.
+    """
+    E = len(vert)
+    prev = np.zeros(E, np.int64)
+    nxt = np.zeros(E, np.int64)
+    for h in range(len(hull_off) - 1):
+        o, e = int(hull_off[h]), int(hull_off[h + 1])
+        idx = np.arange(o, e)
+        prev[o:e] = np.roll(idx, 1)
+        nxt[o:e] = np.roll(idx, -1)
+    A, B, n, nn = vert[prev], vert, normal, normal[nxt]
+    AB = B - A
+    L2 = np.maximum((AB ** 2).sum(1), 1e-300)
+    off = np.zeros(nx * ny + 1, np.int32)
+    chunks = []
+    for cy in range(ny):
+        for cx in range(nx):
+            # the cell rectangle, grown a little: the kernel bins the origin in fp32
+            l, b = gx0 + cx * cell - 0.05, gy0 + cy * cell - 0.05
+            r, t = l + cell + 0.1, b + cell + 0.1
+            corners = np.array([[l, b], [r, b], [r, t], [l, t]])
+            rel = corners[:, None, :] - B[None, :, :]
+            facing = (np.einsum("ced,ed->ce", rel, n).max(0) > -eps) | (np.einsum("ced,ed->ce", rel, nn).max(0) > -eps)
+
+            def to_rect(P):
+                dx = np.maximum(np.maximum(l - P[:, 0], P[:, 0] - r), 0.0)
+                dy = np.maximum(np.maximum(b - P[:, 1], P[:, 1] - t), 0.0)
+                return np.hypot(dx, dy)
+            d = np.minimum(to_rect(A), to_rect(B))
+            for c in corners:
+                tt = np.clip(((c - A) * AB).sum(1) / L2, 0.0, 1.0)
+                q = A + AB * tt[:, None]
+                d = np.minimum(d, np.hypot(c[0] - q[:, 0], c[1] - q[:, 1]))
+            # a segment crossing the cell has distance 0: it then has an end point or a crossing inside, and the
+            # corner-to-segment distances above are < the cell diagonal < any sensible range, so it is listed anyway
+            sel = np.nonzero(facing & (d < view_range + eps))[0]
+            ctr = np.array([(l + r) / 2, (b + t) / 2])
+            tt = np.clip(((ctr - A[sel]) * AB[sel]).sum(1) / L2[sel], 0.0, 1.0)
+            q = A[sel] + AB[sel] * tt[:, None]
+            order = np.argsort(np.hypot(ctr[0] - q[:, 0], ctr[1] - q[:, 1]), kind="stable")
+            chunks.append(sel[order].astype(np.int32))
+            off[cy * nx + cx + 1] = off[cy * nx + cx] + len(sel)
+    flat = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
+    return off, flat
+
+
 def compile_map(m: Map, *, cell: Optional[float] = None, ray_reach: float = 2.0,
                 contact_reach: float = 6.0, slack: float = 0.05, name: Optional[str] = None,
-                spawn_override: Optional[Dict[str, List[dict]]] = None) -> CompiledMap:
+                spawn_override: Optional[Dict[str, List[dict]]] = None, view_range: float = 402.0) -> CompiledMap:
     """Blocks -> convex hulls -> flat arrays + uniform grid cell lists.
 
     ``ray_reach``  = wall radius + ray radius: a sensor ray can only report a hull while its centre
@@ -396,6 +457,9 @@ def compile_map(m: Map, *, cell: Optional[float] = None, ray_reach: float = 2.0,
         ray_off[c + 1] = ray_off[c] + len(lst)
     ray_list = np.asarray([i for lst in per_cell_e for i in lst], np.int32)
 
+    # candidate lists for the sensor sweep (view_range = ray length + wall radius + ray radius by default)
+    view_off, view_edges = view_lists(vert, normal, hull_off, gx0, gy0, float(cell), nx, ny, float(view_range))
+
     return CompiledMap(
         name=name or Path(m.map_path).name.split(".")[0],
         window=tuple(float(v) for v in m.window_dimensions),
@@ -406,6 +470,7 @@ def compile_map(m: Map, *, cell: Optional[float] = None, ray_reach: float = 2.0,
         grid_x0=gx0, grid_y0=gy0, cell=float(cell), nx=nx, ny=ny,
         ray_cell_off=ray_off, ray_cell_edges=ray_list, edge_hull=edge_hull,
         con_cell_off=con_off, con_cell_hulls=con_list,
+        view_cell_off=view_off, view_cell_edges=view_edges, view_range=float(view_range),
     )
 
 

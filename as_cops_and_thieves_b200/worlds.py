@@ -56,6 +56,8 @@ class CatWorlds:
             regions=np.ascontiguousarray(cmap.regions if len(cmap.regions) else np.zeros((1, 4)), np.float64),
             con_cell_off=np.ascontiguousarray(cmap.con_cell_off, np.int32),
             con_cell_hulls=np.ascontiguousarray(np.append(cmap.con_cell_hulls, 0), np.int32),
+            view_cell_off=np.ascontiguousarray(cmap.view_cell_off, np.int32),
+            view_cell_edges=np.ascontiguousarray(np.append(cmap.view_cell_edges, 0), np.int32),
         )
         k = self._keep
         md = CatMapDesc(
@@ -63,7 +65,9 @@ class CatWorlds:
             _lib.np_ptr(k["edge_len"]), _lib.np_ptr(k["hull_bb"]), cmap.n_cops, cmap.n_thieves,
             _lib.np_ptr(k["init_pos"]), _lib.np_ptr(k["region_off"]), _lib.np_ptr(k["regions"]),
             cmap.grid_x0, cmap.grid_y0, cmap.cell, cmap.nx, cmap.ny,
-            _lib.np_ptr(k["con_cell_off"]), _lib.np_ptr(k["con_cell_hulls"]))
+            _lib.np_ptr(k["con_cell_off"]), _lib.np_ptr(k["con_cell_hulls"]),
+            _lib.np_ptr(k["view_cell_off"]) if len(k["view_cell_off"]) == cmap.nx * cmap.ny + 1 else None,
+            _lib.np_ptr(k["view_cell_edges"]), float(cmap.view_range))
         cp = CatParams(**{name: p[name] for name, _ in CatParams._fields_})
         handle = C.c_void_p()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CAT_ABI_VERSION 2
+#define CAT_ABI_VERSION 3
 #define CAT_MAX_AGENTS 8
 #define CAT_MAX_RAYS 128
 #define CAT_WALL_SLOTS 4 /* cached wall arbiters kept per agent */
@@ -68,6 +68,14 @@ typedef struct {
   int32_t nx, ny;
   const int32_t* con_cell_off;   /* [nx*ny+1] hulls within contact reach of each cell */
   const int32_t* con_cell_hulls;
+  /* Optional (NULL = scan every edge): per grid cell, the edges that can be sensor candidates for some origin
+   * inside the cell (facing it and within view_range), nearest first — maps.view_lists().  A conservative
+   * superset: the kernel still applies the exact per-origin test to every listed edge, so results do not
+   * depend on these lists; they only shorten the candidate scan.  Ignored unless
+   * view_range >= ray_length + wall_radius + ray_radius. */
+  const int32_t* view_cell_off;   /* [nx*ny+1] */
+  const int32_t* view_cell_edges; /* edge ids (< 65535) */
+  double view_range;
 } CatMapDesc;
 
 /* pyproject.toml:12-19 [tool.physical-params], entity.py:84-86, Chipmunk space defaults, SimpleEnv defaults */

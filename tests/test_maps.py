@@ -149,3 +149,43 @@ def test_free_space_regions_override():
     cm = compile_map(m, spawn_override=free_space_regions(m))
     assert cm.region_off.tolist() == [0, 1, 2, 3]
     assert np.all(cm.regions[:, 2] > 500)
+
+
+@pytest.mark.parametrize("name", ["squarinth", "lbirinth", "labyrinth", "agh-map"])
+def test_view_lists_are_conservative_and_nearest_first(name):
+    """Every edge the kernel's per-origin candidate test can accept (faces the origin through its own plane or
+    the next plane of the hull, and lies within the sensor reach) must be in the list of the origin's grid
+    cell — the lists only shorten the scan, they may never drop a candidate."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import parity_utils as pu
+    cm = pu.named_cmap(name, free_spawn=name in ("labyrinth", "agh-map"))
+    assert len(cm.view_cell_off) == cm.nx * cm.ny + 1 and cm.view_cell_off[-1] == len(cm.view_cell_edges)
+    assert cm.view_range >= 400 + 2
+    E = cm.n_edges
+    prev, nxt = np.zeros(E, int), np.zeros(E, int)
+    for h in range(cm.n_hulls):
+        o, e = int(cm.hull_off[h]), int(cm.hull_off[h + 1])
+        prev[o:e] = np.roll(np.arange(o, e), 1)
+        nxt[o:e] = np.roll(np.arange(o, e), -1)
+    A, B, n, nn = cm.vert[prev], cm.vert, cm.normal, cm.normal[nxt]
+    AB = B - A
+    rng = np.random.default_rng(0)
+    pts = np.column_stack([rng.uniform(cm.grid_x0, cm.grid_x0 + cm.nx * cm.cell, 3000),
+                           rng.uniform(cm.grid_y0, cm.grid_y0 + cm.ny * cm.cell, 3000)])
+    worst = 0
+    for o in pts:
+        cx, cy = int((o[0] - cm.grid_x0) / cm.cell), int((o[1] - cm.grid_y0) / cm.cell)
+        lst = cm.view_cell_edges[cm.view_cell_off[cy * cm.nx + cx]:cm.view_cell_off[cy * cm.nx + cx + 1]]
+        pd = ((o - B) * n).sum(1)
+        pdn = ((o - B) * nn).sum(1)
+        t = np.clip(((o - A) * AB).sum(1) / (AB ** 2).sum(1), 0, 1)
+        d = np.hypot(*(o - (A + AB * t[:, None])).T)
+        cand = np.nonzero(((pd > 0) | (pdn > 0)) & (d < 402.0))[0]
+        assert set(cand.tolist()) <= set(lst.tolist()), (name, o)
+        worst = max(worst, len(lst))
+    assert worst <= E
+    if name == "agh-map":       # the point of the lists: far fewer than all 496 edges
+        sizes = np.diff(cm.view_cell_off)
+        assert sizes.mean() < 0.4 * E

@@ -194,6 +194,32 @@ def test_ragged_configuration_parity(cuda_device, tmp_path, n_rays, dt):
     cw.close()
 
 
+@pytest.mark.parametrize("name,free", [("agh-map", True), ("labyrinth", True), ("squarinth", False)])
+def test_view_lists_do_not_change_results(cuda_device, name, free):
+    """The per-cell candidate lists only shorten the edge scan: stepping with them, without them (every edge
+    scanned) and with lists built for a too-short range (ignored by the library) must agree bit for bit."""
+    import dataclasses
+    cmap = pu.named_cmap(name, free_spawn=free)
+    bare = dataclasses.replace(cmap, view_cell_off=np.zeros(0, np.int32), view_cell_edges=np.zeros(0, np.int32))
+    short = dataclasses.replace(cmap, view_range=100.0)
+    N = 1024
+    ws = [CatWorlds(c, N, device=cuda_device, seed=9, want_hits=True) for c in (cmap, bare, short)]
+    g = torch.Generator().manual_seed(2)
+    for w in ws:
+        w.reset()
+    for _ in range(120):
+        a = torch.randint(0, 4, (N, 3), dtype=torch.uint8, generator=g).to(cuda_device)
+        for w in ws:
+            w.step(a)
+    torch.cuda.synchronize()
+    for w in ws[1:]:
+        assert torch.equal(w.state, ws[0].state)
+        for k in ("obs_dist", "obs_type", "reward", "terminated", "winner", "hit_point", "state_f32"):
+            assert torch.equal(getattr(w, k).view(torch.uint8), getattr(ws[0], k).view(torch.uint8)), k
+    for w in ws:
+        w.close()
+
+
 def test_analytic_golden_vectors_through_cuda(cuda_device):
     m, vectors = pu.load_analytic()
     cmap = compile_map(m, name="analytic")
