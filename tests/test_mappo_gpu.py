@@ -14,10 +14,10 @@ from as_cops_and_thieves_b200 import selfplay
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kind", ["lstm", "mlp"])
-def test_learner_collects_and_updates(cuda_device, kind):
+@pytest.mark.parametrize("kind,autocast", [("lstm", "none"), ("mlp", "none"), ("lstm", "bf16")])
+def test_learner_collects_and_updates(cuda_device, kind, autocast):
     env = BatchedCopsThievesEnv(load_named_map("squarinth"), 128, device=cuda_device, seed=1, max_step_count=40)
-    cfg = MAPPOConfig(rollouts=32, model=kind, kl_threshold=0.0)
+    cfg = MAPPOConfig(rollouts=32, model=kind, kl_threshold=0.0, update_autocast=autocast)
     learner = MAPPOLearner(env, cfg, seed=0)
     assert learner.n_parameters() == (2_588_175 if kind == "lstm" else learner.n_parameters())
     before = {a: [p.detach().clone() for p in learner.parameters(a)] for a in learner.agents}

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--max-step-count", type=int, default=2000)     # self_play_driver.py:34
     ap.add_argument("--archive", default="policy_archive")
     ap.add_argument("--free-spawn", type=int, default=1)
+    ap.add_argument("--autocast", default="none", choices=["none", "bf16"])
     a = ap.parse_args()
 
     rank, local_rank, world_size = dist_env()
@@ -51,7 +52,8 @@ def main():
     gid0, n_local = shard_range(a.worlds * world_size, rank, world_size)
     env = BatchedCopsThievesEnv(m, n_local, device=dev, seed=0, gid0=gid0, max_step_count=a.max_step_count,
                                 spawn_override=free_space_regions(m) if a.free_spawn else None)
-    cfg = MAPPOConfig(rollouts=a.rollouts, model=a.model, distributed=world_size > 1, world_size=world_size)
+    cfg = MAPPOConfig(rollouts=a.rollouts, model=a.model, distributed=world_size > 1, world_size=world_size,
+                      update_autocast=a.autocast)
     learner = MAPPOLearner(env, cfg, seed=0)
     archive = Path(a.archive) if rank == 0 else Path(a.archive + f".rank{rank}")
     for it in range(a.iterations):
