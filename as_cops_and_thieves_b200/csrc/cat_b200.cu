@@ -1747,7 +1747,9 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   KParams& k = env->kp;
   k.blob = env->blob_dev; k.blob_bytes = blob_bytes;
   // per-cell candidate lists (optional; valid only if they were built for at least this sensor range)
-  if (map->view_cell_off && map->view_cell_edges &&
+  // Worth it only when the full scan is long: the lists live in global memory (two dependent loads per sweep,
+  // cold after an L2 flush), and a map of a few dozen edges is scanned in one or two batches anyway.
+  if (map->view_cell_off && map->view_cell_edges && E >= 96 &&
       map->view_range >= pr->ray_length + pr->wall_radius + pr->ray_radius) {
     const int n_list = map->view_cell_off[ncell];
     std::vector<uint16_t> ve((size_t)(n_list > 0 ? n_list : 1));
