@@ -1220,7 +1220,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
   const int wpc = blockDim.x >> 5;   // warps per CTA: chosen per environment by the host (pick_launch_shape)
   const long long stride = (long long)gridDim.x * wpc;
 #pragma unroll 1
-  for (long long world = k.world_begin + (long long)blockIdx.x * wpc + warp; world < k.world_end; world += stride) {
+  for (long long wbase = k.world_begin + (long long)blockIdx.x * wpc; wbase < k.world_end; wbase += stride) {
+#ifndef CAT_NO_WORLD_SYNC
+    // Re-align the CTA's warps once per world.  Nothing is shared between them — the point is the instruction
+    // cache: the kernel is ~70 KB of SASS, and warps that drift apart each pull a different part of it (ncu: 2.4
+    // warps per issue slot stalled on `no_instruction`).  Starting every world together keeps them in the same
+    // code for most of it: -3 ... 4.5 % step time on every map; finer barriers (per agent sweep) lose more to
+    // waiting than they gain (profiles/r1_notes.md).  Every warp of the CTA walks the same wbase sequence.
+    __syncthreads();
+#endif
+    const long long world = wbase + warp;
+    if (world >= k.world_end) continue;
     float* grec = k.state + (size_t)world * k.rec_words;
     int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
 
