@@ -91,8 +91,12 @@ def region(f, l):
     return r
 
 
-agg = collections.defaultdict(lambda: [0, 0, 0])
 lagg = collections.defaultdict(lambda: [0, 0, 0])
+hot = collections.Counter()       # distinct instructions executed in >= 10 % of the world-steps, per region
+agg = collections.defaultdict(lambda: [0, 0, 0])
+llagg = collections.defaultdict(lambda: [0, 0, 0])
+hot = collections.Counter()       # distinct instructions executed in >= 10 % of the world-steps, per region
+agg = collections.defaultdict(lambda: [0, 0, 0])
 tot = [0, 0, 0]
 base = None
 for r in rows[2:]:
@@ -101,13 +105,16 @@ for r in rows[2:]:
         base = a
     ln = addr2line.get(a - base) or ("?", 0)
     v = [int(r[ii]), int(r[it]), int(r[isamp])]
+    if v[0] >= 0.1 * nworlds:
+        hot[region(*ln)] += 1
     for k in range(3):
         agg[region(*ln)][k] += v[k]
         lagg[ln][k] += v[k]
         tot[k] += v[k]
 print(f"total warp-inst/world {tot[0] / nworlds:.0f}  thread-inst/world {tot[1] / nworlds:.0f}  eff {tot[1] / tot[0]:.1f}")
+print(f"hot static footprint (instructions executed in >= 10 % of world-steps): {sum(hot.values())} instr = {sum(hot.values()) * 16 / 1024:.1f} KB")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-    print(f"{k:26s} warp-inst {v[0] / nworlds:8.0f}/world ({v[0] / tot[0] * 100:5.1f}%)  thread-inst/world {v[1] / nworlds:9.0f}  eff {v[1] / max(v[0], 1):5.1f}  samples {v[2] / max(tot[2], 1) * 100:5.1f}%")
+    print(f"{k:26s} warp-inst {v[0] / nworlds:8.0f}/world ({v[0] / tot[0] * 100:5.1f}%)  thread-inst/world {v[1] / nworlds:9.0f}  eff {v[1] / max(v[0], 1):5.1f}  samples {v[2] / max(tot[2], 1) * 100:5.1f}%  hot-instr {hot[k]:4d}")
 for (f, l), v in sorted(lagg.items(), key=lambda kv: -kv[1][0])[:nlines]:
     txt = src[l - 1].strip()[:100] if f.startswith("cat_b200") and l > 0 else ""
     print(f"{f}:{l:5d} inst {v[0] / tot[0] * 100:5.1f}% eff {v[1] / max(v[0], 1):5.1f} samp {v[2] / max(tot[2], 1) * 100:5.1f}% | {txt}")
