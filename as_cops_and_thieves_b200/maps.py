@@ -209,8 +209,6 @@ class CompiledMap:
     cell: float = 32.0
     nx: int = 1
     ny: int = 1
-    ray_cell_off: np.ndarray = field(default_factory=lambda: np.zeros(2, np.int32))
-    ray_cell_edges: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # EDGE ids (ascending)
     edge_hull: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))        # hull of each edge
     con_cell_off: np.ndarray = field(default_factory=lambda: np.zeros(2, np.int32))
     con_cell_hulls: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
@@ -260,34 +258,6 @@ def _cells_touching_hull(verts, normals, bb, rho, gx0, gy0, cell, nx, ny) -> np.
         px = np.where(nx_ >= 0, cx0, cx0 + cell)
         py = np.where(ny_ >= 0, cy0, cy0 + cell)
         keep &= ((px - vx) * nx_ + (py - vy) * ny_) <= rho
-    return (iy[keep] * nx + ix[keep]).astype(np.int64)
-
-
-def _cells_touching_segment(a, b, rho, gx0, gy0, cell, nx, ny) -> np.ndarray:
-    """Conservative set of grid cells that may contain a point within ``rho`` of segment a-b.
-
-    Kept iff the cell overlaps the segment's AABB grown by rho, is not entirely farther than rho
-    from the segment's supporting line, and is not entirely beyond either end cap by more than rho.
-    """
-    l, r = min(a[0], b[0]), max(a[0], b[0])
-    bo, t = min(a[1], b[1]), max(a[1], b[1])
-    ix0 = max(0, int(math.floor((l - rho - gx0) / cell)))
-    ix1 = min(nx - 1, int(math.floor((r + rho - gx0) / cell)))
-    iy0 = max(0, int(math.floor((bo - rho - gy0) / cell)))
-    iy1 = min(ny - 1, int(math.floor((t + rho - gy0) / cell)))
-    if ix1 < ix0 or iy1 < iy0:
-        return np.zeros(0, np.int64)
-    ix, iy = np.meshgrid(np.arange(ix0, ix1 + 1), np.arange(iy0, iy1 + 1), indexing="xy")
-    ix, iy = ix.ravel(), iy.ravel()
-    cx = np.stack([gx0 + ix * cell, gx0 + (ix + 1) * cell, gx0 + ix * cell, gx0 + (ix + 1) * cell], axis=1)
-    cy = np.stack([gy0 + iy * cell, gy0 + iy * cell, gy0 + (iy + 1) * cell, gy0 + (iy + 1) * cell], axis=1)
-    d = np.array([b[0] - a[0], b[1] - a[1]], np.float64)
-    ln = float(np.hypot(d[0], d[1]))
-    tx, ty = d / ln
-    perp = (cx - a[0]) * (-ty) + (cy - a[1]) * tx          # signed distance of each corner to the line
-    along = (cx - a[0]) * tx + (cy - a[1]) * ty            # coordinate along the segment
-    keep = ~((perp.min(axis=1) > rho) | (perp.max(axis=1) < -rho))
-    keep &= ~((along.max(axis=1) < -rho) | (along.min(axis=1) > ln + rho))
     return (iy[keep] * nx + ix[keep]).astype(np.int64)
 
 
@@ -371,16 +341,16 @@ def view_lists(vert: np.ndarray, normal: np.ndarray, hull_off: np.ndarray, gx0: 
     return off, flat
 
 
-def compile_map(m: Map, *, cell: Optional[float] = None, ray_reach: float = 2.0,
+def compile_map(m: Map, *, cell: Optional[float] = None,
                 contact_reach: float = 6.0, slack: float = 0.05, name: Optional[str] = None,
                 spawn_override: Optional[Dict[str, List[dict]]] = None, view_range: float = 402.0) -> CompiledMap:
     """Blocks -> convex hulls -> flat arrays + uniform grid cell lists.
 
-    ``ray_reach``  = wall radius + ray radius: a sensor ray can only report a hull while its centre
-    line is within this distance of the raw hull.  ``contact_reach`` = agent radius + wall radius
-    (contact iff centre-to-hull distance <= 6), also the spawn rejection distance
-    (``point_query_nearest(pos, 5)`` against hulls of radius 1 -> raw distance < 6).  ``slack`` is
-    added to both so fp32 cell walking can never step past a listed hull.
+    ``contact_reach`` = agent radius + wall radius (contact iff centre-to-hull distance <= 6),
+    also the spawn rejection distance (``point_query_nearest(pos, 5)`` against hulls of radius 1 -> raw
+    distance < 6) and what the "ray starts inside a wall's reach" lookup needs; ``slack`` is added so a point
+    binned in fp32 can never miss a listed hull.  ``view_range`` = ray length + wall radius + ray radius: the
+    reach the per-cell sensor candidate lists (``view_lists``) are built for.
 
     ``spawn_override`` maps agent id -> list of ``{"x","y","w","h"}`` regions and replaces what the
     map file says (used for the synthetic free-space spawns of the agh-map/labyrinth benchmarks).
@@ -441,21 +411,9 @@ def compile_map(m: Map, *, cell: Optional[float] = None, ray_reach: float = 2.0,
 
     con_off, con_list = build_lists(contact_reach + slack)
 
-    # sensor rays walk EDGE lists: edge i (plane v[i-1]->v[i] + bevelled vertex v[i]) can only be hit
-    # while the ray centre is within ray_reach of that segment
     edge_hull = np.zeros(len(vert), np.int32)
-    per_cell_e: List[List[int]] = [[] for _ in range(nx * ny)]
     for h in range(H):
-        o, e = int(hull_off[h]), int(hull_off[h + 1])
-        edge_hull[o:e] = h
-        for i in range(o, e):
-            prev = vert[i - 1] if i > o else vert[e - 1]
-            for c in _cells_touching_segment(prev, vert[i], ray_reach + slack, gx0, gy0, cell, nx, ny):
-                per_cell_e[int(c)].append(i)          # ascending edge id by construction
-    ray_off = np.zeros(nx * ny + 1, np.int32)
-    for c, lst in enumerate(per_cell_e):
-        ray_off[c + 1] = ray_off[c] + len(lst)
-    ray_list = np.asarray([i for lst in per_cell_e for i in lst], np.int32)
+        edge_hull[int(hull_off[h]):int(hull_off[h + 1])] = h
 
     # candidate lists for the sensor sweep (view_range = ray length + wall radius + ray radius by default)
     view_off, view_edges = view_lists(vert, normal, hull_off, gx0, gy0, float(cell), nx, ny, float(view_range))
@@ -468,7 +426,7 @@ def compile_map(m: Map, *, cell: Optional[float] = None, ray_reach: float = 2.0,
         init_pos=init_pos, region_off=np.asarray(region_off, np.int32),
         regions=np.asarray(regions, np.float64).reshape(-1, 4),
         grid_x0=gx0, grid_y0=gy0, cell=float(cell), nx=nx, ny=ny,
-        ray_cell_off=ray_off, ray_cell_edges=ray_list, edge_hull=edge_hull,
+        edge_hull=edge_hull,
         con_cell_off=con_off, con_cell_hulls=con_list,
         view_cell_off=view_off, view_cell_edges=view_edges, view_range=float(view_range),
     )

@@ -104,7 +104,7 @@ def test_convex_hull_drops_duplicates_and_collinear():
 
 @pytest.mark.parametrize("name", ["squarinth", "labyrinth", "agh-map"])
 def test_grid_lists_are_conservative(name):
-    """Every hull within reach of a point must be listed in the point's cell (both list kinds)."""
+    """Every hull within contact reach of a point must be listed in the point's cell."""
     from oracle.cat_oracle import Oracle
     cm = compile_map(load_named_map(name))
     orc = Oracle(cm)
@@ -114,27 +114,16 @@ def test_grid_lists_are_conservative(name):
     pts = rng.uniform(lo, hi, size=(1500, 2))
     for p in pts:
         c = int((p[1] - cm.grid_y0) // cm.cell) * cm.nx + int((p[0] - cm.grid_x0) // cm.cell)
-        ray = set(cm.ray_cell_edges[cm.ray_cell_off[c]:cm.ray_cell_off[c + 1]].tolist())
         con = set(cm.con_cell_hulls[cm.con_cell_off[c]:cm.con_cell_off[c + 1]].tolist())
         for h in range(cm.n_hulls):
             d = orc.hull_distance(h, p)
             if d <= 6.0:
                 assert h in con
-            if d <= 2.0 and d > 0:
-                # every edge whose segment is within ray reach of p must be listed (edge-granular lists)
-                o, e = cm.hull_off[h], cm.hull_off[h + 1]
-                for i in range(o, e):
-                    a = cm.vert[i - 1] if i > o else cm.vert[e - 1]
-                    b = cm.vert[i]
-                    t = np.clip(((p - a) @ (b - a)) / ((b - a) @ (b - a)), 0, 1)
-                    if np.hypot(*(p - (a + t * (b - a)))) <= 2.0:
-                        assert i in ray
-                        assert cm.edge_hull[i] == h
     # lists are sorted ascending (fixes the arbiter order)
-    for off, lst in ((cm.ray_cell_off, cm.ray_cell_edges), (cm.con_cell_off, cm.con_cell_hulls)):
-        for c in range(cm.nx * cm.ny):
-            seg = lst[off[c]:off[c + 1]]
-            assert np.all(np.diff(seg) > 0)
+    for c in range(cm.nx * cm.ny):
+        seg = cm.con_cell_hulls[cm.con_cell_off[c]:cm.con_cell_off[c + 1]]
+        assert np.all(np.diff(seg) > 0)
+    assert np.array_equal(cm.edge_hull, np.repeat(np.arange(cm.n_hulls), np.diff(cm.hull_off)))
 
 
 def test_points_outside_grid_are_far_from_every_hull():
