@@ -2,10 +2,11 @@
 //
 // One warp owns one world for one lockstep transition (persistent CTAs loop over worlds):
 //   state record (coalesced) -> termination test -> action impulses -> 90-ray sensor sweep per
-//   agent (one lane per ray, uniform-grid walk over the wall hulls staged in shared memory by one
-//   TMA bulk copy per CTA) -> float16 observation chain -> rewards -> team-shared merge ->
-//   rigid-body step (position integrate, circle-hull / circle-circle contacts, warm start,
-//   10 sequential-impulse iterations) -> auto-reset (Philox) -> outputs + state record (coalesced).
+//   agent (the wall edges, staged in shared memory by one TMA bulk copy per CTA, are RASTERISED into
+//   a per-agent 1-D depth buffer: lanes = candidate edges, then lanes = (edge, ray) pairs) ->
+//   float16 observation chain -> rewards -> team-shared merge -> rigid-body step (position integrate,
+//   circle-hull / circle-circle contacts, warm start, sequential impulses) -> auto-reset (Philox) ->
+//   outputs + state record (coalesced).  Plus the MAPPO GAE / advantage-normalisation kernels.
 //
 // Restates /root/reference/src/environments/base_env.py:354-413,521-554,286-352,
 // /root/reference/src/agents/entity.py:126-241, cop.py:49-75, thief.py:48-69,
@@ -14,7 +15,7 @@
 // cpShapeSegmentQuery, cpPolyShapeSegmentQuery, CircleSegmentQuery, cpBBSegmentQuery) in fp32,
 // origin-relative so that ray distances keep ~1e-5 absolute accuracy at coordinates ~1e3.
 //
-// No CPU fallback, no Triton, no tensor cores (the path is ALU/latency bound).
+// No CPU fallback, no Triton, no tensor cores (the step is instruction-issue bound, GAE is HBM bound).
 
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -307,18 +308,6 @@ __device__ __forceinline__ float2 wall_hit_normal(const MapView& m, uint32_t fea
   return make_float2((r.ox - e.x + s * r.ux) * inv, (r.oy - e.y + s * r.uy) * inv);
 }
 
-// CircleSegmentQuery against an agent circle (cached centre c, reach rs = r_agent + r_ray): s or INF.
-__device__ __forceinline__ float ray_circle(float cx, float cy, float rs, const Ray& r) {
-  const float rx = r.ox - cx, ry = r.oy - cy;
-  const float cp = fmaf(rx, r.uy, -ry * r.ux);
-  const float disc = fmaf(-cp, cp, rs * rs);
-  if (disc >= 0.f) {
-    const float s = -fmaf(rx, r.ux, ry * r.uy) - fast_sqrt(disc);
-    if (s >= 0.f) return s;
-  }
-  return CUDART_INF_F;
-}
-
 __device__ __forceinline__ Ray make_ray(float ax, float ay, float dx, float dy) {
   Ray r;
   r.ox = ax; r.oy = ay;
@@ -490,7 +479,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
   const float* pos = w.rec;
   const float* tc = w.rec + k.o_tc;
   const uint32_t flags = reinterpret_cast<const uint32_t*>(w.rec)[k.o_flags];
-  const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len, rs2 = rsum * rsum;
+  const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len;
   const float reach = k.agent_r + k.ray_r, reach2 = reach * reach, inv_reach = 1.f / reach;
   const float range2 = (L + rsum) * (L + rsum);
   // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates.
@@ -645,7 +634,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
           if (zero_agent >= 0) key = min(key, make_key(0.f, kAgentTag + zero_agent));
           else {
 #pragma unroll 1
-            for (int q = 0; q < A - 1; ++q) {   // CircleSegmentQuery, perpendicular-offset form (as ray_circle)
+            for (int q = 0; q < A - 1; ++q) {   // CircleSegmentQuery against a cached agent centre, perpendicular-offset form
               const float4 o4 = others[q];
               const float cp = fmaf(o4.x, dv.y, -o4.y * dv.x);
               const float disc = fmaf(-cp, cp, reach2);
