@@ -256,16 +256,20 @@ def test_reset_matches_oracle_and_is_invariant_to_sharding(cuda_device):
     assert np.array_equal(pf.astype(np.float64), ost.pos), "Philox spawn positions must be bit-identical"
     assert np.array_equal(full.obs_type.cpu().numpy(), oout.obs_type) or \
         (full.obs_type.cpu().numpy() != oout.obs_type).mean() < 5e-3
-    # 3 shards with global ids reproduce the unsharded run
+    full.close()
+    # 3 shards with global ids reproduce the unsharded run, across episode ends: every world times out at step
+    # 40 and 80 and re-spawns inside the step from its (seed, GLOBAL world id, episode) Philox stream
     from as_cops_and_thieves_b200.sharding import shard_range
+    full = CatWorlds(cmap, N, device=cuda_device, seed=99, want_f32=False, max_step_count=40)
+    full.reset()
     parts = []
     for r in range(3):
         g0, n = shard_range(N, r, 3)
-        w = CatWorlds(cmap, n, device=cuda_device, gid0=g0, seed=99, want_f32=False)
+        w = CatWorlds(cmap, n, device=cuda_device, gid0=g0, seed=99, want_f32=False, max_step_count=40)
         w.reset()
         parts.append((w, g0, n))
     rng = np.random.default_rng(0)
-    for _ in range(25):
+    for _ in range(100):
         a = torch.from_numpy(rng.integers(0, 4, (N, 3)).astype(np.uint8)).to(cuda_device)
         full.step(a)
         for w, g0, n in parts:
@@ -275,6 +279,7 @@ def test_reset_matches_oracle_and_is_invariant_to_sharding(cuda_device):
         assert torch.equal(w.state.view(torch.int32), full.state.view(torch.int32).view(N, -1)[g0:g0 + n].reshape(-1))
         assert torch.equal(w.obs_dist, full.obs_dist[g0:g0 + n])
         w.close()
+    assert int(full.get_state()["episode"].min()) >= 3
     full.close()
 
 
