@@ -11,8 +11,10 @@ world range, there is no data-path collective.
 
 Prints ONE JSON line (rank 0).  `value` = agent-steps/s over all ranks with everything resident in
 HBM; `e2e` = the same metric through the host-buffer API (pinned actions in, observations / rewards /
-flags out, copies inside the timed region).  L2 is flushed between timed steps (the working set, a few
-MB, is far smaller than the 126 MB L2), so each step is timed separately with CUDA events and summed.
+flags out, copies inside the timed region).  Cold L2: one step's working set is a few MB, far smaller than the
+126 MB L2, so the timed steps rotate over enough independent world sets that their buffers exceed L2 ("inputs
+larger than L2"); K steps are timed back to back between one CUDA-event pair.  The flush-between-steps method is
+run as a cross-check (config.cross_check_flush_method).
 """
 from __future__ import annotations
 
@@ -183,26 +185,60 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ GPU arm
-def time_steps(torch, cw, acts, K, W, flush, dist=None):
-    """W warm-up steps, then K steps each timed with its own CUDA-event pair (L2 flushed in between,
-    outside the timed span).  Returns total timed milliseconds on this rank."""
-    for i in range(W):
-        cw.step(acts[i % len(acts)])
+L2_BYTES = 126e6                        # B200 L2
+
+
+def make_world_sets(CatWorlds, cmap, n_local, gid0, n_global, dev):
+    """Independent sets of `n_local` worlds, enough of them that their state + output buffers together are 1.5x
+    the L2.  The timed steps rotate over the sets (one launch = one set), so every step reads its state from
+    and writes its observations to HBM — "inputs larger than L2" — and K steps can be timed back to back with
+    ONE CUDA-event pair, as they run in use, instead of one event pair per step around a flush kernel (which
+    adds ~5 us of event / launch-gap overhead to every 40 us step).  Sets differ by global world id."""
+    first = CatWorlds(cmap, n_local, device=dev, gid0=gid0, seed=0, want_f32=False, want_shared=False)
+    footprint = first.state.numel() + first._out.numel()
+    n_sets = max(2, int(-(-1.5 * L2_BYTES // footprint)))
+    sets = [first] + [CatWorlds(cmap, n_local, device=dev, gid0=gid0 + j * n_global, seed=0, want_f32=False,
+                                want_shared=False) for j in range(1, n_sets)]
+    for w in sets:
+        w.reset()
+    return sets, footprint
+
+
+def time_steps(torch, sets, acts, K, W, dist=None):
+    """W warm-up steps per set, then EXACTLY K steps (round-robin over the sets) between one pair of CUDA events
+    on the launching stream, barrier + synchronize on both sides.  Returns the timed milliseconds on this rank."""
+    n = len(sets)
+    for i in range(W * n):
+        sets[i % n].step(acts[i % len(acts)])
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        sets[i % n].step(acts[i % len(acts)])
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def time_steps_flushed(torch, cw, acts, K, W, flush):
+    """Cross-check with the other method the contract allows: ONE world set, a 192 MiB write between steps to
+    flush L2, each step timed with its own CUDA-event pair (flush outside the timed span), times summed."""
+    for i in range(W):
+        cw.step(acts[i % len(acts)])
     torch.cuda.synchronize()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     for i in range(K):
-        if flush is not None:
-            flush.add_(1)                       # > L2-sized write: evicts state / outputs / actions from L2
+        flush.add_(1)                           # > L2-sized write: evicts state / outputs / actions from L2
         starts[i].record()
         cw.step(acts[i % len(acts)])
         stops[i].record()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
     torch.cuda.synchronize()
     return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
 
@@ -310,16 +346,18 @@ def run_b200(args):
     K, W = max(1, args.steps), max(3, args.warmup)
 
     cmap = build_cmap(map_name, free)
-    cw = CatWorlds(cmap, n_local, device=dev, gid0=gid0, seed=0, want_f32=False, want_shared=False)
-    cw.reset()
+    sets, footprint = make_world_sets(CatWorlds, cmap, n_local, gid0, n_global, dev)
+    cw = sets[0]
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     acts = [torch.randint(0, 4, (n_local, cw.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(16)]
     flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # 192 MiB > 126 MB L2
 
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
     sampler.start()
-    ms_total = time_steps(torch, cw, acts, K, W, flush, dist)
+    ms_total = time_steps(torch, sets, acts, K, W, dist)
     clocks = sampler.stop()
+    k_flush = min(K, 500)
+    ms_flushed = time_steps_flushed(torch, cw, acts, k_flush, 10, flush) / k_flush
     e2e_steps = min(K, 1000)
     e2e_ms, h2d, d2h = time_e2e(torch, cw, e2e_steps, 5, dist, mode="zero_copy")
     e2e_pipe_ms, _, _ = time_e2e(torch, cw, e2e_steps, 5, dist, mode="pipelined")
@@ -353,7 +391,12 @@ def run_b200(args):
                    "global_worlds": n_global, "agents_per_world": A, "rays_per_agent": cw.R, "dt": 1 / 60,
                    "max_step_count": 400, "spawn": "free-space regions" if free else "map spawn regions",
                    "outputs": "f16 distance + u8 type + f32 reward + u8 flags (native dtypes)",
-                   "l2": "flushed between timed steps (192 MiB write), each step timed with its own CUDA events",
+                   "l2": f"inputs larger than L2: the timed steps rotate over {len(sets)} independent sets of {n_local} worlds "
+                         f"({footprint * len(sets) / 1e6:.0f} MB of state + output buffers > 126 MB L2), one launch = one set; "
+                         "K steps timed back to back with one CUDA-event pair",
+                   "cross_check_flush_method": {"ms_per_step": ms_flushed, "steps": k_flush,
+                                                "how": "one world set, 192 MiB write between steps, each step timed with "
+                                                       "its own event pair (adds ~5 us of event / launch-gap overhead per step)"},
                    "parallelism": f"worlds sharded over {world_size} GPU(s), no data-path collective",
                    "cpu_affinity": f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus else "unbound"},
         "clocks": clocks,
@@ -384,23 +427,24 @@ def run_b200(args):
                 continue
             c2 = build_cmap(mn, fr)
             g0, nl = shard_range(nw * world_size, rank, world_size)
-            w2 = CatWorlds(c2, nl, device=dev, gid0=g0, seed=0, want_f32=False, want_shared=False)
-            w2.reset()
+            sets2, _ = make_world_sets(CatWorlds, c2, nl, g0, nw * world_size, dev)
+            w2 = sets2[0]
             a2 = [torch.randint(0, 4, (nl, w2.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(8)]
-            ms = time_steps(torch, w2, a2, 300, 20, flush, dist)
+            ms = time_steps(torch, sets2, a2, 300, 5, dist)
             if dist is not None:
                 tt = torch.tensor([ms], dtype=torch.float64, device=dev)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 ms = float(tt[0])
             others[wl] = {"value": nw * world_size * w2.A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
                           "hull_edges": int(c2.n_edges), "worlds_per_gpu": nw}
-            w2.close()
+            for w_ in sets2:
+                w_.close()
         line["other_workloads"] = others
     if rank == 0 and world_size == 1 and not args.no_extras:
         # the skrl-facing layout: + team-shared observations + fp32 flattened obs (A,N,180) + state (N,1090)
         w3 = CatWorlds(cmap, n_local, device=dev, seed=0, want_f32=True, want_shared=True)
         w3.reset()
-        ms = time_steps(torch, w3, acts, 300, 20, flush)
+        ms = time_steps_flushed(torch, w3, acts, 300, 20, flush)
         line["other_workloads"][args.workload + "+skrl-layouts"] = {"value": n_local * A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
                                                                     "bytes_per_agent_step": 786 + 1453}
         w3.close()
@@ -416,7 +460,8 @@ def run_b200(args):
             "sample": f"1 agh-map world (file spawn positions) x {cpu1['steps']} steps in {cpu1['seconds']:.1f} s, oracle port"}
     elif rank == 0:
         line["cpu_baseline"] = None
-    cw.close()
+    for w_ in sets:
+        w_.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
