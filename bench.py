@@ -383,6 +383,22 @@ def run_b200(args):
         except Exception:
             traffic = None
 
+    issue = None
+    ti = ROOT / "profiles" / "thread_instr_per_world_step.json"   # from the committed ncu capture of this workload
+    if ti.exists() and not args.worlds:
+        try:
+            per_world = json.load(open(ti)).get(args.workload)
+            if per_world:
+                n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+                mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+                peak_ti = n_sm * 128 * mhz * 1e6                 # one instruction per lane per clock
+                ach_ti = per_world * n_local / (launch_ms * 1e-3)
+                issue = {"what": "thread-level instructions per second of cat_world_kernel vs. 128 lanes x SMs x clock",
+                         "thread_instr_per_world_step": per_world, "achieved": ach_ti, "peak": peak_ti,
+                         "frac": ach_ti / peak_ti, "source": "profiles/thread_instr_per_world_step.json (ncu) x live rate"}
+        except Exception:
+            issue = None
+
     line = {
         "metric": "agent-steps/s (physics+raycast obs)", "value": value, "unit": "agent-steps/s",
         "n_gpus": world_size, "steps": K, "warmup": W, "ms_per_step": launch_ms, "higher_is_better": True,
@@ -414,6 +430,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                      "algorithmic_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP, "kernel": "cat_world_kernel",
+                     "instruction_throughput": issue,
                      "note": "ALU/latency-bound path (SURVEY.md §8d): HBM fraction is reported as asked, not a target; "
                              "what bounds the kernel is instruction issue (ncu: 68-76 % of issue slots busy, 23-25 of 32 "
                              "lanes active; profiles/r1_cat_world_kernel_*.txt)"},
