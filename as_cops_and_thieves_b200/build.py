@@ -1,7 +1,7 @@
 """In-tree build of the CUDA extension: ``nvcc`` -> ``as_cops_and_thieves_b200/libcat_b200.so``.
 
 sm_100a only (``-gencode arch=compute_100a,code=sm_100a``), ``-lineinfo`` so ncu's source page maps
-to ``csrc/cat_b200.cu``.  The shared library has a plain C ABI (``include/cat_b200.h``) and links
+to ``csrc/*.cuh`` (``cat_b200.cu`` = C ABI + host side; ``world_kernel.cuh``, ``gae_kernels.cuh``, ``state_view.cuh`` = the kernels).  The shared library has a plain C ABI (``include/cat_b200.h``) and links
 only the CUDA runtime; Python binds it with ctypes (``_lib.py``).  nvcc cross-compiles without a
 GPU, so this runs on the CPU-only build box too.
 """
@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 SRC = PKG / "csrc" / "cat_b200.cu"
 LIB = PKG / "libcat_b200.so"
-DEPS = [SRC, ROOT / "include" / "cat_b200.h", ROOT / "include" / "cat_philox.h"]
+DEPS = [SRC, *sorted((PKG / "csrc").glob("*.cuh")), ROOT / "include" / "cat_b200.h", ROOT / "include" / "cat_philox.h"]
 
 
 def nvcc_path() -> str:

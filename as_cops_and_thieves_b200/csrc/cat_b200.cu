@@ -33,30 +33,7 @@
 
 namespace {
 
-#ifndef CAT_WARPS_PER_CTA
-#define CAT_WARPS_PER_CTA 8
-#endif
-#ifndef CAT_MIN_CTAS_PER_SM
-#define CAT_MIN_CTAS_PER_SM 4
-#endif
-constexpr int kWarpsPerCta = CAT_WARPS_PER_CTA;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kMinCtasPerSm = CAT_MIN_CTAS_PER_SM;
-constexpr int kSlots = CAT_WALL_SLOTS;
-constexpr int kNear = 4;            // hulls an origin can be "inside" (alpha = 0 rule) per agent
-constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-
-enum { TYPE_WALL = 0, TYPE_COP = 1, TYPE_THIEF = 2, TYPE_EMPTY = 4 };
-enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2, MODE_INIT = 3 };
-
 thread_local std::string g_last_error;
-
-#ifdef CAT_STATS   // developer build only (tools/raster_stats.py): rasteriser work counters
-__device__ unsigned long long g_stats[8];
-#define CAT_COUNT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
-#else
-#define CAT_COUNT(i, v)
-#endif
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -69,1504 +46,9 @@ int fail(int code, const std::string& msg) {
       return fail(CAT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
   } while (0)
 
-// ------------------------------------------------------------------ shared-memory map blob
-struct BlobHeader {
-  int32_t n_hulls, n_edges, nx, ny;
-  float gx0, gy0, cell, inv_cell;
-  int32_t off_edge, off_len, off_hbb, off_heo;
-  int32_t off_nextn, off_edgehull, off_conoff, off_conlist;
-  int32_t off_dir, off_regoff, off_regions, off_initpos;
-  int32_t off_batchbb;
-  int32_t pad[3];
-};
-static_assert(sizeof(BlobHeader) == 96, "header must stay 16-byte sized");
-
-struct MapView {
-  const float4* edge;      // vx, vy, nx, ny  (vertex ending the edge, outward normal)
-  const float* edge_len;
-  const float4* hull_bb;   // l,b,r,t grown by the wall radius (the shape's bb)
-  const uint32_t* hull_eo; // edge offset | count << 16
-  const float4* batch_bb;    // bounding box of edges [32b, 32b+32) incl. both end points
-  const float2* next_n;      // outward normal of the NEXT edge of the same hull (shares vertex v_i)
-  const uint16_t* edge_hull; // hull of each edge
-  const uint16_t* con_off;
-  const uint16_t* con_list;
-  const float4* dir;       // per ray: ux, uy, 1/ux, 1/uy (unit direction and its reciprocals)
-  const int32_t* reg_off;
-  const float4* regions;
-  const float2* init_pos;
-  int H, nx, ny;
-  float gx0, gy0, cell, inv_cell;
-};
-
-struct KParams {
-  const unsigned char* blob;
-  int blob_bytes;
-  const int32_t* view_off;      // global memory: per grid cell candidate-edge lists (nullptr = scan all edges)
-  const uint16_t* view_edges;
-  float* state;
-  int rec_words;
-  int n_worlds;
-  int world_begin, world_end;   // the slice of worlds this launch steps (chunked host path); default [0, n_worlds)
-  long long gid0;
-  int A, nc, R, P, nrays, nrays_pad, maxc, n_edges;
-  int mode;
-  // record offsets (words)
-  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags;
-  // per-warp scratch offsets (bytes) and size
-  int s_rdist, s_rtype, s_min, s_near, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, scratch_bytes;
-  int state_dim;
-  // constants
-  float dt, inv_dt, impulse, inv_mass, agent_r, max_speed, term_r, ray_len, ray_r, wall_r;
-  float slop, bias_coef;
-  int iterations, persistence, max_steps, stale, auto_reset;
-  unsigned long long seed;
-  // I/O
-  const void* actions[CAT_MAX_AGENTS];
-  int actions_kind;
-  const uint8_t* reset_mask;
-  uint16_t* obs_dist;
-  uint8_t* obs_type;
-  int dist_stride, type_stride;   // bytes between worlds
-  int obs_vec;                    // 1: both strides and bases are 16-byte aligned -> uint4 stores
-  float* reward;
-  uint8_t* terminated;
-  uint8_t* truncated;
-  int8_t* winner;
-  uint16_t* shared_dist;
-  uint8_t* shared_type;
-  uint16_t* team_pos;
-  float* obs_f32;
-  float* state_f32;
-  float* hit_point;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ MapView make_view(const unsigned char* blob) {
-  const BlobHeader* h = reinterpret_cast<const BlobHeader*>(blob);
-  MapView m;
-  m.edge = reinterpret_cast<const float4*>(blob + h->off_edge);
-  m.edge_len = reinterpret_cast<const float*>(blob + h->off_len);
-  m.hull_bb = reinterpret_cast<const float4*>(blob + h->off_hbb);
-  m.hull_eo = reinterpret_cast<const uint32_t*>(blob + h->off_heo);
-  m.next_n = reinterpret_cast<const float2*>(blob + h->off_nextn);
-  m.batch_bb = reinterpret_cast<const float4*>(blob + h->off_batchbb);
-  m.edge_hull = reinterpret_cast<const uint16_t*>(blob + h->off_edgehull);
-  m.con_off = reinterpret_cast<const uint16_t*>(blob + h->off_conoff);
-  m.con_list = reinterpret_cast<const uint16_t*>(blob + h->off_conlist);
-  m.dir = reinterpret_cast<const float4*>(blob + h->off_dir);
-  m.reg_off = reinterpret_cast<const int32_t*>(blob + h->off_regoff);
-  m.regions = reinterpret_cast<const float4*>(blob + h->off_regions);
-  m.init_pos = reinterpret_cast<const float2*>(blob + h->off_initpos);
-  m.H = h->n_hulls; m.nx = h->nx; m.ny = h->ny;
-  m.gx0 = h->gx0; m.gy0 = h->gy0; m.cell = h->cell; m.inv_cell = h->inv_cell;
-  return m;
-}
-
-// ------------------------------------------------------------------ geometry (device)
-
-// Closest feature of the raw hull to point p (CircleToPoly's GJK/EPA result for a point):
-// d = signed distance (negative inside: least-penetration edge), n = unit vector from p towards
-// the hull surface.  Same quantity cpPolyShapePointQuery reports as +-minDist.  Everything is
-// evaluated relative to the hull's own vertices so that d keeps ~1e-6 absolute accuracy.
-__device__ __noinline__ float3 hull_closest_impl(const float4* __restrict__ edge, uint32_t eo, float px, float py) {
-  const int o = eo & 0xFFFF, n = eo >> 16;
-  bool inside = true, binterior = false;
-  float maxpd = -CUDART_INF_F, mnx = 0.f, mny = 0.f;
-  float bestd2 = CUDART_INF_F, bdx = 0.f, bdy = 0.f, benx = 0.f, beny = 0.f, bpd = 0.f;
-  float4 pv = edge[o + n - 1];
-  float v0x = pv.x, v0y = pv.y;
-#pragma unroll 1
-  for (int i = 0; i < n; ++i) {
-    const float4 e = edge[o + i];
-    const float pd = (px - e.x) * e.z + (py - e.y) * e.w;
-    if (pd > 0.f) inside = false;
-    if (pd > maxpd) { maxpd = pd; mnx = e.z; mny = e.w; }
-    const float edx = e.x - v0x, edy = e.y - v0y;
-    const float r0x = px - v0x, r0y = py - v0y;
-    float t = (r0x * edx + r0y * edy) / (edx * edx + edy * edy);
-    const bool interior = (t > 0.f) && (t < 1.f);
-    t = fminf(fmaxf(t, 0.f), 1.f);
-    const float ddx = r0x - edx * t, ddy = r0y - edy * t;  // p - q
-    const float d2 = interior ? pd * pd : ddx * ddx + ddy * ddy;
-    if (d2 < bestd2) { bestd2 = d2; bdx = ddx; bdy = ddy; benx = e.z; beny = e.w; binterior = interior; bpd = pd; }
-    v0x = e.x; v0y = e.y;
-  }
-  if (inside) return make_float3(maxpd, -mnx, -mny);
-  if (binterior) return make_float3(fabsf(bpd), -benx, -beny);
-  const float d = sqrtf(bestd2);
-  const float inv = 1.f / (d + 1.17549435e-38f);
-  return make_float3(d, -bdx * inv, -bdy * inv);
-}
-
-__device__ __forceinline__ void hull_closest(const MapView& m, int h, float px, float py, float& d, float& nx,
-                                             float& ny) {
-  const float3 r = hull_closest_impl(m.edge, m.hull_eo[h], px, py);
-  d = r.x; nx = r.y; ny = r.z;
-}
-
-// cpBBSegmentQuery(bb, a, b) < 1: the BB-tree visits a leaf only if the THIN segment enters its bb.
-// (idx, idy) = 1 / (b - a) per axis (unused where the delta is exactly zero).
-__device__ __forceinline__ bool thin_bb_hit(const float4 bb, float ox, float oy, bool zx, bool zy, float idx,
-                                            float idy) {
-  float tmin = -CUDART_INF_F, tmax = CUDART_INF_F;
-  if (zx) {
-    if (ox < bb.x || bb.z < ox) return false;
-  } else {
-    const float t1 = (bb.x - ox) * idx, t2 = (bb.z - ox) * idx;
-    tmin = fminf(t1, t2);
-    tmax = fmaxf(t1, t2);
-  }
-  if (zy) {
-    if (oy < bb.y || bb.w < oy) return false;
-  } else {
-    const float t1 = (bb.y - oy) * idy, t2 = (bb.w - oy) * idy;
-    tmin = fmaxf(tmin, fminf(t1, t2));
-    tmax = fminf(tmax, fmaxf(t1, t2));
-  }
-  return (tmin <= tmax) && (0.f <= tmax) && (tmin < 1.f);
-}
-
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-// Depth-buffer key of a ray: (float bits of s) << 32 | feature.  Walls: edge * 2 + (1 = bevelled vertex);
-// agents: kAgentTag + j — larger than any wall feature, so at equal s the static shape wins, like
-// cpSpaceSegmentQueryFirst (static index first, dynamic only if strictly closer).  s = distance along
-// the ray of the fat-ray centre at first touch (alpha * L).
-constexpr uint32_t kAgentTag = 0x40000000u;
-constexpr uint32_t kNoFeature = 0xFFFFFFFFu;
-__device__ __forceinline__ unsigned long long make_key(float s, uint32_t feat) {
-  return ((unsigned long long)__float_as_uint(s) << 32) | feat;
-}
-
-// atan2 to ~1e-4 rad (odd minimax polynomial on [0,1] + octant folding); callers pad their angular
-// spans by 2e-3 rad, so this only ever adds a spare (edge, ray) test, never drops one.
-__device__ __forceinline__ float fast_atan2(float y, float x) {
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float a = __fdividef(fminf(ax, ay), fmaxf(fmaxf(ax, ay), 1e-30f));
-  const float q = a * a;
-  float r = fmaf(fmaf(fmaf(-0.0464964749f, q, 0.15931422f), q, -0.327622764f), q * a, a);
-  if (ay > ax) r = 1.57079637f - r;
-  if (x < 0.f) r = 3.14159274f - r;
-  return copysignf(r, y);
-}
-
-// float16(npy_hypotf(dx, dy)) for float16-valued dx, dy: numpy evaluates hypotf (glibc: sqrt in double, rounded to
-// float) and then rounds to half.  dx*dx and dy*dy are exact in fp32 (11-bit significands), so
-// sqrt.rn.f32(fma(dx, dx, dy*dy)) is within 1.5 fp32 ulp of that float; the two can only round to different
-// halves when the low 13 bits sit within 2 ulp of the tie point (or in the half-subnormal range): only then is the
-// double-precision path taken (about 6 rays in 10^4).
-__device__ __forceinline__ uint16_t half_hypot_bits(float dxh, float dyh) {
-  float hyp = __fsqrt_rn(fmaf(dxh, dxh, dyh * dyh));
-  const uint32_t low = __float_as_uint(hyp) & 0x1FFFu;
-  if ((low - 0x0FFEu <= 4u) || hyp < 6.2e-5f) hyp = (float)sqrt((double)dxh * (double)dxh + (double)dyh * (double)dyh);
-  return __half_as_ushort(__float2half_rn(hyp));
-}
-
-struct Ray {
-  float ox, oy, ux, uy, L;
-  bool zx, zy;      // direction component exactly zero (cpBBSegmentQuery special case)
-  float idx, idy;   // 1 / (L * u)
-};
-
-// One edge of cpPolyShapeSegmentQuery against the ray o + s*u: plane i offset by rsum = wall_r + ray_r
-// (accepted inside the edge's tangential extent) and the bevelled vertex v_i as a circle of radius rsum
-// (CircleSegmentQuery, perpendicular-offset form of the discriminant).  Returns the smaller s (INF if
-// neither is hit; range / nearest checks are the caller's) and which of the two it was.
-__device__ __forceinline__ float ray_edge(const float4 e, float len, const Ray& r, float rsum, float rs2, int& kind) {
-  const float rx = r.ox - e.x, ry = r.oy - e.y;
-  const float d = fmaf(rx, e.z, fmaf(ry, e.w, -rsum));   // a.n - v0.n - rsum
-  const float un = fmaf(r.ux, e.z, r.uy * e.w);          // (b.n - a.n) / L
-  float s = CUDART_INF_F;
-  kind = 0;
-  if (d >= 0.f && un < 0.f) {
-    const float sp = __fdividef(d, -un);
-    const float c = fmaf(e.z, fmaf(sp, r.uy, ry), -e.w * fmaf(sp, r.ux, rx));  // cross(n, P - v_i) in [-len, 0]
-    if (c <= 0.f && c >= -len) s = sp;
-  }
-  const float cp = fmaf(rx, r.uy, -ry * r.ux);
-  const float disc = fmaf(-cp, cp, rs2);
-  if (disc >= 0.f) {
-    const float sc = -fmaf(rx, r.ux, ry * r.uy) - fast_sqrt(disc);
-    if (sc >= 0.f && sc < s) { s = sc; kind = 1; }
-  }
-  return s;
-}
-
-// Surface normal of a wall hit (plane: the edge normal; bevel: from the vertex to the ray centre).
-__device__ __forceinline__ float2 wall_hit_normal(const MapView& m, uint32_t feat, float s, const Ray& r, float rsum) {
-  const float4 e = m.edge[feat >> 1];
-  if ((feat & 1u) == 0) return make_float2(e.z, e.w);
-  const float inv = 1.f / rsum;
-  return make_float2((r.ox - e.x + s * r.ux) * inv, (r.oy - e.y + s * r.uy) * inv);
-}
-
-__device__ __forceinline__ Ray make_ray(float ax, float ay, float dx, float dy) {
-  Ray r;
-  r.ox = ax; r.oy = ay;
-  r.L = sqrtf(dx * dx + dy * dy);
-  const float inv = r.L > 0.f ? 1.f / r.L : 0.f;
-  r.ux = dx * inv; r.uy = dy * inv;
-  r.zx = dx == 0.f; r.zy = dy == 0.f;
-  r.idx = r.zx ? 0.f : 1.f / dx;
-  r.idy = r.zy ? 0.f : 1.f / dy;
-  return r;
-}
-
-// Thin segment a -> b against the wall hulls h0, h0+32, ... with query radius 0 (capture line of
-// sight, base_env.py:536-544): true if any blocks (alpha < 1), including the alpha = 0 rule.
-// Rare path (only evaluated for thief-cop pairs closer than the capture radius): not inlined.
-__device__ __noinline__ bool los_blocked(const unsigned char* blob, int h0, float ax, float ay, float bx, float by,
-                                         float wall_r) {
-  const MapView m = make_view(blob);
-  const Ray r = make_ray(ax, ay, bx - ax, by - ay);
-  bool blocked = false;
-#pragma unroll 1
-  for (int h = h0; h < m.H && !blocked; h += 32) {
-    if (!thin_bb_hit(m.hull_bb[h], ax, ay, r.zx, r.zy, r.idx, r.idy)) continue;
-    const float3 c = hull_closest_impl(m.edge, m.hull_eo[h], ax, ay);
-    if (c.x - wall_r <= 0.f) { blocked = true; break; }  // start point inside the rounded hull
-    if (!(r.L > 0.f)) continue;
-    const uint32_t eo = m.hull_eo[h];
-#pragma unroll 1
-    for (int ei = eo & 0xFFFF, ee = (eo & 0xFFFF) + (eo >> 16); ei < ee && !blocked; ++ei) {
-      int kind;
-      blocked = ray_edge(m.edge[ei], m.edge_len[ei], r, wall_r, wall_r * wall_r, kind) < r.L;  // alpha < 1
-    }
-  }
-  return blocked;
-}
-
-__device__ __forceinline__ int grid_cell(const MapView& m, float x, float y) {
-  const float gx = (x - m.gx0) * m.inv_cell, gy = (y - m.gy0) * m.inv_cell;
-  if (!(gx >= 0.f && gy >= 0.f && gx < (float)m.nx && gy < (float)m.ny)) return -1;
-  return (int)gy * m.nx + (int)gx;
-}
-
-// ------------------------------------------------------------------ per-warp world context
-struct Warp {
-  float* rec;
-  uint16_t* rdist;
-  uint8_t* rtype;
-  uint32_t* minbits;
-  uint16_t* near;
-  uint32_t* nearcnt;
-  float* con;       // contact entries, 8 words each
-  uint32_t* ccount; // wall contacts per agent
-  uint8_t* order;   // compact solver order
-  unsigned long long* best;  // per ray: (float bits of s) << 32 | feature id  — the 1-D depth buffer
-  uint16_t* cand;   // candidate edge ids awaiting rasterisation
-  const unsigned char* blob;  // the map blob in shared memory
-  int lane;
-};
-
-// Rasterise up to 32 candidate edges (cand[0..n)) of one agent into its per-ray depth buffer `best`.
-// Lane l owns candidate l and computes the span of ray indices whose thin line can come within rsum of
-// the edge (conservative: angle of the offset segment's far end and of the bevel circle, padded); the
-// (edge, ray) pairs of all 32 spans are then flattened with a warp scan so that every lane tests one
-// pair per iteration regardless of how uneven the spans are.  Not inlined: one compact copy keeps the
-// kernel's instruction footprint inside the instruction cache.
-__device__ __noinline__ void raster_batch(const unsigned char* blob, unsigned long long* best, const uint16_t* cand,
-                                          int n, float ox, float oy, float rsum, float L, int R) {
-  const MapView m = make_view(blob);
-  const int lane = threadIdx.x & 31;
-  const float rs2 = rsum * rsum, inv_L = 1.f / L;
-  int e = 0, i0 = 0, cnt = 0;
-  if (lane < n) {
-    e = cand[lane];
-    const float4 ed = m.edge[e];
-    const float bx = ed.x - ox, by = ed.y - oy;           // B - o (B = v_i, the vertex ending the edge)
-    const float nb2 = bx * bx + by * by;
-    if (nb2 <= rs2) { cnt = R; }                           // origin inside the bevel circle: every direction
-    else {
-      const float thB = fast_atan2(by, bx);
-      const float x = fminf(rsum * rsqrtf(nb2), 1.f);
-      const float wv = x * fmaf(0.5708f, x * x, 1.f);     // >= asin(x) on [0,1]: half-width of the bevel circle
-      float lo = -wv, hi = wv;
-      const float pd = -(bx * ed.z + by * ed.w);          // (o - B).n
-      if (pd - rsum >= 0.f) {
-        // offset segment A'B' (B' lies on the bevel circle, already covered): far end A' = B - len*t + n*rsum
-        const float len = m.edge_len[e];
-        const float apx = bx + ed.z * rsum + len * ed.w, apy = by + ed.w * rsum - len * ed.z;   // t = (-ny, nx)
-        float dA = fast_atan2(apy, apx) - thB;
-        dA = dA > CUDART_PI_F ? dA - 2.f * CUDART_PI_F : (dA < -CUDART_PI_F ? dA + 2.f * CUDART_PI_F : dA);
-        lo = fminf(lo, dA); hi = fmaxf(hi, dA);
-      }
-      const float pad = 2e-3f;
-      const float inv_dth = (float)R * (0.5f / CUDART_PI_F);
-      const int ilo = (int)ceilf((thB + lo - pad) * inv_dth), ihi = (int)floorf((thB + hi + pad) * inv_dth);
-      cnt = min(max(ihi - ilo + 1, 0), R);
-      i0 = ilo;                                            // |ilo| < 2R
-      if (i0 < 0) i0 += R;
-      if (i0 < 0) i0 += R;
-      if (i0 >= R) i0 -= R;
-      if (cnt > 0 && cnt <= 3) {
-        // Occlusion: a narrow (far) edge whose every ray already holds a strictly nearer hit cannot win the
-        // depth test.  Any hit on this edge or its bevel has s >= dist(origin, raw segment) - rsum.
-        const float len = m.edge_len[e];
-        const float qa = fmaf(-by, ed.z, bx * ed.w);        // position of o along A->B, relative to B
-        const float dq = qa - fminf(fmaxf(qa, -len), 0.f);
-        const float smin = fast_sqrt(fmaf(pd, pd, dq * dq)) * 0.9999f - rsum - 1e-3f;
-        bool occluded = true;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          int i = i0 + q;
-          if (i >= R) i -= R;
-          if (q < cnt) occluded = occluded && __uint_as_float((uint32_t)(best[i] >> 32)) < smin;
-        }
-        CAT_COUNT(2, 1);
-        if (occluded) { cnt = 0; CAT_COUNT(3, 1); }
-      }
-    }
-    CAT_COUNT(0, 1);
-    CAT_COUNT(1, cnt);
-  }
-  int scan = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, scan, d); if (lane >= d) scan += t; }
-  const int total = __shfl_sync(0xFFFFFFFFu, scan, 31);
-  const int excl = scan - cnt;
-#pragma unroll 1
-  for (int p0 = 0; p0 < total; p0 += 32) {
-    const int p = p0 + lane;
-    int l = 0;   // owner = first lane whose inclusive scan exceeds p
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const int v = __shfl_sync(0xFFFFFFFFu, scan, l + step - 1);
-      if (v <= p) l += step;
-    }
-    l = min(l, 31);
-    const int el = __shfl_sync(0xFFFFFFFFu, e, l), i0l = __shfl_sync(0xFFFFFFFFu, i0, l);
-    const int exl = __shfl_sync(0xFFFFFFFFu, excl, l);
-    if (p < total) {
-      int i = i0l + (p - exl);
-      if (i >= R) i -= R;
-      const float4 dv = m.dir[i];
-      Ray r;
-      r.ox = ox; r.oy = oy; r.ux = dv.x; r.uy = dv.y; r.L = L;
-      r.zx = dv.x == 0.f; r.zy = dv.y == 0.f; r.idx = dv.z * inv_L; r.idy = dv.w * inv_L;
-      int kind;
-      const float sHit = ray_edge(m.edge[el], m.edge_len[el], r, rsum, rs2, kind);
-      if (sHit < L) {
-        unsigned long long* slot = &best[i];
-        const unsigned long long key = make_key(sHit, (uint32_t)(el * 2 + kind));
-        // cpBBTree leaf test: a hull is only ever visited if the THIN ray enters its bb (rarely fails, so
-        // it is evaluated only for hits that would win the depth test)
-        if (key < *slot && thin_bb_hit(m.hull_bb[m.edge_hull[el]], ox, oy, r.zx, r.zy, r.idx, r.idy)) atomicMin(slot, key);
-      }
-    }
-  }
-}
-
-// Sensor sweep of every agent of one world (entity.py:159-220) into shared memory.
-//
-// 90 rays from one origin are a 1-D depth buffer, so the walls are RASTERISED into it instead of each
-// ray searching the map: per agent, (1) lanes = rays: seed the buffer with the other agents' circles and
-// the alpha = 0 rules; (2) lanes = edges: keep edges that face the origin and lie within range, then
-// expand them into (edge, ray) pairs spread evenly over the lanes (raster_batch) and resolve the nearest
-// hit per ray with a 64-bit shared-memory atomicMin; (3) lanes = rays: hit point, float16 chain, type.
-// Work is proportional to what is actually in view (~2 edge tests per ray on agh-map), lanes stay
-// converged, and there is no per-ray traversal.
-__device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
-  const int A = k.A, R = k.R, lane = w.lane, E = k.n_edges;
-  const float* pos = w.rec;
-  const float* tc = w.rec + k.o_tc;
-  const uint32_t flags = reinterpret_cast<const uint32_t*>(w.rec)[k.o_flags];
-  const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len;
-  const float reach = k.agent_r + k.ray_r, reach2 = reach * reach, inv_reach = 1.f / reach;
-  const float range2 = (L + rsum) * (L + rsum);
-  // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates.
-  // Only agents flagged by the last physics step / re-spawn (a wall within contact reach) can have any.
-  if (lane < A) {
-    uint32_t cnt = 0;
-    if ((flags >> lane) & 1u) {
-      const float px = pos[2 * lane], py = pos[2 * lane + 1];
-      const int cell = grid_cell(m, px, py);
-      if (cell >= 0) {
-        for (int q = m.con_off[cell]; q < m.con_off[cell + 1]; ++q) {
-          const int h = m.con_list[q];
-          const float4 bb = m.hull_bb[h];  // already grown by wall_r: cheap reject before the exact distance
-          if (px < bb.x - k.ray_r || px > bb.z + k.ray_r || py < bb.y - k.ray_r || py > bb.w + k.ray_r) continue;
-          float d, nx, ny;
-          hull_closest(m, h, px, py, d, nx, ny);
-          if (d - k.wall_r <= k.ray_r && cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
-        }
-      }
-    }
-    w.nearcnt[lane] = cnt;
-    w.minbits[lane] = kEmpty;
-  }
-  __syncwarp();
-
-  const int nsub = (R + 31) >> 5;
-#pragma unroll 1
-  for (int a = 0; a < A; ++a) {
-    // ---- warp-uniform, per agent
-    const float ox = pos[2 * a], oy = pos[2 * a + 1];
-    const uint32_t ncnt = w.nearcnt[a];
-    int zero_agent = -1;   // first other agent whose circle is within ray_r of the origin (alpha = 0)
-    for (int j = A - 1; j >= 0; --j) {
-      if (j == a) continue;
-      const float ddx = ox - tc[2 * j], ddy = oy - tc[2 * j + 1];
-      if (ddx * ddx + ddy * ddy <= reach2) zero_agent = j;
-    }
-
-    // ---- (1) clear the depth buffer (the dynamic shapes and the alpha = 0 rules are merged in step 3)
-#pragma unroll 1
-    for (int i = lane; i < R; i += 32) w.best[a * R + i] = make_key(L, kNoFeature);
-    __syncwarp();
-
-    // ---- (2) lanes = edges: candidates face the origin (plane i or the next plane, which share vertex v_i
-    //          and hence its bevel) and lie within sensor range of the origin
-    //          Batches of 32 edges (hulls are stored in Morton order, so a batch is compact) are visited NEAR TO FAR:
-    //          lane b measures the distance of batch b's bounding box once, a counting rank orders them, and
-    //          the walk stops at the first batch beyond sensor range.  Near walls are then already in the depth
-    //          buffer when the far edges are set up, which lets the rasteriser drop occluded edges.
-    int ncand = 0;
-    const int nb = (E + 31) >> 5;
-    // Preferred source of edges: the static list of this origin's grid cell (the edges that can be candidates
-    // for SOME origin in the cell, nearest first; global memory / L2, next batch prefetched) — on agh-map ~150
-    // of 496 edges.  Origins outside the grid, or environments created without lists, scan the batches.
-    int vq = 0, vq1 = 0;
-    const int vcell = k.view_off ? grid_cell(m, ox, oy) : -1;
-    const bool use_view = vcell >= 0;
-    uint32_t vnext = 0xFFFFu;
-    if (use_view) {
-      vq = __ldg(k.view_off + vcell); vq1 = __ldg(k.view_off + vcell + 1);
-      if (vq + lane < vq1) vnext = __ldg(k.view_edges + vq + lane);
-    }
-    const bool ordered = !use_view && nb <= 32;
-    float bdist = CUDART_INF_F;
-    int brank = 0;
-    if (ordered) {
-      if (lane < nb) {
-        const float4 bb = m.batch_bb[lane];
-        const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
-        bdist = fmaf(ddx, ddx, ddy * ddy);
-      }
-#pragma unroll 1
-      for (int j = 0; j < nb; ++j) {
-        const float dj = __shfl_sync(0xFFFFFFFFu, bdist, j);
-        brank += (dj < bdist || (dj == bdist && j < lane)) ? 1 : 0;
-      }
-    }
-#pragma unroll 1
-    for (int it = 0; ; ++it) {
-      int e;
-      if (use_view) {
-        if (vq >= vq1) break;
-        e = vnext == 0xFFFFu ? E : (int)vnext;
-        vq += 32;
-        vnext = vq + lane < vq1 ? (uint32_t)__ldg(k.view_edges + vq + lane) : 0xFFFFu;
-      } else {
-        if (it >= nb) break;
-        int base;
-        if (ordered) {
-          const int b = __ffs(__ballot_sync(0xFFFFFFFFu, lane < nb && brank == it)) - 1;
-          if (__shfl_sync(0xFFFFFFFFu, bdist, b) >= range2) break;   // this and every later batch is out of range
-          base = b << 5;
-        } else {
-          base = it << 5;
-          const float4 bb = m.batch_bb[it];
-          const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
-          if (fmaf(ddx, ddx, ddy * ddy) >= range2) continue;
-        }
-        e = base + lane;
-      }
-      bool is_cand = false;
-      if (e < E) {
-        const float4 ed = m.edge[e];
-        const float2 nn = m.next_n[e];
-        const float rx = ox - ed.x, ry = oy - ed.y;
-        const float pd = rx * ed.z + ry * ed.w;
-        const float pdn = rx * nn.x + ry * nn.y;
-        const float len = m.edge_len[e];
-        const float qa = fmaf(ry, ed.z, -rx * ed.w);       // position of o along A->B, relative to B
-        const float dq = qa - fminf(fmaxf(qa, -len), 0.f);
-        is_cand = (pd > 0.f || pdn > 0.f) && (fmaf(pd, pd, dq * dq) < range2);
-      }
-      const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
-      if (is_cand) w.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)e;
-      ncand += __popc(cmask);
-      __syncwarp();
-      if (ncand >= 32) {
-        raster_batch(w.blob, w.best + a * R, w.cand, 32, ox, oy, rsum, L, R);
-        __syncwarp();
-        uint16_t t = 0;
-        if (lane + 32 < ncand) t = w.cand[lane + 32];
-        __syncwarp();
-        if (lane + 32 < ncand) w.cand[lane] = t;
-        ncand -= 32;
-        __syncwarp();
-      }
-    }
-    if (ncand > 0) raster_batch(w.blob, w.best + a * R, w.cand, ncand, ox, oy, rsum, L, R);
-    __syncwarp();
-
-    // the other agents' cached centres relative to this origin, compacted (the candidate queue is free now)
-    float4* others = reinterpret_cast<float4*>(w.cand);
-    if (lane < A && lane != a)
-      others[lane < a ? lane : lane - 1] = make_float4(ox - tc[2 * lane], oy - tc[2 * lane + 1], __uint_as_float(kAgentTag + lane), 0.f);
-    __syncwarp();
-
-    // ---- (3) lanes = rays: entity.py:200-215 — hit point, float16 chain at each of its rounding points, type
-    const float oxh = __half2float(__float2half_rn(ox)), oyh = __half2float(__float2half_rn(oy));
-    const int want = (a < k.nc) ? TYPE_THIEF : TYPE_COP;
-#pragma unroll 1
-    for (int sub = 0; sub < nsub; ++sub) {
-      const int i = sub * 32 + lane;
-      if (i < R) {
-        const int r = a * R + i;
-        const float4 dv = m.dir[i];
-        unsigned long long key = w.best[r];     // nearest wall hit from the rasteriser
-        {
-          Ray rq;
-          rq.ox = ox; rq.oy = oy; rq.ux = dv.x; rq.uy = dv.y; rq.L = L;
-          rq.zx = dv.x == 0.f; rq.zy = dv.y == 0.f; rq.idx = dv.z * inv_L; rq.idy = dv.w * inv_L;
-          // dynamic shapes: the other agents' cached centres (keys order walls before agents at equal s)
-          if (zero_agent >= 0) key = min(key, make_key(0.f, kAgentTag + zero_agent));
-          else {
-#pragma unroll 1
-            for (int q = 0; q < A - 1; ++q) {   // CircleSegmentQuery against a cached agent centre, perpendicular-offset form
-              const float4 o4 = others[q];
-              const float cp = fmaf(o4.x, dv.y, -o4.y * dv.x);
-              const float disc = fmaf(-cp, cp, reach2);
-              if (disc >= 0.f) {
-                const float sc = -fmaf(o4.x, dv.x, o4.y * dv.y) - fast_sqrt(disc);
-                if (sc >= 0.f && sc < L) key = min(key, make_key(sc, __float_as_uint(o4.z)));
-              }
-            }
-          }
-          // static shapes with the origin inside their reach: alpha = 0, but only if the thin ray enters the bb
-#pragma unroll 1
-          for (uint32_t q = 0; q < ncnt; ++q) {
-            const int h = w.near[a * kNear + q];
-            if (thin_bb_hit(m.hull_bb[h], ox, oy, rq.zx, rq.zy, rq.idx, rq.idy)) key = min(key, make_key(0.f, 0u));
-          }
-        }
-        const uint32_t feat = (uint32_t)key;
-        const float sHit = __uint_as_float((uint32_t)(key >> 32));
-        uint16_t dbits;
-        uint8_t type;
-        float hx = fmaf(L, dv.x, ox), hy = fmaf(L, dv.y, oy);   // ray end: reported when nothing is hit or alpha = 0
-        if (feat == kNoFeature) {
-          dbits = __half_as_ushort(__float2half_rn(L));
-          type = TYPE_EMPTY;
-        } else {
-          const bool is_agent = feat >= kAgentTag;
-          if (sHit > 0.f) {
-            float2 n;
-            if (!is_agent) {
-              Ray rr; rr.ox = ox; rr.oy = oy; rr.ux = dv.x; rr.uy = dv.y;
-              n = wall_hit_normal(m, feat, sHit, rr, rsum);
-            } else {
-              const int j = (int)(feat - kAgentTag);
-              n = make_float2((ox - tc[2 * j] + sHit * dv.x) * inv_reach, (oy - tc[2 * j + 1] + sHit * dv.y) * inv_reach);
-            }
-            hx = ox + sHit * dv.x - n.x * k.ray_r; hy = oy + sHit * dv.y - n.y * k.ray_r;
-          }
-          const float pxh = __half2float(__float2half_rn(hx)), pyh = __half2float(__float2half_rn(hy));
-          const float dxh = __half2float(__float2half_rn(pxh - oxh));
-          const float dyh = __half2float(__float2half_rn(pyh - oyh));
-          dbits = half_hypot_bits(dxh, dyh);
-          type = !is_agent ? TYPE_WALL : ((int)(feat - kAgentTag) >= k.nc ? TYPE_THIEF : TYPE_COP);
-          // rewards need the nearest opponent seen by this agent (cop.py:66-70, thief.py:60-63)
-          if (type == want) atomicMin(&w.minbits[a], (uint32_t)dbits);
-        }
-        w.rdist[r] = dbits;
-        w.rtype[r] = type;
-        if (k.hit_point) {
-          float2* hp = reinterpret_cast<float2*>(k.hit_point) + (size_t)world * k.nrays + r;
-          *hp = make_float2(hx, hy);
-        }
-      }
-    }
-    __syncwarp();   // `others` aliases the candidate queue of the next agent
-  }
-  __syncwarp();
-}
-
-// Optional fp32 layouts (what skrl's wrapper would build on the host): per-agent flattened observation
-// and the flattened centralised-critic state.  Only called when the caller asked for them; kept out of
-// line so the native-dtype fast path stays small.
-__device__ __noinline__ void write_flat_layouts(const KParams& k, const uint16_t* rdist, const uint8_t* rtype,
-                                                const float* pos, long long world) {
-  const int A = k.A, R = k.R, lane = threadIdx.x & 31;
-  if (k.obs_f32) {  // [A][N][2R]: [distance | object_type] as skrl flattens the Dict (keys sorted)
-#pragma unroll 1
-    for (int a = 0; a < A; ++a) {
-      float* dst = k.obs_f32 + ((size_t)a * k.n_worlds + world) * (2 * R);
-#pragma unroll 1
-      for (int i = lane; i < 2 * R; i += 32)
-        dst[i] = i < R ? __half2float(__ushort_as_half(rdist[a * R + i])) : (float)rtype[a * R + i - R];
-    }
-  }
-  if (k.state_f32) {
-    // env.state(): per agent [distance_shared | object_type_shared | own_distances | own_obj_types | team_positions]
-    float* dst = k.state_f32 + (size_t)world * k.state_dim;
-    int base = 0;
-#pragma unroll 1
-    for (int a = 0; a < A; ++a) {
-      const int team = a < k.nc ? 0 : 1;
-      const int a0 = team == 0 ? 0 : k.nc, a1 = team == 0 ? k.nc : A;
-      const int blk = 4 * R + 2 * (a1 - a0);
-#pragma unroll 1
-      for (int i = lane; i < blk; i += 32) {
-        float v;
-        if (i < 2 * R) {
-          const int ri = i < R ? i : i - R;
-          uint8_t t = TYPE_EMPTY;
-          uint16_t d = 0;
-#pragma unroll 1
-          for (int b = a0; b < a1; ++b)
-            if (t == TYPE_EMPTY) { t = rtype[b * R + ri]; d = rdist[b * R + ri]; }
-          v = i < R ? __half2float(__ushort_as_half(d)) : (float)t;
-        } else if (i < 3 * R) v = __half2float(__ushort_as_half(rdist[a * R + i - 2 * R]));
-        else if (i < 4 * R) v = (float)rtype[a * R + i - 3 * R];
-        else v = __half2float(__float2half_rn(pos[2 * a0 + (i - 4 * R)]));
-        dst[base + i] = v;
-      }
-      base += blk;
-    }
-  }
-}
-
-// Write the observation-side outputs of one world from shared memory (coalesced).
-__device__ __forceinline__ void write_observation(const KParams& k, const Warp& w, long long world) {
-  const int A = k.A, R = k.R, lane = w.lane, nrays = k.nrays;
-  const float* pos = w.rec;
-  if (k.obs_vec) {
-    // 16-byte aligned world blocks (mapped pinned host memory): one or two 512-byte warp stores per array
-    if (k.obs_dist) {
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(k.obs_dist) + (size_t)world * k.dist_stride);
-      const uint4* src = reinterpret_cast<const uint4*>(w.rdist);
-#pragma unroll 1
-      for (int i = lane; i < (nrays * 2 + 15) / 16; i += 32) dst[i] = src[i];
-    }
-    if (k.obs_type) {
-      uint4* dst = reinterpret_cast<uint4*>(k.obs_type + (size_t)world * k.type_stride);
-      const uint4* src = reinterpret_cast<const uint4*>(w.rtype);
-#pragma unroll 1
-      for (int i = lane; i < (nrays + 15) / 16; i += 32) dst[i] = src[i];
-    }
-  } else {
-    if (k.obs_dist) {
-      unsigned char* base = reinterpret_cast<unsigned char*>(k.obs_dist) + (size_t)world * k.dist_stride;
-      if (((nrays | (k.dist_stride >> 1)) & 1) == 0) {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(base);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(w.rdist);
-#pragma unroll 1
-        for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
-      } else {
-        uint16_t* dst = reinterpret_cast<uint16_t*>(base);
-#pragma unroll 1
-        for (int i = lane; i < nrays; i += 32) dst[i] = w.rdist[i];
-      }
-    }
-    if (k.obs_type) {
-      uint8_t* base = k.obs_type + (size_t)world * k.type_stride;
-      if (((nrays | k.type_stride) & 1) == 0) {
-        uint16_t* dst = reinterpret_cast<uint16_t*>(base);
-        const uint16_t* src = reinterpret_cast<const uint16_t*>(w.rtype);
-#pragma unroll 1
-        for (int i = lane; i < nrays / 2; i += 32) dst[i] = src[i];
-      } else {
-#pragma unroll 1
-        for (int i = lane; i < nrays; i += 32) base[i] = w.rtype[i];
-      }
-    }
-  }
-  if (k.team_pos) {  // observation_spaces.py:92-95
-#pragma unroll 1
-    for (int i = lane; i < 2 * A; i += 32)
-      k.team_pos[(size_t)world * 2 * A + i] = __half_as_ushort(__float2half_rn(pos[i]));
-  }
-  // observation_spaces.py:97-121 net effect: first non-EMPTY (type, distance) in team order
-  if (k.shared_dist || k.shared_type) {
-#pragma unroll 1
-    for (int team = 0; team < 2; ++team) {
-      const int a0 = team == 0 ? 0 : k.nc, a1 = team == 0 ? k.nc : A;
-#pragma unroll 1
-      for (int i = lane; i < R; i += 32) {
-        uint8_t t = TYPE_EMPTY;
-        uint16_t d = 0;
-#pragma unroll 1
-        for (int a = a0; a < a1; ++a)
-          if (t == TYPE_EMPTY) { t = w.rtype[a * R + i]; d = w.rdist[a * R + i]; }
-        if (k.shared_dist) k.shared_dist[((size_t)world * 2 + team) * R + i] = d;
-        if (k.shared_type) k.shared_type[((size_t)world * 2 + team) * R + i] = t;
-      }
-    }
-  }
-  if (k.obs_f32 || k.state_f32) write_flat_layouts(k, w.rdist, w.rtype, pos, world);
-}
-
-// cop.py:49-75 / thief.py:48-69 in fp32 from the f16 distance.
-__device__ __forceinline__ float agent_reward(const KParams& k, int a, uint32_t minbits, bool captured, bool timeout) {
-  const bool is_cop = a < k.nc;
-  if (captured) return is_cop ? 1.f : -1.f;
-  if (timeout) return is_cop ? -1.f : 1.f;
-  const bool seen = minbits != kEmpty;
-  const float d = seen ? __half2float(__ushort_as_half((uint16_t)minbits)) : 0.f;
-  if (is_cop) return seen ? (-0.02f + 1.5f * expf(-d / 50.f)) : -0.04f;
-  return seen ? tanhf((d - 100.f) / 50.f) / 10.f : 0.15f;
-}
-
-// cpSpaceStep(dt) for one world, state in shared memory.
-__device__ __forceinline__ void physics_world(const KParams& k, const MapView& m, const Warp& w) {
-  const int A = k.A, P = k.P, lane = w.lane;
-  float* pos = w.rec;
-  float* vel = w.rec + k.o_vel;
-  float* vb = w.rec + k.o_vb;
-  float* tc = w.rec + k.o_tc;
-  uint32_t* wkey = reinterpret_cast<uint32_t*>(w.rec + k.o_wkey);
-  float* wjn = w.rec + k.o_wjn;
-  uint32_t* page = reinterpret_cast<uint32_t*>(w.rec + k.o_page);
-  float* pjn = w.rec + k.o_pjn;
-  const float rsum_w = k.agent_r + k.wall_r;
-
-  // (1) cpBodyUpdatePosition, (2) shape caches
-  if (lane < 2 * A) {
-    const float p = pos[lane] + (vel[lane] + vb[lane]) * k.dt;
-    pos[lane] = p; tc[lane] = p; vb[lane] = 0.f;
-  }
-  __syncwarp();
-
-  // (3) narrow phase.  Entry: {nx, ny, bias, jn, jBias, nMass, meta, slot}
-  // (3a) lanes = (agent, hull of the agent's grid cell) pairs: bounding-box reject + closest feature, all
-  //      pairs of the world in one pass; hits are staged per agent in list order ({nx, ny, d, hull}).
-  {
-    int q0 = 0, len = 0;
-    if (lane < A) {
-      const int cell = grid_cell(m, pos[2 * lane], pos[2 * lane + 1]);
-      if (cell >= 0) { q0 = m.con_off[cell]; len = m.con_off[cell + 1] - q0; }
-      w.ccount[lane] = 0;
-    }
-    int incl = len;   // inclusive scan over the (at most 8) agent lanes
-#pragma unroll
-    for (int d = 1; d < CAT_MAX_AGENTS; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-    const int total = __shfl_sync(0xFFFFFFFFu, incl, A - 1);
-    __syncwarp();
-#pragma unroll 1
-    for (int p0 = 0; p0 < total; p0 += 32) {
-      const int p = p0 + lane;
-      int a = 0;
-#pragma unroll 1
-      for (int j = 0; j < A - 1; ++j) a += (p >= __shfl_sync(0xFFFFFFFFu, incl, j)) ? 1 : 0;
-      const int q0a = __shfl_sync(0xFFFFFFFFu, q0, a), excl = __shfl_sync(0xFFFFFFFFu, incl - len, a);
-      bool hit = false;
-      float d = 0.f, nx = 0.f, ny = 0.f;
-      int h = 0;
-      if (p < total) {
-        h = m.con_list[q0a + (p - excl)];
-        const float px = pos[2 * a], py = pos[2 * a + 1];
-        const float4 bb = m.hull_bb[h];  // QueryReject: the shape bbs must overlap (hull bb already grown by wall_r)
-        if (!(px + k.agent_r < bb.x || bb.z < px - k.agent_r || py + k.agent_r < bb.y || bb.w < py - k.agent_r)) {
-          hull_closest(m, h, px, py, d, nx, ny);
-          hit = d <= rsum_w;  // CircleToPoly: d <= r_circle + r_poly
-        }
-      }
-      const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
-      const uint32_t same = __match_any_sync(0xFFFFFFFFu, a);
-      if (hit) {
-        const uint32_t rank = w.ccount[a] + __popc(hits & same & ((1u << lane) - 1u));
-        if (rank < (uint32_t)kSlots) {
-          float* c = w.con + (a * kSlots + rank) * 8;
-          c[0] = nx; c[1] = ny; c[2] = d;
-          reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)h;
-        }
-      }
-      __syncwarp();
-      if (hit && (hits & same & ((1u << lane) - 1u)) == 0) w.ccount[a] += __popc(hits & same);   // first hit lane of each agent
-      __syncwarp();
-    }
-  }
-  // (3b) lanes = agents: arbiter cache look-up for the staged contacts, in list order (cpArbiterUpdate)
-  if (lane < A) {
-    const uint32_t nstaged = min(w.ccount[lane], (uint32_t)kSlots);
-    uint32_t cnt = 0, used = 0;
-#pragma unroll 1
-    for (uint32_t idx = 0; idx < nstaged; ++idx) {
-      float* cs = w.con + (lane * kSlots + idx) * 8;
-      const float nx = cs[0], ny = cs[1], d = cs[2];
-      const int h = (int)reinterpret_cast<uint32_t*>(cs)[7];
-      // reuse the cached arbiter of this (agent, hull) pair if any
-      int slot = -1;
-#pragma unroll 1
-      for (int s = 0; s < kSlots; ++s)
-        if (wkey[lane * kSlots + s] != kEmpty && (wkey[lane * kSlots + s] & 0xFFFF) == (uint32_t)h) slot = s;
-      float jn0 = 0.f;
-      bool first = true;
-      if (slot >= 0) {
-        jn0 = wjn[lane * kSlots + slot];
-        first = (wkey[lane * kSlots + slot] >> 16) != 0;  // used in the previous step -> not first
-      } else {
-        // free slot, else the oldest slot not used this step
-        uint32_t oldest = 0;
-#pragma unroll 1
-        for (int s = 0; s < kSlots; ++s) {
-          if (used & (1u << s)) continue;
-          const uint32_t key = wkey[lane * kSlots + s];
-          const uint32_t age = key == kEmpty ? 0x10000u : (key >> 16) + 1u;
-          if (age > oldest) { oldest = age; slot = s; }
-        }
-      }
-      if (slot >= 0) {
-        used |= 1u << slot;
-        wkey[lane * kSlots + slot] = (uint32_t)h;  // age 0 = used this step
-        float* c = w.con + (lane * kSlots + cnt) * 8;   // cnt <= idx: never overwrites an unread staged entry
-        c[0] = nx; c[1] = ny;
-        c[2] = -k.bias_coef * fminf(0.f, (d - rsum_w) + k.slop) * k.inv_dt;  // cpArbiterPreStep
-        c[3] = jn0; c[4] = 0.f; c[5] = 1.f / k.inv_mass;
-        reinterpret_cast<uint32_t*>(c)[6] = (uint32_t)lane | (0xFFu << 8) | (first ? 1u << 16 : 0u);
-        reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)(lane * kSlots + slot);
-        ++cnt;
-      }
-    }
-    // cpSpaceArbiterSetFilter: arbiters not used this step age; dropped at collision_persistence
-#pragma unroll 1
-    for (int s = 0; s < kSlots; ++s) {
-      if (used & (1u << s)) continue;
-      const uint32_t key = wkey[lane * kSlots + s];
-      if (key == kEmpty) continue;
-      const uint32_t age = (key >> 16) + 1u;
-      if ((int)age >= k.persistence) { wkey[lane * kSlots + s] = kEmpty; wjn[lane * kSlots + s] = 0.f; }
-      else wkey[lane * kSlots + s] = (key & 0xFFFF) | (age << 16);
-    }
-    w.ccount[lane] = cnt;
-  }
-  {
-    // agents with a wall inside contact reach are the only ones that can start a ray inside a wall's reach next step
-    const uint32_t near_mask = __ballot_sync(0xFFFFFFFFu, lane < A && w.ccount[lane] > 0);
-    if (lane == 0) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = near_mask;
-  }
-  uint32_t pair_hit = 0;
-  if (lane < P) {
-    // pair index -> (i, j), i-major
-    int i = 0, rem = lane;
-#pragma unroll 1
-    while (rem >= A - 1 - i) { rem -= A - 1 - i; ++i; }
-    const int j = i + 1 + rem;
-    const float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1];
-    const float mind = 2.f * k.agent_r, dsq = dx * dx + dy * dy;
-    const uint32_t age = page[lane];
-    if (dsq < mind * mind) {  // CircleToCircle (strict)
-      const float dist = sqrtf(dsq);
-      float* c = w.con + (A * kSlots + lane) * 8;
-      const float invd = dist > 0.f ? 1.f / dist : 0.f;
-      c[0] = dist > 0.f ? dx * invd : 1.f;
-      c[1] = dy * invd;
-      c[2] = -k.bias_coef * fminf(0.f, (dist - mind) + k.slop) * k.inv_dt;
-      c[3] = age != kEmpty ? pjn[lane] : 0.f;
-      c[4] = 0.f; c[5] = 1.f / (2.f * k.inv_mass);
-      reinterpret_cast<uint32_t*>(c)[6] = (uint32_t)i | ((uint32_t)j << 8) | (age != 0 ? 1u << 16 : 0u);
-      reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)lane;
-      page[lane] = 0;
-      pair_hit = 1;
-    } else if (age != kEmpty) {
-      const uint32_t na = age + 1u;
-      if ((int)na >= k.persistence) { page[lane] = kEmpty; pjn[lane] = 0.f; } else page[lane] = na;
-    }
-  }
-  const uint32_t pair_mask = __ballot_sync(0xFFFFFFFFu, pair_hit != 0);
-  __syncwarp();
-
-  // (7) warm start + (8) sequential impulses.
-  // An iteration that changes no accumulated impulse leaves v / v_bias untouched too, so every later
-  // iteration would recompute exactly the same zeros: stopping there is bit-identical to running all of them.
-  if (pair_mask == 0) {
-    // No agent-agent contact: the wall contacts of different agents touch disjoint state, so their
-    // sequential-impulse sweeps are independent -> lane a solves agent a, velocities in registers.
-    const uint32_t n = lane < A ? w.ccount[lane] : 0u;
-    if (n > 0) {
-      const float minv = k.inv_mass;
-      float* cbase = w.con + lane * kSlots * 8;
-      float vx = vel[2 * lane], vy = vel[2 * lane + 1], bx = vb[2 * lane], by = vb[2 * lane + 1];
-#pragma unroll 1
-      for (uint32_t q = 0; q < n; ++q) {  // cpArbiterApplyCachedImpulse (dt_coef = 1)
-        const float* c = cbase + q * 8;
-        if (reinterpret_cast<const uint32_t*>(c)[6] & (1u << 16)) continue;  // first contact: nothing applied
-        vx -= c[0] * c[3] * minv; vy -= c[1] * c[3] * minv;
-      }
-#pragma unroll 1
-      for (int it = 0; it < k.iterations; ++it) {
-        bool changed = false;
-#pragma unroll 1
-        for (uint32_t q = 0; q < n; ++q) {  // cpArbiterApplyImpulse against a static body, e = 0, u = 0
-          float* c = cbase + q * 8;
-          const float nx = c[0], ny = c[1], nMass = c[5];
-          const float vbn = (-bx) * nx + (-by) * ny;
-          const float vrn = (-vx) * nx + (-vy) * ny;
-          const float jbnOld = c[4], jnOld = c[3];
-          const float jBias = fmaxf(jbnOld + (c[2] - vbn) * nMass, 0.f);
-          const float jnAcc = fmaxf(jnOld - vrn * nMass, 0.f);
-          c[4] = jBias; c[3] = jnAcc;
-          const float jb = (jBias - jbnOld) * minv, j = (jnAcc - jnOld) * minv;
-          bx -= nx * jb; by -= ny * jb;
-          vx -= nx * j; vy -= ny * j;
-          changed |= (jb != 0.f) | (j != 0.f);
-        }
-        if (!changed) break;
-      }
-      vel[2 * lane] = vx; vel[2 * lane + 1] = vy; vb[2 * lane] = bx; vb[2 * lane + 1] = by;
-#pragma unroll 1
-      for (uint32_t q = 0; q < n; ++q) {  // persist jnAcc in the arbiter cache
-        const float* c = cbase + q * 8;
-        wjn[reinterpret_cast<const uint32_t*>(c)[7]] = c[3];
-      }
-    }
-  } else if (lane == 0) {
-    // Agent-agent contacts couple the bodies: one fixed global order (wall contacts agent-major, then pairs), lane 0
-    int n = 0;
-#pragma unroll 1
-    for (int a = 0; a < A; ++a)
-#pragma unroll 1
-      for (uint32_t q = 0; q < w.ccount[a]; ++q) w.order[n++] = (uint8_t)(a * kSlots + q);
-#pragma unroll 1
-    for (int p = 0; p < P; ++p)
-      if (pair_mask & (1u << p)) w.order[n++] = (uint8_t)(A * kSlots + p);
-    const float minv = k.inv_mass;
-#pragma unroll 1
-    for (int q = 0; q < n; ++q) {  // cpArbiterApplyCachedImpulse (dt_coef = 1)
-      float* c = w.con + w.order[q] * 8;
-      const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
-      if (meta & (1u << 16)) continue;  // first contact: nothing applied
-      const int a = meta & 0xFF, b = (meta >> 8) & 0xFF;
-      const float jx = c[0] * c[3] * minv, jy = c[1] * c[3] * minv;
-      vel[2 * a] -= jx; vel[2 * a + 1] -= jy;
-      if (b != 0xFF) { vel[2 * b] += jx; vel[2 * b + 1] += jy; }
-    }
-#pragma unroll 1
-    for (int it = 0; it < k.iterations; ++it) {
-      bool changed = false;
-#pragma unroll 1
-      for (int q = 0; q < n; ++q) {  // cpArbiterApplyImpulse, e = 0, u = 0
-        float* c = w.con + w.order[q] * 8;
-        const uint32_t meta = reinterpret_cast<uint32_t*>(c)[6];
-        const int a = meta & 0xFF, b = (meta >> 8) & 0xFF;
-        const float nx = c[0], ny = c[1], nMass = c[5];
-        float vbx = -vb[2 * a], vby = -vb[2 * a + 1], vrx = -vel[2 * a], vry = -vel[2 * a + 1];
-        if (b != 0xFF) { vbx += vb[2 * b]; vby += vb[2 * b + 1]; vrx += vel[2 * b]; vry += vel[2 * b + 1]; }
-        const float vbn = vbx * nx + vby * ny;
-        const float vrn = vrx * nx + vry * ny;
-        const float jbnOld = c[4];
-        const float jBias = fmaxf(jbnOld + (c[2] - vbn) * nMass, 0.f);
-        const float jnOld = c[3];
-        const float jnAcc = fmaxf(jnOld - vrn * nMass, 0.f);
-        c[4] = jBias; c[3] = jnAcc;
-        const float jb = (jBias - jbnOld) * minv, j = (jnAcc - jnOld) * minv;
-        vb[2 * a] -= nx * jb; vb[2 * a + 1] -= ny * jb;
-        vel[2 * a] -= nx * j; vel[2 * a + 1] -= ny * j;
-        if (b != 0xFF) {
-          vb[2 * b] += nx * jb; vb[2 * b + 1] += ny * jb;
-          vel[2 * b] += nx * j; vel[2 * b + 1] += ny * j;
-        }
-        changed |= (jb != 0.f) | (j != 0.f);
-      }
-      if (!changed) break;
-    }
-#pragma unroll 1
-    for (int q = 0; q < n; ++q) {  // persist jnAcc in the arbiter cache
-      const float* c = w.con + w.order[q] * 8;
-      const uint32_t meta = reinterpret_cast<const uint32_t*>(c)[6];
-      const uint32_t slot = reinterpret_cast<const uint32_t*>(c)[7];
-      if (((meta >> 8) & 0xFF) == 0xFF) wjn[slot] = c[3]; else pjn[slot] = c[3];
-    }
-  }
-  __syncwarp();
-}
-
-// BaseEnv.reset for one world (base_env.py:313-350, _get_non_colliding_position :123-166).
-__device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
-  const int A = k.A, lane = w.lane;
-  float* pos = w.rec;
-  float* vel = w.rec + k.o_vel;
-  float* tc = w.rec + k.o_tc;
-  uint32_t* ep = reinterpret_cast<uint32_t*>(w.rec + k.o_ep);
-  const uint32_t episode = *ep + 1u;
-  float nx_ = 0.f, ny_ = 0.f;
-  if (lane < A) {
-    const int r0 = m.reg_off[lane], nr = m.reg_off[lane + 1] - r0;
-    if (nr > 0) {
-      const unsigned long long gid = (unsigned long long)(k.gid0 + world);
-      const uint32_t idx = cat_spawn_region_index(k.seed, gid, episode, (uint32_t)lane, (uint32_t)nr);
-      const float4 reg = m.regions[r0 + (int)idx];
-      nx_ = reg.x + reg.z / 2.f; ny_ = reg.y + reg.w / 2.f;  // base_env.py:163-166 fallback
-#pragma unroll 1
-      for (uint32_t t = 0; t < 20; ++t) {
-        float ux, uy;
-        cat_spawn_uniforms(k.seed, gid, episode, (uint32_t)lane, t, &ux, &uy);
-        const float px = fmaf(reg.z, ux, reg.x), py = fmaf(reg.w, uy, reg.y);
-        // point_query_nearest(pos, 5, ray_filter): any shape with distance < 5
-        bool blocked = false;
-        const int cell = grid_cell(m, px, py);
-        if (cell >= 0) {
-#pragma unroll 1
-          for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && !blocked; ++q) {
-            float d, ax, ay;
-            hull_closest(m, m.con_list[q], px, py, d, ax, ay);
-            if (d - k.wall_r < k.agent_r) blocked = true;
-          }
-        }
-#pragma unroll 1
-        for (int j = 0; j < A && !blocked; ++j) {
-          if (j == lane) continue;
-          const float dx = px - tc[2 * j], dy = py - tc[2 * j + 1];
-          if (sqrtf(dx * dx + dy * dy) - k.agent_r < k.agent_r) blocked = true;
-        }
-        if (!blocked) { nx_ = px; ny_ = py; break; }
-      }
-    } else {
-      const float2 ip = m.init_pos[lane];  // base_env.py:328-332 -> Entity.reset() default
-      nx_ = ip.x; ny_ = ip.y;
-    }
-  }
-  __syncwarp();  // every lane has finished reading the stale centres
-  if (lane < A) {
-    pos[2 * lane] = nx_; pos[2 * lane + 1] = ny_;       // entity.py:154-156
-    vel[2 * lane] = 0.f; vel[2 * lane + 1] = 0.f;        // entity.py:157
-    if (!k.stale) { tc[2 * lane] = nx_; tc[2 * lane + 1] = ny_; }
-  }
-  if (lane == 0) {
-    *ep = episode;
-    reinterpret_cast<int32_t*>(w.rec)[k.o_sc] = 0;  // base_env.py:350
-    reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0xFFu;  // re-spawned bodies may sit next to a wall
-  }
-  __syncwarp();
-}
-
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(const __grid_constant__ KParams k) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long mbar;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // Stage the map once per CTA: one elected thread issues a TMA bulk copy (cp.async.bulk ->
-  // UBLKCP) that completes on an mbarrier; everyone else waits on the barrier's phase.
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // Prefetch this warp's first record while the map copy is in flight (with one world per warp, the usual case
-  // at a few thousand worlds, both latencies would otherwise add up on the critical path).
-  const long long first_world = k.world_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const bool prefetched = k.rec_words <= 64 && k.mode != MODE_INIT && first_world < k.world_end;
-  float pf0 = 0.f, pf1 = 0.f;
-  if (prefetched) {
-    const float* g = k.state + (size_t)first_world * k.rec_words;
-    if (lane < k.rec_words) pf0 = g[lane];
-    if (lane + 32 < k.rec_words) pf1 = g[lane + 32];
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(k.blob_bytes)
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
-        "l"(k.blob), "r"(k.blob_bytes), "r"(smem_u32(&mbar))
-        : "memory");
-  }
-  {
-    uint32_t done = 0;
-#pragma unroll 1
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(smem_u32(&mbar)), "r"(0)
-          : "memory");
-    }
-  }
-  const MapView m = make_view(smem);
-
-  unsigned char* scratch = smem + ((k.blob_bytes + 127) & ~127) + (size_t)warp * k.scratch_bytes;
-  Warp w;
-  w.rec = reinterpret_cast<float*>(scratch);
-  w.rdist = reinterpret_cast<uint16_t*>(scratch + k.s_rdist);
-  w.rtype = reinterpret_cast<uint8_t*>(scratch + k.s_rtype);
-  w.minbits = reinterpret_cast<uint32_t*>(scratch + k.s_min);
-  w.near = reinterpret_cast<uint16_t*>(scratch + k.s_near);
-  w.nearcnt = reinterpret_cast<uint32_t*>(scratch + k.s_nearcnt);
-  w.con = reinterpret_cast<float*>(scratch + k.s_con);
-  w.ccount = reinterpret_cast<uint32_t*>(scratch + k.s_ccount);
-  w.order = reinterpret_cast<uint8_t*>(scratch + k.s_order);
-  w.best = reinterpret_cast<unsigned long long*>(scratch + k.s_best);
-  w.cand = reinterpret_cast<uint16_t*>(scratch + k.s_cand);
-  w.blob = smem;
-  w.lane = lane;
-
-  // the staging tails beyond A*R rays are shipped by the 16-byte store path: keep them zero
-  for (int i = k.nrays + lane; i < k.nrays_pad; i += 32) { w.rdist[i] = 0; w.rtype[i] = 0; }
-  const int A = k.A;
-  const int wpc = blockDim.x >> 5;   // warps per CTA: chosen per environment by the host (pick_launch_shape)
-  const long long stride = (long long)gridDim.x * wpc;
-#pragma unroll 1
-  for (long long wbase = k.world_begin + (long long)blockIdx.x * wpc; wbase < k.world_end; wbase += stride) {
-#ifndef CAT_NO_WORLD_SYNC
-    // Re-align the CTA's warps once per world.  Nothing is shared between them — the point is the instruction
-    // cache: the kernel is ~70 KB of SASS, and warps that drift apart each pull a different part of it (ncu: 2.4
-    // warps per issue slot stalled on `no_instruction`).  Starting every world together keeps them in the same
-    // code for most of it: -3 ... 4.5 % step time on every map; finer barriers (per agent sweep) lose more to
-    // waiting than they gain (profiles/r1_notes.md).  Every warp of the CTA walks the same wbase sequence.
-    __syncthreads();
-#endif
-    const long long world = wbase + warp;
-    if (world >= k.world_end) continue;
-    float* grec = k.state + (size_t)world * k.rec_words;
-    int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
-
-    if (k.mode == MODE_INIT) {  // fresh environment (entity.py:115,124): agents at map positions
-#pragma unroll 1
-      for (int i = lane; i < k.rec_words; i += 32) {
-        float v = 0.f;
-        if (i < 2 * A) v = (i & 1) ? m.init_pos[i >> 1].y : m.init_pos[i >> 1].x;
-        else if (i >= k.o_tc && i < k.o_tc + 2 * A) { const int q = i - k.o_tc; v = (q & 1) ? m.init_pos[q >> 1].y : m.init_pos[q >> 1].x; }
-        else if ((i >= k.o_wkey && i < k.o_wkey + A * kSlots) || (i >= k.o_page && i < k.o_page + k.P)) v = __uint_as_float(kEmpty);
-        else if (i == k.o_flags) v = __uint_as_float(0xFFu);
-        grec[i] = v;
-      }
-      continue;
-    }
-    if (k.mode == MODE_RESET && k.reset_mask && !k.reset_mask[world]) continue;
-
-    if (prefetched && world == first_world) {
-      if (lane < k.rec_words) w.rec[lane] = pf0;
-      if (lane + 32 < k.rec_words) w.rec[lane + 32] = pf1;
-    } else {
-#pragma unroll 1
-      for (int i = lane; i < k.rec_words; i += 32) w.rec[i] = grec[i];
-    }
-    __syncwarp();
-
-    bool do_step = k.mode == MODE_STEP, do_reset = k.mode == MODE_RESET;
-    bool captured = false, timeout = false;
-    if (do_step) {  // ---------------- base_env.py:354-383 ----------------
-      const float* pos = w.rec;
-      float* vel = w.rec + k.o_vel;
-      const int step_count = reci[k.o_sc] + 1;  // :372
-      __syncwarp();
-      if (lane == 0) reci[k.o_sc] = step_count;
-      // _termination_criterion (:521-554): thief-major; LOS blocked by walls only; dist < radius (strict)
-#pragma unroll 1
-      for (int t = k.nc; t < A && !captured; ++t)
-#pragma unroll 1
-        for (int c = 0; c < k.nc && !captured; ++c) {
-          const float tx = pos[2 * t], ty = pos[2 * t + 1], cx = pos[2 * c], cy = pos[2 * c + 1];
-          const float dx = tx - cx, dy = ty - cy;
-          if (dx * dx + dy * dy < k.term_r * k.term_r) {
-            const bool blocked = los_blocked(smem, lane, tx, ty, cx, cy, k.wall_r);
-            if (!__any_sync(0xFFFFFFFFu, blocked)) captured = true;
-          }
-        }
-      timeout = !captured && step_count >= k.max_steps;
-      // Entity._perform_action (entity.py:126-134)
-      if (lane < A) {
-        int act;
-        const size_t ai = (size_t)world * A + lane;
-        if (k.actions_kind == 0) act = reinterpret_cast<const uint8_t*>(k.actions[0])[ai];
-        else if (k.actions_kind == 1) act = reinterpret_cast<const int32_t*>(k.actions[0])[ai];
-        else if (k.actions_kind == 2) act = (int)reinterpret_cast<const long long*>(k.actions[0])[ai];
-        else act = (int)reinterpret_cast<const long long*>(k.actions[lane])[world];
-        float fx = 0.f, fy = 0.f;
-        if (act == 0) fx = -k.impulse; else if (act == 1) fy = k.impulse;
-        else if (act == 2) fx = k.impulse; else if (act == 3) fy = -k.impulse;
-        float vx = vel[2 * lane] + fx * k.inv_mass, vy = vel[2 * lane + 1] + fy * k.inv_mass;
-        const float sp = sqrtf(vx * vx + vy * vy);
-        if (sp > k.max_speed) { vx = vx / sp * k.max_speed; vy = vy / sp * k.max_speed; }
-        vel[2 * lane] = vx; vel[2 * lane + 1] = vy;
-      }
-      __syncwarp();
-    }
-
-    // One call site each for the sensor sweep, the output writer, the physics and the re-spawn:
-    //   STEP    : observe -> rewards/flags -> (write) -> physics -> [done: reset -> observe -> write]
-    //   RESET   : reset -> observe -> write
-    //   OBSERVE : observe -> write
-#pragma unroll 1
-    for (;;) {
-      if (do_reset) { reset_world(k, m, w, world); do_reset = false; }
-      // entity.py:143 — observation of the pre-physics state.  A world that ends on this step and
-      // is re-spawned in it emits the NEW episode's observation (C-10) and a terminal reward that does not depend
-      // on what is seen, so its terminal sensor sweep would be thrown away: skip it.  With one world per warp the
-      // launch lasts as long as its slowest warp, and a second sweep made every finishing world that warp.
-      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world(k, m, w, world);
-      bool again = false;
-      if (do_step) {
-        if (lane < A && k.reward)
-          k.reward[(size_t)world * A + lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
-        const bool done = captured || timeout;
-        if (lane == 0) {
-          if (k.terminated) k.terminated[world] = done ? 1 : 0;  // entity.py:146
-          if (k.truncated) k.truncated[world] = timeout ? 1 : 0;   // base_env.py:397
-          if (k.winner) k.winner[world] = done ? (captured ? 0 : 1) : -1;
-        }
-        again = done && k.auto_reset;  // emit the observation of the re-spawned state instead
-      }
-      if (!again) write_observation(k, w, world);
-      __syncwarp();
-      if (do_step) {
-        physics_world(k, m, w);  // base_env.py:392
-        do_step = false;
-        if (again) { do_reset = true; continue; }
-      }
-      break;
-    }
-    if (k.mode != MODE_OBSERVE) {
-#pragma unroll 1
-      for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
-    }
-    __syncwarp();
-  }
-}
-
-// ------------------------------------------------------------------ state pack / unpack
-struct ViewParams {
-  float* state;
-  int rec_words, n_worlds, A, P;
-  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags;
-  CatStateView v;
-  int set;
-};
-
-__global__ void cat_state_view_kernel(const ViewParams p) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= p.n_worlds) return;
-  float* rec = p.state + (size_t)w * p.rec_words;
-  uint32_t* recu = reinterpret_cast<uint32_t*>(rec);
-  const int A = p.A, P = p.P;
-  auto xfer = [&](float* ext, int off, int n) {
-    if (!ext) return;
-    for (int i = 0; i < n; ++i) { if (p.set) rec[off + i] = ext[(size_t)w * n + i]; else ext[(size_t)w * n + i] = rec[off + i]; }
-  };
-  xfer(p.v.pos, 0, 2 * A);
-  if (p.set && p.v.pos) recu[p.o_flags] = 0xFFu;  // positions changed: re-evaluate the alpha = 0 candidates
-  xfer(p.v.vel, p.o_vel, 2 * A);
-  xfer(p.v.vbias, p.o_vb, 2 * A);
-  xfer(p.v.tc, p.o_tc, 2 * A);
-  xfer(p.v.wall_jn, p.o_wjn, A * kSlots);
-  xfer(p.v.pair_jn, p.o_pjn, P);
-  if (p.v.step_count) { if (p.set) recu[p.o_sc] = (uint32_t)p.v.step_count[w]; else p.v.step_count[w] = (int32_t)recu[p.o_sc]; }
-  if (p.v.episode) { if (p.set) recu[p.o_ep] = p.v.episode[w]; else p.v.episode[w] = recu[p.o_ep]; }
-  if (p.v.wall_hull && p.v.wall_age) {
-    for (int i = 0; i < A * kSlots; ++i) {
-      const size_t e = (size_t)w * A * kSlots + i;
-      if (p.set) {
-        recu[p.o_wkey + i] = p.v.wall_hull[e] < 0 ? kEmpty : ((uint32_t)p.v.wall_hull[e] & 0xFFFF) | ((uint32_t)p.v.wall_age[e] << 16);
-      } else {
-        const uint32_t key = recu[p.o_wkey + i];
-        p.v.wall_hull[e] = key == kEmpty ? -1 : (int32_t)(key & 0xFFFF);
-        p.v.wall_age[e] = key == kEmpty ? -1 : (int32_t)(key >> 16);
-      }
-    }
-  }
-  if (p.v.pair_age) {
-    for (int i = 0; i < P; ++i) {
-      const size_t e = (size_t)w * P + i;
-      if (p.set) recu[p.o_page + i] = p.v.pair_age[e] < 0 ? kEmpty : (uint32_t)p.v.pair_age[e];
-      else p.v.pair_age[e] = recu[p.o_page + i] == kEmpty ? -1 : (int32_t)recu[p.o_page + i];
-    }
-  }
-}
-
-// ------------------------------------------------------------------ GAE
-// adv_t = delta_t + c_t * adv_{t+1} with delta_t = r_t - V_t + gamma * nd_t * V_{t+1}, c_t = gamma * lambda * nd_t is a
-// first-order linear recurrence, i.e. a scan of affine maps, so it parallelises over T as well as over
-// the (world, agent) columns.  One CTA owns 32 columns (lanes: 128-B coalesced rows) and walks T backwards
-// in chunks of kGaeSegs segments x kGaeS steps: warp s loads segment s of the chunk (all 8 x {r, V, done}
-// loads issued up front), folds it into one affine map (A, B); the kGaeSegs maps of a column are combined
-// by a shuffle scan (through shared memory, kGaeSegs lanes per column), and every thread then replays its
-// steps from registers and writes advantages / returns.  Every input byte is read once and every output
-// byte written once: 9 B read + 8 B written per sample.  CTAs are small (128 threads, 6 per SM) and the next
-// chunk's loads are issued before the scan (software pipeline), so loads stay in flight during the scan and
-// store phases.  sum / sum^2 of the advantages are reduced per
-// CTA and added in fp64 for the normalisation pass.
-#ifndef CAT_GAE_SEGS
-#define CAT_GAE_SEGS 4   // measured on B200 (gpurun_out/prof_gae4.log): 4 segments x 32 columns, 6 CTAs per SM is the fastest shape
-#endif
-#ifndef CAT_GAE_MIN_CTAS
-#define CAT_GAE_MIN_CTAS 6
-#endif
-constexpr int kGaeCols = 32, kGaeSegs = CAT_GAE_SEGS, kGaeS = 8;
-constexpr int kGaeColsPerWarp = kGaeCols / kGaeSegs;  // scan phase: each warp scans 4 columns, 8 lanes per column
-
-struct GaeChunk {          // one thread's 8 steps of one chunk, as loaded
-  float r[kGaeS], v[kGaeS], vnext;
-  uint32_t done;           // bit i: done flag of step i
-};
-
-// kFull: every step of the chunk exists (t >= 0) and every column of the CTA is < M, so nothing is clamped or
-// predicated.  Index: element offsets are formed in 32 bits when T*M < 2^31 (one IMAD.WIDE per access instead of
-// 64-bit multiply-adds — address arithmetic was a third of the kernel's instructions and the kernel is close to
-// issue-bound once the loads are batched).
-template <bool kFull, typename Index>
-__device__ __forceinline__ void gae_load(GaeChunk& ck, const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
-                                         const float* __restrict__ values, int base, int seg, int M, int col, bool valid,
-                                         float carry_v) {
-  // Branch-free: every address is clamped into the array so that all 24 loads issue back to back (a predicated
-  // load per step would make the compiler wait for each step's `done` byte before issuing the next step's loads);
-  // steps before t = 0 / columns beyond M are masked afterwards.
-  const int ccol = kFull ? col : (valid ? col : 0);
-  uint32_t raw[kGaeS];
-#pragma unroll
-  for (int i = 0; i < kGaeS; ++i) {
-    const Index idx = (Index)(kFull ? base + i : max(base + i, 0)) * (Index)M + (Index)ccol;
-    ck.r[i] = __ldcs(rewards + idx); ck.v[i] = __ldcs(values + idx); raw[i] = __ldcs(dones + idx);
-  }
-  ck.done = 0;
-#pragma unroll
-  for (int i = 0; i < kGaeS; ++i) ck.done |= (raw[i] ? 1u : 0u) << i;
-  ck.vnext = carry_v;  // V_{t+1} of this thread's last step: the first V of the later segment (seg 0: patched by the caller)
-  if (seg > 0) ck.vnext = __ldg(values + (Index)(kFull ? base + kGaeS : max(base + kGaeS, 0)) * (Index)M + (Index)ccol);
-}
-
-template <bool kFull>
-__device__ __forceinline__ void gae_fold(GaeChunk& ck, int base, float gamma, float gl, float& A, float& B) {
-  A = 1.f; B = 0.f;
-#pragma unroll
-  for (int i = kGaeS - 1; i >= 0; --i) {
-    if (kFull || base + i >= 0) {
-      const float nd = (ck.done >> i) & 1u ? 0.f : 1.f;
-      const float vn = (i == kGaeS - 1) ? ck.vnext : ck.v[i + 1];
-      ck.r[i] = ck.r[i] - ck.v[i] + gamma * nd * vn;  // delta_t
-      B = fmaf(gl * nd, B, ck.r[i]);
-      A *= gl * nd;
-    }
-  }
-}
-
-template <bool kFull, typename Index>
-__device__ __forceinline__ void gae_store(const GaeChunk& ck, float adv, int base, int M, int col, bool valid, float gl,
-                                          float* __restrict__ returns, float* __restrict__ advantages, float& p1, float& p2) {
-#pragma unroll
-  for (int i = kGaeS - 1; i >= 0; --i) {
-    const int t = base + i;
-    if (kFull || (valid && t >= 0)) {
-      const float nd = (ck.done >> i) & 1u ? 0.f : 1.f;
-      adv = fmaf(gl * nd, adv, ck.r[i]);
-      const Index idx = (Index)t * (Index)M + (Index)col;
-      advantages[idx] = adv;
-      __stcs(returns + idx, adv + ck.v[i]);
-      p1 += adv; p2 = fmaf(adv, adv, p2);
-    }
-  }
-}
-
-template <typename Index>
-__global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
-    cat_gae_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, const float* __restrict__ values,
-                   const float* __restrict__ last_values, float* __restrict__ returns, float* __restrict__ advantages,
-                   double* __restrict__ stats, int T, int M, float gamma, float lam) {
-  __shared__ float sA[kGaeSegs][kGaeCols + 1], sB[kGaeSegs][kGaeCols + 1];
-  __shared__ float sCarryAdv[kGaeCols], sCarryV[kGaeCols];
-  __shared__ double sh1[kGaeSegs], sh2[kGaeSegs];
-  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-  const int col = blockIdx.x * kGaeCols + lane;
-  const bool valid = col < M;
-  const bool cols_full = blockIdx.x * kGaeCols + kGaeCols <= M;   // CTA-uniform
-  const float gl = gamma * lam;
-  constexpr int kChunk = kGaeSegs * kGaeS;
-  float carry_adv = 0.f, carry_v = valid ? last_values[col] : 0.f;
-  double s1 = 0.0, s2 = 0.0;
-  GaeChunk cur;
-  if (cols_full && T >= kChunk) gae_load<true, Index>(cur, rewards, dones, values, T - (seg + 1) * kGaeS, seg, M, col, valid, carry_v);
-  else gae_load<false, Index>(cur, rewards, dones, values, T - (seg + 1) * kGaeS, seg, M, col, valid, carry_v);
-#pragma unroll 1
-  for (int t_hi = T; t_hi > 0; t_hi -= kChunk) {
-    const int base = t_hi - (seg + 1) * kGaeS;  // this thread's steps: base .. base + 7 (those >= 0)
-    const bool full = cols_full && t_hi >= kChunk;
-    if (seg == 0) cur.vnext = carry_v;            // known only now: V at the first step of the later chunk
-    // software pipeline: the next (earlier) chunk's loads are in flight during this chunk's scan and stores
-    GaeChunk nxt;
-    if (t_hi > kChunk) {
-      if (cols_full && t_hi >= 2 * kChunk) gae_load<true, Index>(nxt, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
-      else gae_load<false, Index>(nxt, rewards, dones, values, base - kChunk, seg, M, col, valid, 0.f);
-    }
-    float A, B;
-    if (full) gae_fold<true>(cur, base, gamma, gl, A, B); else gae_fold<false>(cur, base, gamma, gl, A, B);
-    sA[seg][lane] = A; sB[seg][lane] = B;
-    if (seg == kGaeSegs - 1) sCarryV[lane] = cur.v[0];  // V at the chunk's first step = V_{t+1} of the next chunk
-    if (seg == 0) sCarryAdv[lane] = carry_adv;
-    __syncthreads();
-    {  // lane group g of warp `seg` scans column seg * 4 + g: sub-lane l holds the map of segment l
-       // (x_{l+1} = B_l + A_l * x_l, x_0 = the advantage carried in from the later chunk)
-      const int sl = lane & (kGaeSegs - 1), scol = seg * kGaeColsPerWarp + lane / kGaeSegs;
-      float a = sA[sl][scol], b = sB[sl][scol];
-#pragma unroll
-      for (int d = 1; d < kGaeSegs; d <<= 1) {
-        const float ap = __shfl_up_sync(0xFFFFFFFFu, a, d, kGaeSegs), bp = __shfl_up_sync(0xFFFFFFFFu, b, d, kGaeSegs);
-        if (sl >= d) { b = fmaf(a, bp, b); a *= ap; }
-      }
-      const float x0 = sCarryAdv[scol];
-      const float xout = fmaf(a, x0, b);                                // advantage at the first step of segment l
-      float xin = __shfl_up_sync(0xFFFFFFFFu, xout, 1, kGaeSegs);       // = advantage entering segment l
-      if (sl == 0) xin = x0;
-      __syncwarp();
-      sA[sl][scol] = xin;
-      if (sl == kGaeSegs - 1) sB[0][scol] = xout;                       // advantage entering the next (earlier) chunk
-    }
-    __syncthreads();
-    const float adv = sA[seg][lane];
-    carry_adv = sB[0][lane];
-    carry_v = sCarryV[lane];
-    float p1 = 0.f, p2 = 0.f;
-    if (full) gae_store<true, Index>(cur, adv, base, M, col, valid, gl, returns, advantages, p1, p2);
-    else gae_store<false, Index>(cur, adv, base, M, col, valid, gl, returns, advantages, p1, p2);
-    s1 += (double)p1; s2 += (double)p2;
-    cur = nxt;
-    __syncthreads();
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
-    s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
-  }
-  if (lane == 0) { sh1[seg] = s1; sh2[seg] = s2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0, b = 0;
-    for (int i = 0; i < kGaeSegs; ++i) { a += sh1[i]; b += sh2[i]; }
-    atomicAdd(&stats[0], a);
-    atomicAdd(&stats[1], b);
-  }
-}
-
-// In-place (adv - mean) / (std + 1e-8): 4 B read + 4 B written per sample, four independent 16-B loads in
-// flight per thread.
-__global__ void __launch_bounds__(256) cat_adv_normalize_kernel(float* __restrict__ adv, long long n,
-                                                                const double* __restrict__ stats, long long count) {
-  const double mean = stats[0] / (double)count;
-  double var = count > 1 ? (stats[1] - (double)count * mean * mean) / (double)(count - 1) : 0.0;
-  if (var < 0.0) var = 0.0;
-  const float fm = (float)mean, inv = (float)(1.0 / (sqrt(var) + 1e-8));
-  const long long n4 = n >> 2;
-  float4* a4 = reinterpret_cast<float4*>(adv);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n4; i += 4 * stride) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = a4[i + u * stride];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      v[u].x = (v[u].x - fm) * inv; v[u].y = (v[u].y - fm) * inv; v[u].z = (v[u].z - fm) * inv; v[u].w = (v[u].w - fm) * inv;
-      a4[i + u * stride] = v[u];
-    }
-  }
-  for (; i < n4; i += stride) {
-    float4 v = a4[i];
-    v.x = (v.x - fm) * inv; v.y = (v.y - fm) * inv; v.z = (v.z - fm) * inv; v.w = (v.w - fm) * inv;
-    a4[i] = v;
-  }
-  for (long long j = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-    adv[j] = (adv[j] - fm) * inv;
-}
+#include "world_kernel.cuh"
+#include "state_view.cuh"
+#include "gae_kernels.cuh"
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 

@@ -6,14 +6,14 @@ lib = Path(sys.argv[1]).resolve()
 ROOT = Path(__file__).resolve().parents[1]
 tmp = Path(tempfile.mkdtemp())
 subprocess.run(f"cd {tmp} && cuobjdump -xelf all {lib} >/dev/null && nvdisasm -g -c *.cubin > dis.txt", shell=True, check=True)
-src = (ROOT / "as_cops_and_thieves_b200/csrc/cat_b200.cu").read_text().split("\n")
+src = (ROOT / "as_cops_and_thieves_b200/csrc/world_kernel.cuh").read_text().split("\n")
 funcs = []
 for i, l in enumerate(src):
     m = re.match(r"^(?:__device__|__global__|static).*?\b(\w+)\s*\(", l)
     if m and not l.strip().startswith("//"):
         funcs.append((i + 1, m.group(1)))
 def owner(f, l):
-    if not f.startswith("cat_b200"):
+    if not f.startswith("world_kernel"):
         return "lib:" + f
     name = "?"
     for s, n in funcs:

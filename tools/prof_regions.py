@@ -45,7 +45,7 @@ for _i in range(2, len(rows)):          # several launches in one report: keep t
         break
 hdr = rows[1]
 ia, ii, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
-src = (ROOT / "as_cops_and_thieves_b200/csrc/cat_b200.cu").read_text().split("\n")
+src = (ROOT / "as_cops_and_thieves_b200/csrc/world_kernel.cuh").read_text().split("\n")
 
 
 def find(pat, start=0):
@@ -82,7 +82,7 @@ marks = sorted([(n, l) for n, l in marks if l], key=lambda x: x[1])
 
 
 def region(f, l):
-    if not f.startswith("cat_b200"):
+    if not f.startswith("world_kernel"):
         return "lib:" + f
     r = "pre"
     for n, s in marks:
@@ -116,5 +116,5 @@ print(f"hot static footprint (instructions executed in >= 10 % of world-steps): 
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print(f"{k:26s} warp-inst {v[0] / nworlds:8.0f}/world ({v[0] / tot[0] * 100:5.1f}%)  thread-inst/world {v[1] / nworlds:9.0f}  eff {v[1] / max(v[0], 1):5.1f}  samples {v[2] / max(tot[2], 1) * 100:5.1f}%  hot-instr {hot[k]:4d}")
 for (f, l), v in sorted(lagg.items(), key=lambda kv: -kv[1][0])[:nlines]:
-    txt = src[l - 1].strip()[:100] if f.startswith("cat_b200") and l > 0 else ""
+    txt = src[l - 1].strip()[:100] if f.startswith("world_kernel") and l > 0 else ""
     print(f"{f}:{l:5d} inst {v[0] / tot[0] * 100:5.1f}% eff {v[1] / max(v[0], 1):5.1f} samp {v[2] / max(tot[2], 1) * 100:5.1f}% | {txt}")
