@@ -166,10 +166,17 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
 // flight per thread.
 __global__ void __launch_bounds__(256) cat_adv_normalize_kernel(float* __restrict__ adv, long long n,
                                                                 const double* __restrict__ stats, long long count) {
-  const double mean = stats[0] / (double)count;
-  double var = count > 1 ? (stats[1] - (double)count * mean * mean) / (double)(count - 1) : 0.0;
-  if (var < 0.0) var = 0.0;
-  const float fm = (float)mean, inv = (float)(1.0 / (sqrt(var) + 1e-8));
+  // mean / 1/(std + eps) once per CTA (fp64 divide + sqrt), broadcast through shared memory
+  __shared__ float s_fm, s_inv;
+  if (threadIdx.x == 0) {
+    const double mean = stats[0] / (double)count;
+    double var = count > 1 ? (stats[1] - (double)count * mean * mean) / (double)(count - 1) : 0.0;
+    if (var < 0.0) var = 0.0;
+    s_fm = (float)mean;
+    s_inv = (float)(1.0 / (sqrt(var) + 1e-8));
+  }
+  __syncthreads();
+  const float fm = s_fm, inv = s_inv;
   const long long n4 = n >> 2;
   float4* a4 = reinterpret_cast<float4*>(adv);
   const long long stride = (long long)gridDim.x * blockDim.x;
