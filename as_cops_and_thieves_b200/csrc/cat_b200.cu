@@ -77,7 +77,7 @@ struct LaunchShape { int threads, smem, grid; };
 
 static bool pick_launch_shape(const CatEnv* env, int n_worlds, LaunchShape* out) {
   long long best_score = -1;
-  for (int wpc = kWarpsPerCta; wpc >= 2; wpc >>= 1) {
+  for (int wpc = kWarpsPerCta; wpc >= 2; --wpc) {   // any warp count: 4096 worlds = 586 CTAs of 7 warps = 28 warps per SM
     const int smem = align_up(env->blob_bytes, 128) + wpc * env->kp.scratch_bytes;
     if (smem > env->max_optin) continue;
     int occ = 0;
