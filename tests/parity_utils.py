@@ -208,3 +208,39 @@ def check_vector(vec, res, pos_tol=1e-6, point_tol=1e-6) -> None:
     for key in ("pos", "vel", "vbias"):
         if key in exp:
             np.testing.assert_allclose(np.asarray(res[key])[agents], exp[key], atol=pos_tol, err_msg=f"{name}:{key}")
+
+
+def random_map_json(seed: int, n_blocks: int = 18, size=(900.0, 700.0), n_cops: int = 2, n_thieves: int = 1) -> dict:
+    """A random map in the reference's ``maps_templates`` schema: an outer frame of four thin rectangles plus
+    rectangles (some with negative extents) and arbitrary — possibly concave, possibly overlapping — polygons, as
+    ``agh-map.json`` has them.  Agents spawn in the free margin left along the frame."""
+    rng = np.random.default_rng(seed)
+    W, H = size
+    blocks = [{"type": "rect", "x": 20, "y": 20, "w": W - 40, "h": 6}, {"type": "rect", "x": 20, "y": H - 26, "w": W - 40, "h": 6},
+              {"type": "rect", "x": 20, "y": 20, "w": 6, "h": H - 40}, {"type": "rect", "x": W - 26, "y": 20, "w": 6, "h": H - 40}]
+    for _ in range(n_blocks):
+        cx, cy = rng.uniform(140, W - 140), rng.uniform(140, H - 140)
+        if rng.random() < 0.4:
+            w, h = rng.uniform(8, 90) * rng.choice([-1, 1]), rng.uniform(8, 90) * rng.choice([-1, 1])
+            blocks.append({"type": "rect", "x": float(cx), "y": float(cy), "w": float(w), "h": float(h)})
+        else:
+            k = int(rng.integers(3, 9))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+            rad = rng.uniform(10, 70, k)                     # star-shaped ring: concave in general
+            vs = [{"x": float(cx + r * np.cos(a)), "y": float(cy + r * np.sin(a))} for a, r in zip(ang, rad)]
+            blocks.append({"type": "poly", "vs": vs})
+    agents = []
+    for i in range(n_cops + n_thieves):
+        y0 = 40 + i * (H - 80) / (n_cops + n_thieves)
+        agents.append({"type": "cop" if i < n_cops else "thief", "x": 60.0, "y": float(y0 + 20),
+                       "spawn_region": {"x": 36.0, "y": float(y0), "w": 60.0, "h": float((H - 80) / (n_cops + n_thieves) - 10)}})
+    return {"window": {"w_px": int(W), "h_px": int(H)}, "canvas": {"w": int(W), "h": int(H)},
+            "objects": {"blocks": blocks}, "agents": agents}
+
+
+def random_cmap(seed: int, tmp_path, **kw):
+    import json
+    from as_cops_and_thieves_b200.maps import Map
+    path = Path(tmp_path) / f"random_{seed}.json"
+    path.write_text(json.dumps(random_map_json(seed, **kw)))
+    return compile_map(Map(str(path)), name=f"random_{seed}")

@@ -178,3 +178,47 @@ def test_view_lists_are_conservative_and_nearest_first(name):
     if name == "agh-map":       # the point of the lists: far fewer than all 496 edges
         sizes = np.diff(cm.view_cell_off)
         assert sizes.mean() < 0.4 * E
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_maps_compile_to_valid_hulls_and_conservative_lists(seed, tmp_path):
+    """Arbitrary user maps, not just the five shipped ones: concave / overlapping polygons and negative-extent
+    rectangles must become strictly convex CCW hulls with outward unit normals, and both per-cell list kinds
+    (contact hulls, sensor candidate edges) must be conservative."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import parity_utils as pu
+    from oracle.cat_oracle import Oracle
+    cm = pu.random_cmap(seed, tmp_path)
+    assert cm.n_hulls >= 10 and cm.n_edges == cm.hull_off[-1]
+    for h in range(cm.n_hulls):
+        o, e = cm.hull_off[h], cm.hull_off[h + 1]
+        v = cm.vert[o:e]
+        n = len(v)
+        assert n >= 3
+        for i in range(n):
+            a, b, c = v[i - 1], v[i], v[(i + 1) % n]
+            assert (b[0] - a[0]) * (c[1] - b[1]) - (b[1] - a[1]) * (c[0] - b[0]) > 0
+            assert abs(np.hypot(*cm.normal[o + i]) - 1) < 1e-12 and (v.mean(axis=0) - v[i]) @ cm.normal[o + i] < 0
+    orc = Oracle(cm)
+    E = cm.n_edges
+    prev, nxt = np.zeros(E, int), np.zeros(E, int)
+    for h in range(cm.n_hulls):
+        o, e = int(cm.hull_off[h]), int(cm.hull_off[h + 1])
+        prev[o:e] = np.roll(np.arange(o, e), 1)
+        nxt[o:e] = np.roll(np.arange(o, e), -1)
+    A, B, nrm, nn = cm.vert[prev], cm.vert, cm.normal, cm.normal[nxt]
+    AB = B - A
+    rng = np.random.default_rng(seed)
+    lo = np.array([cm.grid_x0, cm.grid_y0])
+    for p in rng.uniform(lo, lo + np.array([cm.nx, cm.ny]) * cm.cell, size=(400, 2)):
+        c = int((p[1] - cm.grid_y0) // cm.cell) * cm.nx + int((p[0] - cm.grid_x0) // cm.cell)
+        con = set(cm.con_cell_hulls[cm.con_cell_off[c]:cm.con_cell_off[c + 1]].tolist())
+        for h in range(cm.n_hulls):
+            if orc.hull_distance(h, p) <= 6.0:
+                assert h in con
+        view = set(cm.view_cell_edges[cm.view_cell_off[c]:cm.view_cell_off[c + 1]].tolist())
+        t = np.clip(((p - A) * AB).sum(1) / (AB ** 2).sum(1), 0, 1)
+        d = np.hypot(*(p - (A + AB * t[:, None])).T)
+        cand = np.nonzero(((((p - B) * nrm).sum(1) > 0) | (((p - B) * nn).sum(1) > 0)) & (d < 402.0))[0]
+        assert set(cand.tolist()) <= view

@@ -220,6 +220,24 @@ def test_view_lists_do_not_change_results(cuda_device, name, free):
         w.close()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_map_parity(cuda_device, tmp_path, seed):
+    """Single-step transition parity on randomly generated maps (concave / overlapping polygons convexified,
+    negative-extent rectangles, 30 hulls, ~130 edges: the per-cell candidate lists are in play)."""
+    cmap = pu.random_cmap(seed, tmp_path, n_blocks=26)
+    assert cmap.n_edges >= 96            # enough edges that the library uses the per-cell candidate lists
+    N = 512
+    cw = CatWorlds(cmap, N, device=cuda_device, want_hits=True, seed=20 + seed)
+    orc = Oracle(cmap, seed=20 + seed)
+    rng = np.random.default_rng(seed)
+    cw.reset()
+    for gap in (0, 60, 150):
+        for _ in range(gap):
+            cw.step(_acts(rng, N, cw.A, cw.device)[1])
+        print(seed, gap, _compare_transition(cw, orc, rng, f"random{seed}@+{gap}"))
+    cw.close()
+
+
 def test_analytic_golden_vectors_through_cuda(cuda_device):
     m, vectors = pu.load_analytic()
     cmap = compile_map(m, name="analytic")
