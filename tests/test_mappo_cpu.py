@@ -123,3 +123,46 @@ def test_pfsp_weight_and_sampling(tmp_path):
     assert frac["cop_iter_0.pt"] < 0.01                      # weights 0.001 : 1 : 1 (unseen policy defaults to 0.5)
     assert abs(frac["cop_iter_2.pt"] - 0.5) < 0.05 and abs(frac["cop_iter_10.pt"] - 0.5) < 0.05
     assert {Path(selfplay.sample_policy_from_archive(arch, "cop", "random", rng)).name for _ in range(200)} == set(frac)
+
+
+class _FakeEnv:
+    """Just enough of BatchedCopsThievesEnv to construct a learner on the CPU (no rollouts, no GAE kernels)."""
+    possible_agents = ["cop_0", "cop_1", "thief_0"]
+    num_envs, state_dim, device = 4, 1090, torch.device("cpu")
+
+    class worlds:
+        R = 90
+
+
+def test_flat_gradient_bucket_and_freezing():
+    learner = mappo.MAPPOLearner(_FakeEnv(), mappo.MAPPOConfig(rollouts=16, model="mlp"), seed=0)
+    a = "cop_0"
+    flat = learner._flat_grad[a]
+    params = learner.parameters(a)
+    assert flat.numel() == sum(p.numel() for p in params)
+    off = 0
+    for p in params:                                   # every .grad is a view into the agent's flat bucket, in order
+        assert p.grad.data_ptr() == flat.data_ptr() + 4 * off and p.grad.shape == p.shape
+        off += p.numel()
+    logits, _ = learner.models[a]["policy"](torch.rand(4, 2, 180))
+    value, _ = learner.models[a]["value"](torch.rand(4, 2, 1090))
+    (logits.sum() + value.sum()).backward()
+    assert float(flat.abs().sum()) > 0                 # autograd accumulated straight into the bucket
+    for p in params:
+        assert p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + 4 * flat.numel()
+    learner.optimizers[a].zero_grad(set_to_none=False)
+    assert float(flat.abs().sum()) == 0
+    # frozen networks get no gradient at all (Adam then skips them), trainable ones keep their slice
+    learner.freeze(a, "policy", True)
+    assert all(p.grad is None and not p.requires_grad for p in learner.models[a]["policy"].parameters())
+    assert all(p.grad is not None for p in learner.models[a]["value"].parameters())
+    learner.freeze(a, "policy", False)
+    off = 0
+    for p in params:
+        assert p.requires_grad and p.grad.data_ptr() == flat.data_ptr() + 4 * off
+        off += p.numel()
+    # identical initial weights for a given seed (every rank builds the same nets before the first all-reduce)
+    other = mappo.MAPPOLearner(_FakeEnv(), mappo.MAPPOConfig(rollouts=16, model="mlp"), seed=0)
+    assert all(torch.equal(p, q) for p, q in zip(params, other.parameters(a)))
+    with pytest.raises(ValueError):
+        mappo.MAPPOLearner(_FakeEnv(), mappo.MAPPOConfig(rollouts=20, sequence_length=16))
