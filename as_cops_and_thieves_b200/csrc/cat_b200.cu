@@ -254,14 +254,14 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   // record layout (4-byte words)
   k.o_vel = 2 * A; k.o_vb = 4 * A; k.o_tc = 6 * A; k.o_wkey = 8 * A; k.o_wjn = 8 * A + A * kSlots;
   k.o_page = 8 * A + 2 * A * kSlots; k.o_pjn = k.o_page + P; k.o_sc = k.o_pjn + P; k.o_ep = k.o_sc + 1; k.o_flags = k.o_ep + 1;
-  k.rec_words = align_up(k.o_flags + 1, 32);
+  k.o_near = k.o_flags + 1;                                   // u16 [A][kNear]: hulls within ray_r of each body (0xFFFF = none)
+  k.rec_words = align_up(k.o_near + (A * kNear + 1) / 2, 32);
   // scratch layout (bytes)
   int so = k.rec_words * 4;
   auto stake = [&](int bytes) { int o = so; so = align_up(so + bytes, 16); return o; };
   k.s_rdist = stake(k.nrays_pad * 2);
   k.s_rtype = stake(k.nrays_pad);
   k.s_min = stake(CAT_MAX_AGENTS * 4);
-  k.s_near = stake(CAT_MAX_AGENTS * kNear * 2);
   k.s_nearcnt = stake(CAT_MAX_AGENTS * 4);
   k.s_con = stake(k.maxc * 32);
   k.s_ccount = stake(CAT_MAX_AGENTS * 4);

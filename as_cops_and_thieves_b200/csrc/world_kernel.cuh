@@ -68,9 +68,9 @@ struct KParams {
   int A, nc, R, P, nrays, nrays_pad, maxc, n_edges;
   int mode;
   // record offsets (words)
-  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags;
+  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags, o_near;
   // per-warp scratch offsets (bytes) and size
-  int s_rdist, s_rtype, s_min, s_near, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, scratch_bytes;
+  int s_rdist, s_rtype, s_min, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, scratch_bytes;
   int state_dim;
   // constants
   float dt, inv_dt, impulse, inv_mass, agent_r, max_speed, term_r, ray_len, ray_r, wall_r;
@@ -438,11 +438,14 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
   const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len;
   const float reach = k.agent_r + k.ray_r, reach2 = reach * reach, inv_reach = 1.f / reach;
   const float range2 = (L + rsum) * (L + rsum);
-  // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates.
-  // Only agents flagged by the last physics step / re-spawn (a wall within contact reach) can have any.
+  // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates.  The list is
+  // part of the state record: the physics step that moved the body already measured its distance to every hull
+  // in contact reach and stored it; it is recomputed here only after a re-spawn / set_state (flag bit set).
   if (lane < A) {
     uint32_t cnt = 0;
     if ((flags >> lane) & 1u) {
+#pragma unroll 1
+      for (int q = 0; q < kNear; ++q) w.near[lane * kNear + q] = 0xFFFFu;
       const float px = pos[2 * lane], py = pos[2 * lane + 1];
       const int cell = grid_cell(m, px, py);
       if (cell >= 0) {
@@ -455,11 +458,15 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
           if (d - k.wall_r <= k.ray_r && cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
         }
       }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < kNear; ++q) cnt += w.near[lane * kNear + q] != 0xFFFFu ? 1u : 0u;
     }
     w.nearcnt[lane] = cnt;
     w.minbits[lane] = kEmpty;
   }
   __syncwarp();
+  if (lane == 0 && flags) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0u;   // lists are now valid for these positions
 
   const int nsub = (R + 31) >> 5;
 #pragma unroll 1
@@ -804,7 +811,9 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
       const int cell = grid_cell(m, pos[2 * lane], pos[2 * lane + 1]);
       if (cell >= 0) { q0 = m.con_off[cell]; len = m.con_off[cell + 1] - q0; }
       w.ccount[lane] = 0;
+      w.nearcnt[lane] = 0;
     }
+    if (lane < A * kNear) w.near[lane] = 0xFFFFu;   // next step's alpha = 0 candidates (hulls within ray_r of the new position)
     int incl = len;   // inclusive scan over the (at most 8) agent lanes
 #pragma unroll
     for (int d = 1; d < CAT_MAX_AGENTS; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
@@ -831,6 +840,12 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
       }
       const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
       const uint32_t same = __match_any_sync(0xFFFFFFFFu, a);
+      const bool isnear = hit && (d - k.wall_r <= k.ray_r);
+      const uint32_t nears = __ballot_sync(0xFFFFFFFFu, isnear);
+      if (isnear) {
+        const uint32_t rank = w.nearcnt[a] + __popc(nears & same & ((1u << lane) - 1u));
+        if (rank < (uint32_t)kNear) w.near[a * kNear + rank] = (uint16_t)h;
+      }
       if (hit) {
         const uint32_t rank = w.ccount[a] + __popc(hits & same & ((1u << lane) - 1u));
         if (rank < (uint32_t)kSlots) {
@@ -841,6 +856,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
       }
       __syncwarp();
       if (hit && (hits & same & ((1u << lane) - 1u)) == 0) w.ccount[a] += __popc(hits & same);   // first hit lane of each agent
+      if (isnear && (nears & same & ((1u << lane) - 1u)) == 0) w.nearcnt[a] += __popc(nears & same);
       __syncwarp();
     }
   }
@@ -898,11 +914,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
     }
     w.ccount[lane] = cnt;
   }
-  {
-    // agents with a wall inside contact reach are the only ones that can start a ray inside a wall's reach next step
-    const uint32_t near_mask = __ballot_sync(0xFFFFFFFFu, lane < A && w.ccount[lane] > 0);
-    if (lane == 0) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = near_mask;
-  }
+  if (lane == 0) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0u;   // the stored near lists are valid for the new positions
   uint32_t pair_hit = 0;
   if (lane < P) {
     // pair index -> (i, j), i-major
@@ -1149,7 +1161,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
   w.rdist = reinterpret_cast<uint16_t*>(scratch + k.s_rdist);
   w.rtype = reinterpret_cast<uint8_t*>(scratch + k.s_rtype);
   w.minbits = reinterpret_cast<uint32_t*>(scratch + k.s_min);
-  w.near = reinterpret_cast<uint16_t*>(scratch + k.s_near);
+  w.near = reinterpret_cast<uint16_t*>(w.rec + k.o_near);   // lives in the state record
   w.nearcnt = reinterpret_cast<uint32_t*>(scratch + k.s_nearcnt);
   w.con = reinterpret_cast<float*>(scratch + k.s_con);
   w.ccount = reinterpret_cast<uint32_t*>(scratch + k.s_ccount);
