@@ -264,7 +264,24 @@ class BatchedCopsThievesEnv(_EnvCommon):
         return self.state_spaces[agent]
 
     def _obs_dict(self) -> Dict[str, torch.Tensor]:
-        return {a: self._w.obs_f32[i] for i, a in enumerate(self.possible_agents)}
+        return self._views()[0]
+
+    def _views(self):
+        """The step's return values are fixed views of the kernel's output buffers, built once: per-agent
+        observation / reward slices, and the u8 flags reinterpreted as bool (the kernel writes 0 / 1), so a step
+        costs one kernel launch and no torch ops.  The same dict objects are returned by every call; their
+        tensors are overwritten by the next step (copy what must outlive it, as skrl's memories do)."""
+        v = getattr(self, "_cached_views", None)
+        if v is None:
+            w = self._w
+            obs = {a: w.obs_f32[i] for i, a in enumerate(self.possible_agents)}
+            rew = {a: w.reward[:, i:i + 1] for i, a in enumerate(self.possible_agents)}
+            term = w.terminated.view(torch.bool).unsqueeze(1)
+            trunc = w.truncated.view(torch.bool).unsqueeze(1)
+            v = (obs, rew, {a: term for a in self.possible_agents}, {a: trunc for a in self.possible_agents},
+                 {a: {"winner": w.winner} for a in self.possible_agents})
+            self._cached_views = v
+        return v
 
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
         if seed is not None:
@@ -281,14 +298,7 @@ class BatchedCopsThievesEnv(_EnvCommon):
                 self._w.step(torch.stack([t.to(self.device) for t in acts], dim=1).to(torch.uint8).contiguous())
         else:
             self._w.step(actions)
-        w = self._w
-        term = (w.terminated != 0).unsqueeze(1)
-        trunc = (w.truncated != 0).unsqueeze(1)
-        rewards = {a: w.reward[:, i:i + 1] for i, a in enumerate(self.possible_agents)}
-        terminated = {a: term for a in self.possible_agents}
-        truncated = {a: trunc for a in self.possible_agents}
-        infos = {a: {"winner": w.winner} for a in self.possible_agents}
-        return self._obs_dict(), rewards, terminated, truncated, infos
+        return self._views()
 
     def state(self) -> torch.Tensor:
         return self._w.state_f32
