@@ -17,6 +17,8 @@
 //
 // No CPU fallback, no Triton, no tensor cores (the step is instruction-issue bound, GAE is HBM bound).
 
+#include <cuda.h>            // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
+#include <cudaTypedefs.h>    // PFN_cuTensorMapEncodeTiled
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -24,6 +26,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -463,6 +466,38 @@ int cat_env_set_state(CatEnv* env, void* state_dev, const CatStateView* view, vo
   return state_view(env, state_dev, view, 1, stream);
 }
 
+// ---- tensor maps for the TMA-fed GAE kernel
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static bool gae_tma_usable(const void* r, const void* d, const void* v, int M) {
+  const char* env = getenv("CAT_GAE_TMA");
+  if (env && env[0] == '0') return false;                                  // opt-out (A/B against the register-pipelined kernel)
+  if (M % 16 != 0) return false;                                           // u8 row stride must be a multiple of 16 bytes
+  if ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(v)) & 15) return false;
+  return tensor_map_encoder() != nullptr;
+}
+
+static bool encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* ptr, int M, int T, int elem) {
+  const cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)T};
+  const cuuint64_t strides[1] = {(cuuint64_t)M * elem};
+  const cuuint32_t box[2] = {(cuuint32_t)kTmaCols, (cuuint32_t)kTmaRows};
+  const cuuint32_t estr[2] = {1, 1};
+  return tensor_map_encoder()(tm, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int cat_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values, float* returns,
             float* advantages, double* stats_dev, int32_t T, int32_t M, float gamma, float lam, void* stream) {
   if (!rewards || !dones || !values || !last_values || !returns || !advantages || !stats_dev)
@@ -471,7 +506,25 @@ int cat_gae(const float* rewards, const uint8_t* dones, const float* values, con
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(double), s));
   const int threads = kGaeCols * kGaeSegs, blocks = (M + kGaeCols - 1) / kGaeCols;
-  if ((long long)(T + kGaeS) * M < (1ll << 31))
+  const bool idx32 = (long long)(T + kTmaRows) * M < (1ll << 31);
+  if (gae_tma_usable(rewards, dones, values, M)) {
+    // TMA-fed variant: tensor maps over (M, T) for r, V (fp32) and done (u8), box 64 columns x 32 steps
+    CUtensorMap tm_r, tm_v, tm_d;
+    if (encode_2d(&tm_r, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rewards, M, T, 4) && encode_2d(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, values, M, T, 4) &&
+        encode_2d(&tm_d, CU_TENSOR_MAP_DATA_TYPE_UINT8, dones, M, T, 1)) {
+      const int smem = kTmaStages * kTmaStageBytes, tblocks = (M + kTmaCols - 1) / kTmaCols;
+      if (idx32) {
+        CUDA_TRY(cudaFuncSetAttribute(cat_gae_tma_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cat_gae_tma_kernel<uint32_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+      } else {
+        CUDA_TRY(cudaFuncSetAttribute(cat_gae_tma_kernel<size_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cat_gae_tma_kernel<size_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+      }
+      CUDA_TRY(cudaGetLastError());
+      return CAT_OK;
+    }
+  }
+  if (idx32)
     cat_gae_kernel<uint32_t><<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
   else
     cat_gae_kernel<size_t><<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam);

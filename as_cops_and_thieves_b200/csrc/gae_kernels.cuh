@@ -162,6 +162,152 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
   }
 }
 
+// ---- the same scan, fed by TMA.  One CTA owns 64 columns; the chunk's 32 x 64 tiles of r, V (fp32) and done (u8)
+// arrive in shared memory through three `cp.async.bulk.tensor.2d` copies (one per array, tensor maps encoded by
+// the host per call) that complete on an mbarrier; a 3-stage ring keeps two chunks (36 KB) in flight per CTA while
+// the third is folded, scanned and written — the in-flight bytes cost no registers, so four CTAs (1024 threads)
+// fit per SM with 144 KB of loads outstanding.  Rows before t = 0 and columns beyond M are zero-filled by the TMA
+// unit (out-of-bounds box) and masked in the arithmetic.  Needs M % 16 == 0 (tensor-map stride rule for the u8
+// array); cat_gae falls back to the kernel above otherwise.
+#ifndef CAT_GAE_TMA_STAGES
+#define CAT_GAE_TMA_STAGES 3
+#endif
+constexpr int kTmaCols = 64, kTmaSegs = 4, kTmaRows = kTmaSegs * kGaeS, kTmaStages = CAT_GAE_TMA_STAGES;
+constexpr int kTmaStageBytes = kTmaRows * kTmaCols * (4 + 4 + 1);   // 18432, a multiple of 128
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tmap), "r"(c0), "r"(c1),
+      "r"((uint32_t)__cvta_generic_to_shared(mbar))
+      : "memory");
+}
+
+template <typename Index>
+__global__ void __launch_bounds__(kTmaCols* kTmaSegs, 4)
+    cat_gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_v,
+                       const __grid_constant__ CUtensorMap tm_d, const float* __restrict__ last_values,
+                       float* __restrict__ returns, float* __restrict__ advantages, double* __restrict__ stats, int T, int M,
+                       float gamma, float lam) {
+  extern __shared__ __align__(128) unsigned char tiles[];
+  __shared__ __align__(8) unsigned long long full[kTmaStages];
+  __shared__ float sA[kTmaSegs][kTmaCols + 8], sB[kTmaSegs][kTmaCols + 8];   // +8: the scan's (segment, column) reads hit 32 banks
+  __shared__ float sCarryAdv[kTmaCols], sCarryV[kTmaCols];
+  __shared__ double sh1[8], sh2[8];
+  const int tid = threadIdx.x, col = tid & (kTmaCols - 1), seg = tid / kTmaCols, lane = tid & 31;
+  const int c0 = blockIdx.x * kTmaCols, gcol = c0 + col;
+  const bool valid = gcol < M;
+  const float gl = gamma * lam;
+  const int nch = (T + kTmaRows - 1) / kTmaRows;
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int k) {   // chunk k covers rows [T - (k+1)*32, T - k*32)
+    const int s = k % kTmaStages, t_lo = T - (k + 1) * kTmaRows;
+    unsigned char* base = tiles + s * kTmaStageBytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full[s])),
+                 "r"(kTmaStageBytes)
+                 : "memory");
+    tma_load_2d(base, &tm_r, c0, t_lo, &full[s]);
+    tma_load_2d(base + kTmaRows * kTmaCols * 4, &tm_v, c0, t_lo, &full[s]);
+    tma_load_2d(base + kTmaRows * kTmaCols * 8, &tm_d, c0, t_lo, &full[s]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < kTmaStages - 1 && k < nch; ++k) issue(k);
+  float carry_adv = 0.f, carry_v = valid ? last_values[gcol] : 0.f;
+  double s1 = 0.0, s2 = 0.0;
+  const int rb = kTmaRows - (seg + 1) * kGaeS;   // this thread's 8 rows of the tile (segment 0 = the latest steps)
+#pragma unroll 1
+  for (int k = 0; k < nch; ++k) {
+    const int s = k % kTmaStages, t_lo = T - (k + 1) * kTmaRows;
+    {
+      const uint32_t parity = (uint32_t)(k / kTmaStages) & 1u, addr = (uint32_t)__cvta_generic_to_shared(&full[s]);
+      uint32_t done = 0;
+#pragma unroll 1
+      while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+    const float* R = reinterpret_cast<const float*>(tiles + s * kTmaStageBytes);
+    const float* V = R + kTmaRows * kTmaCols;
+    const unsigned char* D = reinterpret_cast<const unsigned char*>(V + kTmaRows * kTmaCols);
+    float r[kGaeS], v[kGaeS];
+    uint32_t dmask = 0;
+#pragma unroll
+    for (int i = 0; i < kGaeS; ++i) {
+      r[i] = R[(rb + i) * kTmaCols + col]; v[i] = V[(rb + i) * kTmaCols + col];
+      dmask |= (D[(rb + i) * kTmaCols + col] ? 1u : 0u) << i;
+    }
+    const float vnext = seg == 0 ? carry_v : V[(rb + kGaeS) * kTmaCols + col];
+    float A = 1.f, B = 0.f;
+#pragma unroll
+    for (int i = kGaeS - 1; i >= 0; --i) {
+      if (t_lo + rb + i >= 0) {
+        const float nd = (dmask >> i) & 1u ? 0.f : 1.f;
+        const float vn = (i == kGaeS - 1) ? vnext : v[i + 1];
+        r[i] = r[i] - v[i] + gamma * nd * vn;
+        B = fmaf(gl * nd, B, r[i]);
+        A *= gl * nd;
+      }
+    }
+    sA[seg][col] = A; sB[seg][col] = B;
+    if (seg == kTmaSegs - 1) sCarryV[col] = v[0];
+    if (seg == 0) sCarryAdv[col] = carry_adv;
+    __syncthreads();
+    {  // 4 lanes per column: sub-lane l holds the map of segment l (x_{l+1} = B_l + A_l * x_l)
+      const int sl = tid & (kTmaSegs - 1), scol = tid / kTmaSegs;
+      float a = sA[sl][scol], b = sB[sl][scol];
+#pragma unroll
+      for (int d = 1; d < kTmaSegs; d <<= 1) {
+        const float ap = __shfl_up_sync(0xFFFFFFFFu, a, d, kTmaSegs), bp = __shfl_up_sync(0xFFFFFFFFu, b, d, kTmaSegs);
+        if (sl >= d) { b = fmaf(a, bp, b); a *= ap; }
+      }
+      const float x0 = sCarryAdv[scol];
+      const float xout = fmaf(a, x0, b);
+      float xin = __shfl_up_sync(0xFFFFFFFFu, xout, 1, kTmaSegs);
+      if (sl == 0) xin = x0;
+      __syncwarp();
+      sA[sl][scol] = xin;
+      if (sl == kTmaSegs - 1) sB[0][scol] = xout;
+    }
+    __syncthreads();
+    float adv = sA[seg][col];
+    carry_adv = sB[0][col];
+    carry_v = sCarryV[col];
+    float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int i = kGaeS - 1; i >= 0; --i) {
+      const int t = t_lo + rb + i;
+      if (valid && t >= 0) {
+        const float nd = (dmask >> i) & 1u ? 0.f : 1.f;
+        adv = fmaf(gl * nd, adv, r[i]);
+        const Index idx = (Index)t * (Index)M + (Index)gcol;
+        advantages[idx] = adv;
+        __stcs(returns + idx, adv + v[i]);
+        p1 += adv; p2 = fmaf(adv, adv, p2);
+      }
+    }
+    s1 += (double)p1; s2 += (double)p2;
+    __syncthreads();                                   // every thread has read stage s (and sA / sB): it can be refilled
+    if (tid == 0 && k + kTmaStages - 1 < nch) issue(k + kTmaStages - 1);   // that stage was consumed in iteration k - 1
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+    s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+  }
+  if (lane == 0) { sh1[tid >> 5] = s1; sh2[tid >> 5] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < (kTmaCols * kTmaSegs) / 32; ++i) { a += sh1[i]; b += sh2[i]; }
+    atomicAdd(&stats[0], a);
+    atomicAdd(&stats[1], b);
+  }
+}
+
 // In-place (adv - mean) / (std + 1e-8): 4 B read + 4 B written per sample, four independent 16-B loads in
 // flight per thread.
 __global__ void __launch_bounds__(256) cat_adv_normalize_kernel(float* __restrict__ adv, long long n,

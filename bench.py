@@ -265,7 +265,7 @@ def time_e2e(torch, cw, K, W, dist=None, mode="pipelined"):
 
 
 def time_gae(torch, dev, flush, T=256, M=49152, iters=30):
-    """north-star item 4: the GAE scan (9 B read + 8 B written per sample) and the in-place advantage
+    """north-star item 4: the GAE scan (TMA-fed kernel; 9 B read + 8 B written per sample) and the in-place advantage
     normalisation (4 B + 4 B), each timed with its own CUDA events.  L2 is flushed before every launch by READING a 192 MiB buffer
     (a write flush would leave 126 MB of dirty lines whose write-back then competes with the timed kernel)."""
     from as_cops_and_thieves_b200 import _lib

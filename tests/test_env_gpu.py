@@ -192,10 +192,15 @@ def test_auto_reset_emits_terminal_reward_and_new_episode_observation(cuda_devic
     w.close()
 
 
-def test_gae_kernels_match_oracle_and_torch(cuda_device):
+@pytest.mark.parametrize("tma", ["0", "1"], ids=["ldg", "tma"])
+def test_gae_kernels_match_oracle_and_torch(cuda_device, monkeypatch, tma):
+    # "tma": the TMA-fed variant (tensor maps + mbarrier ring) for the shapes it accepts (columns % 16 == 0); the
+    # other shapes exercise the fallback to the register-pipelined kernel
+    monkeypatch.setenv("CAT_GAE_TMA", tma)
     g = torch.Generator().manual_seed(0)
     # T spans: one partial segment, one chunk (256 = 32 segments x 8 steps), ragged multi-chunk carries
-    for T, shape in ((64, (300, 3)), (16, (1000,)), (5, (7, 1)), (1, (33,)), (256, (40,)), (257, (31, 3)), (600, (65,))):
+    for T, shape in ((64, (300, 3)), (16, (1000,)), (5, (7, 1)), (1, (33,)), (256, (40,)), (257, (31, 3)), (600, (65,)),
+                     (600, (64,)), (33, (16, 3)), (257, (1024,)), (32, (16,)), (1, (16,)), (96, (80,))):
         r = torch.randn((T,) + shape, generator=g)
         v = torch.randn((T,) + shape, generator=g)
         d = torch.rand((T,) + shape, generator=g) < 0.08
