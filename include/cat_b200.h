@@ -185,7 +185,9 @@ int cat_env_set_state(CatEnv* env, void* state_dev, const CatStateView* view, vo
 
 /* skrl MAPPO._update GAE (call site agent_learning_utils.py:198-199).
  * rewards/values [T][M] f32, dones [T][M] u8, last_values [M]; returns/advantages [T][M].
- * stats_dev: 2 doubles {sum(adv), sum(adv^2)} accumulated by this call (zeroed first). */
+ * stats_dev: 2 doubles {sum(adv), sum(adv^2)} accumulated by this call (zeroed first).
+ * Runs the TMA-fed kernel when M % 16 == 0 and the three input arrays are 16-byte aligned, the register-pipelined
+ * kernel otherwise (environment CAT_GAE_TMA=0 forces the latter); both give the same results to fp32 rounding. */
 int cat_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values,
             float* returns, float* advantages, double* stats_dev, int32_t T, int32_t M, float gamma,
             float lam, void* stream);
