@@ -466,6 +466,7 @@ def run_b200(args):
                                                                     "bytes_per_agent_step": 786 + 1453}
         w3.close()
         line["gae"] = time_gae(torch, dev, flush)
+        line["gae_T1024"] = time_gae(torch, dev, flush, T=1024, iters=10)     # a reference-length rollout (4096 / 4)
         cpu = time_cpu_port(map_name, free, 512, seconds=12.0)
         line["cpu_baseline"] = {"value": cpu["value"], "unit": "agent-steps/s", "cores": cpu["cores"], "kind": "port",
                                 "sample": f"{cpu['worlds']} {map_name} worlds x {cpu['steps']} steps in {cpu['seconds']:.1f} s, "
