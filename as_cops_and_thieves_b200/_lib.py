@@ -13,10 +13,11 @@ import numpy as np
 
 from . import build as _build
 
-CAT_ABI_VERSION = 3
+CAT_ABI_VERSION = 4
 CAT_MAX_AGENTS = 8
 CAT_MAX_RAYS = 128
 CAT_WALL_SLOTS = 4
+CAT_NEAR_SLOTS = 4
 
 
 class CatError(RuntimeError):
@@ -46,7 +47,7 @@ class CatParams(C.Structure):
         ("n_rays", C.c_int32), ("iterations", C.c_int32),
         ("collision_slop", C.c_double), ("collision_bias", C.c_double),
         ("collision_persistence", C.c_int32), ("stale_shape_cache", C.c_int32),
-        ("auto_reset", C.c_int32), ("seed", C.c_uint64),
+        ("auto_reset", C.c_int32), ("seed", C.c_uint64), ("ray_list_cell", C.c_double),
     ]
 
 
@@ -58,13 +59,21 @@ class CatStepIO(C.Structure):
         ("shared_dist", C.c_void_p), ("shared_type", C.c_void_p), ("team_pos", C.c_void_p),
         ("obs_f32", C.c_void_p), ("state_f32", C.c_void_p), ("hit_point", C.c_void_p),
         ("obs_dist_world_stride", C.c_int32), ("obs_type_world_stride", C.c_int32),
+        ("record", C.c_void_p), ("record_world_stride", C.c_int32),
+        ("critic_f32", C.c_void_p), ("obs_bf16", C.c_void_p), ("critic_bf16", C.c_void_p),
     ]
+
+
+class CatRecordLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("bytes", "off_dist", "off_type", "off_reward", "off_terminated",
+                                         "off_truncated", "off_winner")]
 
 
 class CatEnvInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_worlds", "n_agents", "n_cops", "n_thieves", "n_rays", "n_hulls", "n_edges", "state_dim",
-        "record_words", "map_blob_bytes", "smem_bytes_per_cta", "warps_per_cta", "grid", "n_pairs")]
+        "record_words", "map_blob_bytes", "smem_bytes_per_cta", "warps_per_cta", "grid", "n_pairs",
+        "ray_list_cells", "ray_list_nx", "ray_list_ny")] + [("ray_list_cell", C.c_float), ("ray_list_bytes", C.c_int64)]
 
 
 class CatStateView(C.Structure):
@@ -76,6 +85,7 @@ class CatStateView(C.Structure):
 #: every symbol ``include/cat_b200.h`` declares
 EXPORTS = (
     "cat_abi_version", "cat_last_error", "cat_env_create", "cat_env_destroy", "cat_env_info",
+    "cat_env_record_layout", "cat_env_overflow_counts",
     "cat_env_set_seed", "cat_env_state_bytes", "cat_env_init_state", "cat_env_reset", "cat_env_step", "cat_env_step_host", "cat_env_observe",
     "cat_env_get_state", "cat_env_set_state", "cat_gae", "cat_adv_normalize",
 )
@@ -113,7 +123,9 @@ def load():
     L.cat_env_init_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     for fn in (L.cat_env_reset, L.cat_env_step, L.cat_env_observe):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStepIO), C.c_void_p]
-    L.cat_env_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStepIO), C.POINTER(CatStepIO), C.c_int32, C.c_void_p]
+    L.cat_env_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.cat_env_record_layout.argtypes = [C.c_void_p, C.POINTER(CatRecordLayout)]
+    L.cat_env_overflow_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 2), C.c_int32]
     for fn in (L.cat_env_get_state, L.cat_env_set_state):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStateView), C.c_void_p]
     L.cat_gae.argtypes = [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p]

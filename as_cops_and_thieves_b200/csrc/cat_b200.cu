@@ -28,7 +28,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cat_b200.h"
@@ -49,21 +51,44 @@ int fail(int code, const std::string& msg) {
       return fail(CAT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
   } while (0)
 
+#include "ray_lists.h"
 #include "world_kernel.cuh"
 #include "state_view.cuh"
 #include "gae_kernels.cuh"
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// Every ABI entry runs with the environment's device current and restores the caller's device on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+    if (prev == device) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEVICE_SCOPE(env)                                                                    \
+  DeviceGuard _guard((env)->device);                                                          \
+  if (!_guard.ok) return fail(CAT_ERR_CUDA, "cudaSetDevice(" + std::to_string((env)->device) + ") failed")
+
 }  // namespace
 
 // ------------------------------------------------------------------ host side / C ABI
+typedef void (*WorldKernel)(const KParams);
+
 struct CatEnv {
+  WorldKernel kernel = nullptr;
   int device = 0;
   int n_worlds = 0;
   unsigned char* blob_dev = nullptr;
   int32_t* view_off_dev = nullptr;
   uint16_t* view_edges_dev = nullptr;
+  uint4* ray_slots_dev = nullptr;
+  uint32_t* ray_ovf_dev = nullptr;
+  unsigned long long* overflow_dev = nullptr;
+  CatRecordLayout rec{};
   KParams kp{};
   CatEnvInfo info{};
   int smem_bytes = 0;
@@ -78,13 +103,23 @@ struct CatEnv {
 
 struct LaunchShape { int threads, smem, grid; };
 
+// the kernel instantiation an environment runs (fixed at creation): agents / rays as compile-time constants for the
+// shipped shape, the any-shape instantiation otherwise (CAT_GENERIC_KERNEL=1 at creation forces it: test knob)
+static WorldKernel pick_world_kernel(int A, int R) {
+  const char* e = getenv("CAT_GENERIC_KERNEL");
+  const bool generic = e && e[0] == '1';
+  return (A == 3 && R == 90 && !generic) ? cat_world_kernel<3, 90> : cat_world_kernel<0, 0>;
+}
+
 static bool pick_launch_shape(const CatEnv* env, int n_worlds, LaunchShape* out) {
   long long best_score = -1;
-  for (int wpc = kWarpsPerCta; wpc >= 2; --wpc) {   // any warp count: 4096 worlds = 586 CTAs of 7 warps = 28 warps per SM
+  int wpc_max = kMaxThreads / 32;
+  if (const char* e = getenv("CAT_MAX_WARPS_PER_CTA")) { const int v = atoi(e); if (v >= 2 && v < wpc_max) wpc_max = v; }   // tuning knob
+  for (int wpc = wpc_max; wpc >= 2; --wpc) {   // any warp count: 4096 worlds = 586 CTAs of 7 warps = 28 warps per SM
     const int smem = align_up(env->blob_bytes, 128) + wpc * env->kp.scratch_bytes;
     if (smem > env->max_optin) continue;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_world_kernel, wpc * 32, smem) != cudaSuccess || occ < 1) continue;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env->kernel, wpc * 32, smem) != cudaSuccess || occ < 1) continue;
     const int need = (n_worlds + wpc - 1) / wpc;
     const bool one_wave = need <= env->n_sm * occ;
     // one wave: fewest warps on the fullest SM; persistent: most resident warps per SM
@@ -219,14 +254,21 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
     for (int i = 0; i < 2 * A; ++i) ip[i] = (float)map->init_pos[i];
   }
 
-  CUDA_TRY(cudaSetDevice(device));
   CatEnv* env = new CatEnv();
   env->device = device;
   env->n_worlds = n_worlds;
-  cudaError_t ce = cudaMalloc(&env->blob_dev, blob_bytes);
-  if (ce != cudaSuccess) { delete env; return fail(CAT_ERR_CUDA, std::string("cudaMalloc(map blob): ") + cudaGetErrorString(ce)); }
-  ce = cudaMemcpy(env->blob_dev, blob.data(), blob_bytes, cudaMemcpyHostToDevice);
-  if (ce != cudaSuccess) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, std::string("cudaMemcpy(map blob): ") + cudaGetErrorString(ce)); }
+  DeviceGuard guard(device);
+  if (!guard.ok) { delete env; return fail(CAT_ERR_CUDA, "cudaSetDevice(" + std::to_string(device) + ") failed (no CUDA device?)"); }
+  // every failure below goes through cat_env_destroy: nothing allocated so far is leaked
+#define CREATE_TRY(expr, what)                                                                              \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) { cat_env_destroy(env); return fail(CAT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+  CREATE_TRY(cudaMalloc(&env->blob_dev, blob_bytes), "cudaMalloc(map blob)");
+  CREATE_TRY(cudaMemcpy(env->blob_dev, blob.data(), blob_bytes, cudaMemcpyHostToDevice), "cudaMemcpy(map blob)");
+  CREATE_TRY(cudaMalloc(&env->overflow_dev, 2 * sizeof(unsigned long long)), "cudaMalloc(overflow counters)");
+  CREATE_TRY(cudaMemset(env->overflow_dev, 0, 2 * sizeof(unsigned long long)), "cudaMemset(overflow counters)");
 
   KParams& k = env->kp;
   k.blob = env->blob_dev; k.blob_bytes = blob_bytes;
@@ -238,17 +280,26 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
     const int n_list = map->view_cell_off[ncell];
     std::vector<uint16_t> ve((size_t)(n_list > 0 ? n_list : 1));
     for (int i = 0; i < n_list; ++i) ve[i] = (uint16_t)map->view_cell_edges[i];
-    cudaError_t e1 = cudaMalloc(&env->view_off_dev, sizeof(int32_t) * (ncell + 1));
-    cudaError_t e2 = cudaMalloc(&env->view_edges_dev, sizeof(uint16_t) * ve.size());
-    if (e1 == cudaSuccess && e2 == cudaSuccess)
-      e1 = cudaMemcpy(env->view_off_dev, map->view_cell_off, sizeof(int32_t) * (ncell + 1), cudaMemcpyHostToDevice);
-    if (e1 == cudaSuccess && e2 == cudaSuccess)
-      e2 = cudaMemcpy(env->view_edges_dev, ve.data(), sizeof(uint16_t) * ve.size(), cudaMemcpyHostToDevice);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      cudaFree(env->view_off_dev); cudaFree(env->view_edges_dev); cudaFree(env->blob_dev); delete env;
-      return fail(CAT_ERR_CUDA, "cudaMalloc/cudaMemcpy(view lists) failed");
-    }
+    CREATE_TRY(cudaMalloc(&env->view_off_dev, sizeof(int32_t) * (ncell + 1)), "cudaMalloc(view lists)");
+    CREATE_TRY(cudaMalloc(&env->view_edges_dev, sizeof(uint16_t) * ve.size()), "cudaMalloc(view lists)");
+    CREATE_TRY(cudaMemcpy(env->view_off_dev, map->view_cell_off, sizeof(int32_t) * (ncell + 1), cudaMemcpyHostToDevice), "cudaMemcpy(view lists)");
+    CREATE_TRY(cudaMemcpy(env->view_edges_dev, ve.data(), sizeof(uint16_t) * ve.size(), cudaMemcpyHostToDevice), "cudaMemcpy(view lists)");
     k.view_off = env->view_off_dev; k.view_edges = env->view_edges_dev;
+  }
+  k.overflow = env->overflow_dev;
+  // per-(cell, ray) candidate lists of the sensor sweep (ray_lists.h), built here from the map description
+  CatEnvInfo& inf = env->info;
+  if (!(pr->ray_list_cell < 0.0)) {
+    RayLists rl;
+    build_ray_lists(map, R, pr->ray_length, pr->wall_radius + pr->ray_radius, pr->ray_list_cell, &rl);
+    CREATE_TRY(cudaMalloc(&env->ray_slots_dev, rl.slots.size() * 4), "cudaMalloc(ray lists)");
+    CREATE_TRY(cudaMalloc(&env->ray_ovf_dev, rl.ovf.size() * 4), "cudaMalloc(ray lists)");
+    CREATE_TRY(cudaMemcpy(env->ray_slots_dev, rl.slots.data(), rl.slots.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(ray lists)");
+    CREATE_TRY(cudaMemcpy(env->ray_ovf_dev, rl.ovf.data(), rl.ovf.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(ray lists)");
+    k.ray_slots = env->ray_slots_dev; k.ray_ovf = env->ray_ovf_dev;
+    k.rg_x0 = rl.g.x0; k.rg_y0 = rl.g.y0; k.rg_inv_cell = rl.g.inv_cell; k.rg_nx = rl.g.nx; k.rg_ny = rl.g.ny;
+    inf.ray_list_cells = rl.g.nx * rl.g.ny; inf.ray_list_nx = rl.g.nx; inf.ray_list_ny = rl.g.ny; inf.ray_list_cell = rl.g.cell;
+    inf.ray_list_bytes = (int64_t)(rl.slots.size() + rl.ovf.size()) * 4;
   }
   k.n_worlds = n_worlds; k.gid0 = gid0;
   k.A = A; k.nc = map->n_cops; k.R = R; k.P = P; k.nrays = A * R; k.nrays_pad = align_up(A * R, 32);
@@ -262,14 +313,24 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   // scratch layout (bytes)
   int so = k.rec_words * 4;
   auto stake = [&](int bytes) { int o = so; so = align_up(so + bytes, 16); return o; };
-  k.s_rdist = stake(k.nrays_pad * 2);
-  k.s_rtype = stake(k.nrays_pad);
+  // the world's output record is staged contiguously (CatRecordLayout): f16 distances | u8 types | f32 rewards | flags
+  CatRecordLayout& rc = env->rec;
+  rc.off_dist = 0;
+  rc.off_type = align_up(k.nrays * 2, 16);
+  rc.off_reward = align_up(rc.off_type + k.nrays, 4);
+  rc.off_terminated = rc.off_reward + 4 * A; rc.off_truncated = rc.off_terminated + 1; rc.off_winner = rc.off_terminated + 2;
+  rc.bytes = align_up(rc.off_terminated + 3, 16);
+  k.r_bytes = rc.bytes; k.r_off_reward = rc.off_reward; k.r_off_flags = rc.off_terminated;
+  k.s_rdist = stake(rc.bytes);
+  k.s_rtype = k.s_rdist + rc.off_type;
   k.s_min = stake(CAT_MAX_AGENTS * 4);
+  k.s_rcell = stake(CAT_MAX_AGENTS * 4);
   k.s_nearcnt = stake(CAT_MAX_AGENTS * 4);
   k.s_con = stake(k.maxc * 32);
   k.s_ccount = stake(CAT_MAX_AGENTS * 4);
   k.s_order = stake(k.maxc);
-  k.s_best = stake(k.nrays_pad * 8);
+  // per-ray hit keys (8 B each); with ray lists the same area first holds the rays' 16-byte candidate slots
+  k.s_best = stake(k.ray_slots ? k.nrays_pad * 16 : k.nrays_pad * 8);
   k.s_cand = stake(64 * 2);
   k.scratch_bytes = align_up(so, 128);
   k.state_dim = 0;
@@ -289,34 +350,42 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   int max_optin = 0, n_sm = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-  const int smem_max = align_up(blob_bytes, 128) + kWarpsPerCta * k.scratch_bytes;
+  const int smem_max = align_up(blob_bytes, 128) + 2 * k.scratch_bytes;
   if (align_up(blob_bytes, 128) + 2 * k.scratch_bytes > max_optin) {
-    cudaFree(env->blob_dev); delete env;
+    cat_env_destroy(env);
     return fail(CAT_ERR_LIMIT, "map does not fit in shared memory (" + std::to_string(smem_max) + " B)");
   }
-  ce = cudaFuncSetAttribute(cat_world_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max < max_optin ? smem_max : max_optin);
-  if (ce != cudaSuccess) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
+  // The attribute belongs to the FUNCTION (per device), not to this environment: always raise it to the device
+  // maximum, so creating an environment for a smaller map never lowers the cap of one that is still alive.
+  cudaFuncAttributes fattr{};
+  env->kernel = pick_world_kernel(A, R);
+  CREATE_TRY(cudaFuncGetAttributes(&fattr, env->kernel), "cudaFuncGetAttributes");
+  max_optin -= (int)fattr.sharedSizeBytes;      // the opt-in limit covers static + dynamic shared memory
+  CREATE_TRY(cudaFuncSetAttribute(env->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin), "cudaFuncSetAttribute");
   env->blob_bytes = blob_bytes; env->max_optin = max_optin; env->n_sm = n_sm;
   LaunchShape shp;
-  if (!pick_launch_shape(env, n_worlds, &shp)) { cudaFree(env->blob_dev); delete env; return fail(CAT_ERR_CUDA, "occupancy query failed"); }
+  if (!pick_launch_shape(env, n_worlds, &shp)) { cat_env_destroy(env); return fail(CAT_ERR_CUDA, "occupancy query failed"); }
   env->threads = shp.threads; env->smem_bytes = shp.smem; env->grid = shp.grid;
   k.world_begin = 0; k.world_end = n_worlds;
 
-  CatEnvInfo& inf = env->info;
   inf.n_worlds = n_worlds; inf.n_agents = A; inf.n_cops = map->n_cops; inf.n_thieves = map->n_thieves;
   inf.n_rays = R; inf.n_hulls = H; inf.n_edges = E; inf.state_dim = k.state_dim; inf.record_words = k.rec_words;
   inf.map_blob_bytes = blob_bytes; inf.smem_bytes_per_cta = env->smem_bytes; inf.warps_per_cta = env->threads / 32;
   inf.grid = env->grid; inf.n_pairs = P;
+#undef CREATE_TRY
   *out = env;
   return CAT_OK;
 }
 
 int cat_env_destroy(CatEnv* env) {
   if (!env) return CAT_OK;
-  cudaSetDevice(env->device);
+  DeviceGuard guard(env->device);
   if (env->blob_dev) cudaFree(env->blob_dev);
   if (env->view_off_dev) cudaFree(env->view_off_dev);
   if (env->view_edges_dev) cudaFree(env->view_edges_dev);
+  if (env->ray_slots_dev) cudaFree(env->ray_slots_dev);
+  if (env->ray_ovf_dev) cudaFree(env->ray_ovf_dev);
+  if (env->overflow_dev) cudaFree(env->overflow_dev);
   for (cudaEvent_t e : env->chunk_events) cudaEventDestroy(e);
   if (env->copies_done) cudaEventDestroy(env->copies_done);
   if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
@@ -327,6 +396,23 @@ int cat_env_destroy(CatEnv* env) {
 int cat_env_info(const CatEnv* env, CatEnvInfo* info) {
   if (!env || !info) return fail(CAT_ERR_INVALID, "null argument");
   *info = env->info;
+  return CAT_OK;
+}
+
+int cat_env_record_layout(const CatEnv* env, CatRecordLayout* layout) {
+  if (!env || !layout) return fail(CAT_ERR_INVALID, "null argument");
+  *layout = env->rec;
+  return CAT_OK;
+}
+
+int cat_env_overflow_counts(CatEnv* env, uint64_t out[2], int32_t reset) {
+  if (!env || !out) return fail(CAT_ERR_INVALID, "null argument");
+  DEVICE_SCOPE(env);
+  CUDA_TRY(cudaDeviceSynchronize());
+  unsigned long long v[2] = {0, 0};
+  CUDA_TRY(cudaMemcpy(v, env->overflow_dev, sizeof(v), cudaMemcpyDeviceToHost));
+  out[0] = v[0]; out[1] = v[1];
+  if (reset) CUDA_TRY(cudaMemset(env->overflow_dev, 0, sizeof(v)));
   return CAT_OK;
 }
 
@@ -365,6 +451,14 @@ static int prepare(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, 
     k.terminated = io->terminated;
     k.truncated = io->truncated; k.winner = io->winner; k.shared_dist = io->shared_dist; k.shared_type = io->shared_type;
     k.team_pos = io->team_pos; k.obs_f32 = io->obs_f32; k.state_f32 = io->state_f32; k.hit_point = io->hit_point;
+    k.critic_f32 = io->critic_f32; k.obs_bf16 = io->obs_bf16; k.critic_bf16 = io->critic_bf16;
+    if (io->record) {
+      k.record = reinterpret_cast<unsigned char*>(io->record);
+      k.record_stride = io->record_world_stride ? io->record_world_stride : k.r_bytes;
+      if ((reinterpret_cast<uintptr_t>(io->record) & 15) || (k.record_stride & 15) || k.record_stride < k.r_bytes)
+        return fail(CAT_ERR_INVALID, "record output must be 16-byte aligned with a world stride that is a multiple of 16 and >= CatRecordLayout.bytes");
+      k.obs_dist = nullptr; k.obs_type = nullptr; k.reward = nullptr; k.terminated = nullptr; k.truncated = nullptr; k.winner = nullptr;
+    }
   } else if (mode == MODE_STEP) {
     return fail(CAT_ERR_INVALID, "step needs a CatStepIO");
   }
@@ -376,7 +470,8 @@ static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, v
   KParams k;
   const int rc = prepare(env, state_dev, io, mode, &k);
   if (rc != CAT_OK) return rc;
-  cat_world_kernel<<<env->grid, env->threads, env->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(k);
+  DEVICE_SCOPE(env);
+  env->kernel<<<env->grid, env->threads, env->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(k);
   CUDA_TRY(cudaGetLastError());
   return CAT_OK;
 }
@@ -387,22 +482,18 @@ int cat_env_step(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream
 int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream) { return launch(env, state_dev, io, MODE_OBSERVE, stream); }
 
 // BaseEnv.step for a caller whose buffers are pinned HOST memory, pipelined: the worlds are stepped in
-// `n_chunks` consecutive launches on `stream`; as soon as a chunk's launch has finished, its slice of every
-// output array is copied to the host arrays on an internal copy stream (DMA engine, full PCIe rate) while
-// the next chunk computes.  `stream` finally waits for the copies, so one cudaStreamSynchronize(stream) by
-// the caller makes every result visible.  dev: the dense device outputs; host: the same arrays in pinned
-// host memory (dense); host->actions: u8 [N][A] in pinned host memory, read by the kernel directly.
-int cat_env_step_host(CatEnv* env, void* state_dev, const CatStepIO* dev, const CatStepIO* host, int32_t n_chunks,
-                      void* stream_) {
-  if (!env || !dev || !host) return fail(CAT_ERR_INVALID, "null argument");
-  if (!host->actions || host->actions_kind != 0) return fail(CAT_ERR_INVALID, "host actions must be u8 [N][A] (kind 0)");
-  if (dev->obs_dist_world_stride || dev->obs_type_world_stride || host->obs_dist_world_stride || host->obs_type_world_stride)
-    return fail(CAT_ERR_INVALID, "the chunked host path uses dense observation arrays");
+// `n_chunks` consecutive launches on `stream`, each writing its worlds' output RECORDS into `records_dev`; as
+// soon as a chunk's launch has finished, its block of records moves to `records_host` with ONE cudaMemcpyAsync on
+// an internal copy stream (DMA engine, full PCIe rate) while the next chunk computes.  `stream` finally waits for
+// the copies, so one cudaStreamSynchronize(stream) by the caller makes every result visible.
+int cat_env_step_host(CatEnv* env, void* state_dev, const uint8_t* host_actions, void* records_dev, void* records_host,
+                      int32_t record_world_stride, int32_t n_chunks, void* stream_) {
+  if (!env || !host_actions || !records_dev || !records_host) return fail(CAT_ERR_INVALID, "null argument");
   const int N = env->n_worlds;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > N) n_chunks = N;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CUDA_TRY(cudaSetDevice(env->device));
+  DEVICE_SCOPE(env);
   if (!env->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
   if (!env->copies_done) CUDA_TRY(cudaEventCreateWithFlags(&env->copies_done, cudaEventDisableTiming));
   while ((int)env->chunk_events.size() < n_chunks) {
@@ -410,12 +501,13 @@ int cat_env_step_host(CatEnv* env, void* state_dev, const CatStepIO* dev, const 
     CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     env->chunk_events.push_back(e);
   }
-  CatStepIO io = *dev;
-  io.actions = host->actions; io.actions_kind = 0;
+  CatStepIO io{};
+  io.actions = host_actions; io.actions_kind = 0;
+  io.record = records_dev; io.record_world_stride = record_world_stride;
   KParams k;
   const int rc = prepare(env, state_dev, &io, MODE_STEP, &k);
   if (rc != CAT_OK) return rc;
-  const int A = k.A, nrays = k.nrays;
+  const size_t stride = (size_t)k.record_stride;
   const int per = ((N + n_chunks - 1) / n_chunks + 7) / 8 * 8;   // worlds per chunk, a multiple of the CTA's 8 warps
   int c = 0;
   for (int w0 = 0; w0 < N; w0 += per, ++c) {
@@ -423,21 +515,12 @@ int cat_env_step_host(CatEnv* env, void* state_dev, const CatStepIO* dev, const 
     LaunchShape shp;
     if (!pick_launch_shape(env, n, &shp)) return fail(CAT_ERR_CUDA, "occupancy query failed");
     k.world_begin = w0; k.world_end = w1;
-    cat_world_kernel<<<shp.grid, shp.threads, shp.smem, stream>>>(k);
+    env->kernel<<<shp.grid, shp.threads, shp.smem, stream>>>(k);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(env->chunk_events[c], stream));
     CUDA_TRY(cudaStreamWaitEvent(env->copy_stream, env->chunk_events[c], 0));
-    auto copy = [&](void* h, const void* d, size_t elem_bytes) -> cudaError_t {
-      if (!h || !d) return cudaSuccess;
-      return cudaMemcpyAsync(static_cast<char*>(h) + (size_t)w0 * elem_bytes, static_cast<const char*>(d) + (size_t)w0 * elem_bytes,
-                             (size_t)n * elem_bytes, cudaMemcpyDeviceToHost, env->copy_stream);
-    };
-    CUDA_TRY(copy(host->obs_dist, dev->obs_dist, (size_t)nrays * 2));
-    CUDA_TRY(copy(host->obs_type, dev->obs_type, (size_t)nrays));
-    CUDA_TRY(copy(host->reward, dev->reward, (size_t)A * 4));
-    CUDA_TRY(copy(host->terminated, dev->terminated, 1));
-    CUDA_TRY(copy(host->truncated, dev->truncated, 1));
-    CUDA_TRY(copy(host->winner, dev->winner, 1));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(records_host) + (size_t)w0 * stride, static_cast<const char*>(records_dev) + (size_t)w0 * stride,
+                             (size_t)n * stride, cudaMemcpyDeviceToHost, env->copy_stream));
   }
   CUDA_TRY(cudaEventRecord(env->copies_done, env->copy_stream));
   CUDA_TRY(cudaStreamWaitEvent(stream, env->copies_done, 0));
@@ -453,6 +536,7 @@ static int state_view(CatEnv* env, void* state_dev, const CatStateView* view, in
   p.o_vel = k.o_vel; p.o_vb = k.o_vb; p.o_tc = k.o_tc; p.o_wkey = k.o_wkey; p.o_wjn = k.o_wjn;
   p.o_page = k.o_page; p.o_pjn = k.o_pjn; p.o_sc = k.o_sc; p.o_ep = k.o_ep; p.o_flags = k.o_flags;
   p.v = *view; p.set = set;
+  DEVICE_SCOPE(env);
   const int threads = 128, blocks = (k.n_worlds + threads - 1) / threads;
   cat_state_view_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   CUDA_TRY(cudaGetLastError());

@@ -10,9 +10,10 @@
 #endif
 constexpr int kWarpsPerCta = CAT_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxThreads = 1024;   // the host picks 2..32 warps per CTA per environment (pick_launch_shape); 64 registers either way
 constexpr int kMinCtasPerSm = CAT_MIN_CTAS_PER_SM;
 constexpr int kSlots = CAT_WALL_SLOTS;
-constexpr int kNear = 4;            // hulls an origin can be "inside" (alpha = 0 rule) per agent
+constexpr int kNear = CAT_NEAR_SLOTS;   // hulls an origin can be "inside" (alpha = 0 rule) per agent
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
 enum { TYPE_WALL = 0, TYPE_COP = 1, TYPE_THIEF = 2, TYPE_EMPTY = 4 };
@@ -60,6 +61,12 @@ struct KParams {
   int blob_bytes;
   const int32_t* view_off;      // global memory: per grid cell candidate-edge lists (nullptr = scan all edges)
   const uint16_t* view_edges;
+  // per (cell, ray) candidate lists (ray_lists.h): slots [cells * R] of 4 words + overflow words; nullptr = rasterise
+  const uint4* ray_slots;
+  const uint32_t* ray_ovf;
+  float rg_x0, rg_y0, rg_inv_cell;
+  int rg_nx, rg_ny;
+  unsigned long long* overflow;  // [2] wall-contact / near-hull slots exceeded (cat_env_overflow_counts)
   float* state;
   int rec_words;
   int n_worlds;
@@ -70,7 +77,9 @@ struct KParams {
   // record offsets (words)
   int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags, o_near;
   // per-warp scratch offsets (bytes) and size
-  int s_rdist, s_rtype, s_min, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, scratch_bytes;
+  int s_rdist, s_rtype, s_min, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, s_rcell, scratch_bytes;
+  // output record of one world, staged contiguously in shared memory at s_rdist (CatRecordLayout)
+  int r_bytes, r_off_reward, r_off_flags;
   int state_dim;
   // constants
   float dt, inv_dt, impulse, inv_mass, agent_r, max_speed, term_r, ray_len, ray_r, wall_r;
@@ -95,6 +104,11 @@ struct KParams {
   float* obs_f32;
   float* state_f32;
   float* hit_point;
+  unsigned char* record;          // record output: one r_bytes block per world, record_stride apart
+  int record_stride;
+  float* critic_f32;
+  uint16_t* obs_bf16;
+  uint16_t* critic_bf16;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -319,6 +333,9 @@ struct Warp {
   uint8_t* order;   // compact solver order
   unsigned long long* best;  // per ray: (float bits of s) << 32 | feature id  — the 1-D depth buffer
   uint16_t* cand;   // candidate edge ids awaiting rasterisation
+  float* rew;       // staged rewards [A] and flags {terminated, truncated, winner} of the world's output record
+  uint8_t* flg;
+  int32_t* rcell;   // per agent: first slot of its ray-list cell, -1 = outside the grid (no wall in reach)
   const unsigned char* blob;  // the map blob in shared memory
   int lane;
 };
@@ -421,23 +438,256 @@ __device__ __noinline__ void raster_batch(const unsigned char* blob, unsigned lo
   }
 }
 
+// Candidate generation + rasterisation of one agent's walls into its depth buffer — the any-map path (no
+// per-(cell, ray) lists: environments created with ray_list_cell < 0).  lanes = edges: candidates face the origin
+// (plane i or the next plane, which share vertex v_i and hence its bevel) and lie within sensor range.  Batches
+// of 32 edges (hulls are stored in Morton order, so a batch is compact) are visited NEAR TO FAR: lane b measures
+// the distance of batch b's bounding box once, a counting rank orders them, and the walk stops at the first batch
+// beyond sensor range; the per-grid-cell static lists (maps.view_lists) shorten the scan when present.
+__device__ __noinline__ void rasterise_agent(const KParams& k, const unsigned char* blob, unsigned char* scratch, int a,
+                                             float ox, float oy) {
+  // (scalars, not the Warp struct: a struct passed by reference to an out-of-line function would live in local memory)
+  const MapView m = make_view(blob);
+  struct { unsigned long long* best; uint16_t* cand; const unsigned char* blob; int lane; } w;
+  w.best = reinterpret_cast<unsigned long long*>(scratch + k.s_best);
+  w.cand = reinterpret_cast<uint16_t*>(scratch + k.s_cand);
+  w.blob = blob; w.lane = threadIdx.x & 31;
+  const int R = k.R, lane = w.lane, E = k.n_edges;
+  const float L = k.ray_len, rsum = k.wall_r + k.ray_r;
+  const float range2 = (L + rsum) * (L + rsum);
+  int ncand = 0;
+  const int nb = (E + 31) >> 5;
+  int vq = 0, vq1 = 0;
+  const int vcell = k.view_off ? grid_cell(m, ox, oy) : -1;
+  const bool use_view = vcell >= 0;
+  uint32_t vnext = 0xFFFFu;
+  if (use_view) {
+    vq = __ldg(k.view_off + vcell); vq1 = __ldg(k.view_off + vcell + 1);
+    if (vq + lane < vq1) vnext = __ldg(k.view_edges + vq + lane);
+  }
+  const bool ordered = !use_view && nb <= 32;
+  float bdist = CUDART_INF_F;
+  int brank = 0;
+  if (ordered) {
+    if (lane < nb) {
+      const float4 bb = m.batch_bb[lane];
+      const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
+      bdist = fmaf(ddx, ddx, ddy * ddy);
+    }
+#pragma unroll 1
+    for (int j = 0; j < nb; ++j) {
+      const float dj = __shfl_sync(0xFFFFFFFFu, bdist, j);
+      brank += (dj < bdist || (dj == bdist && j < lane)) ? 1 : 0;
+    }
+  }
+#pragma unroll 1
+  for (int it = 0; ; ++it) {
+    int e;
+    if (use_view) {
+      if (vq >= vq1) break;
+      e = vnext == 0xFFFFu ? E : (int)vnext;
+      vq += 32;
+      vnext = vq + lane < vq1 ? (uint32_t)__ldg(k.view_edges + vq + lane) : 0xFFFFu;
+    } else {
+      if (it >= nb) break;
+      int base;
+      if (ordered) {
+        const int b = __ffs(__ballot_sync(0xFFFFFFFFu, lane < nb && brank == it)) - 1;
+        if (__shfl_sync(0xFFFFFFFFu, bdist, b) >= range2) break;   // this and every later batch is out of range
+        base = b << 5;
+      } else {
+        base = it << 5;
+        const float4 bb = m.batch_bb[it];
+        const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
+        if (fmaf(ddx, ddx, ddy * ddy) >= range2) continue;
+      }
+      e = base + lane;
+    }
+    bool is_cand = false;
+    if (e < E) {
+      const float4 ed = m.edge[e];
+      const float2 nn = m.next_n[e];
+      const float rx = ox - ed.x, ry = oy - ed.y;
+      const float pd = rx * ed.z + ry * ed.w;
+      const float pdn = rx * nn.x + ry * nn.y;
+      const float len = m.edge_len[e];
+      const float qa = fmaf(ry, ed.z, -rx * ed.w);       // position of o along A->B, relative to B
+      const float dq = qa - fminf(fmaxf(qa, -len), 0.f);
+      is_cand = (pd > 0.f || pdn > 0.f) && (fmaf(pd, pd, dq * dq) < range2);
+    }
+    const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
+    if (is_cand) w.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)e;
+    ncand += __popc(cmask);
+    __syncwarp();
+    if (ncand >= 32) {
+      raster_batch(w.blob, w.best + a * R, w.cand, 32, ox, oy, rsum, L, R);
+      __syncwarp();
+      uint16_t t = 0;
+      if (lane + 32 < ncand) t = w.cand[lane + 32];
+      __syncwarp();
+      if (lane + 32 < ncand) w.cand[lane] = t;
+      ncand -= 32;
+      __syncwarp();
+    }
+  }
+  if (ncand > 0) raster_batch(w.blob, w.best + a * R, w.cand, ncand, ox, oy, rsum, L, R);
+  __syncwarp();
+}
+
+// Stage the (cell, ray) slots of every ray of the world into shared memory: one 16-byte cp.async per ray, no
+// registers held, issued as early as the positions are known so that the L2 / HBM latency hides behind the
+// termination test and the action impulses.  Slot r lands at w.best + 2 r (16-byte stride); the walk later writes
+// ray r's result key over the first half of its own slot.
+template <int TA, int TR>
+__device__ __forceinline__ void stage_ray_slots(const KParams& k, const Warp& w) {
+  const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane;
+  const float* pos = w.rec;
+  asm volatile("cp.async.wait_all;" ::: "memory");   // (a world that ends and re-spawns in one step stages twice)
+  if (lane < A) {
+    const float gx = (pos[2 * lane] - k.rg_x0) * k.rg_inv_cell, gy = (pos[2 * lane + 1] - k.rg_y0) * k.rg_inv_cell;
+    int base = -1;   // outside the grid: farther than the sensor reach from every wall
+    if (gx >= 0.f && gy >= 0.f && gx < (float)k.rg_nx && gy < (float)k.rg_ny) base = ((int)gy * k.rg_nx + (int)gx) * R;
+    w.rcell[lane] = base;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int a = 0; a < A; ++a) {
+    const int base = w.rcell[a];
+#pragma unroll 1
+    for (int i = lane; i < R; i += 32) {
+      uint4* dst = reinterpret_cast<uint4*>(w.best) + (a * R + i);
+      if (base >= 0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(k.ray_slots + base + i) : "memory");
+      else *dst = make_uint4(kRayEnd, kRayEnd, kRayEnd, kRayEnd);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Wall hits of EVERY ray of the world from the per-(cell, ray) candidate lists (ray_lists.h).
+//
+// lanes = rays, assigned dynamically: a lane walks its ray's list nearest bound first — one exact
+// cpPolyShapeSegmentQuery edge test per iteration — until the hit it holds is nearer than the next entry's lower
+// bound, then publishes the hit (over its own slot) and takes the next ray nobody has taken.  No candidate
+// generation, no angular spans, no scan / search, no atomics: the work per ray is the 1-3 edges its fat ray can
+// actually meet before its first hit.
+//   The BB-tree leaf rule (a hull counts only if the THIN ray enters its bounding box) is checked once, on the
+// winner; if it fails (a grazing fat ray) the list is walked again with the rule applied to every hit.
+//   Hit key = (float bits of s, feature): smaller s first, then smaller feature — the order of the rasteriser's
+// 64-bit atomicMin, so both paths pick the same hit bit for bit.
+template <int TA, int TR>
+__device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, const Warp& w) {
+  const int A = TA ? TA : k.A, R = TR ? TR : k.R, nrays = A * R, lane = w.lane;
+  const float L = k.ray_len, rsum = k.wall_r + k.ray_r, rs2 = rsum * rsum, inv_L = 1.f / k.ray_len;
+  const float inv_R = 1.f / (float)R;
+  const float* pos = w.rec;
+  uint4* slots = reinterpret_cast<uint4*>(w.best);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
+  const uint32_t kLbits = __float_as_uint(L);
+  const uint32_t lt = (1u << lane) - 1u;
+  int cur = lane < nrays ? lane : -1;
+  int next = 32;                       // warp-uniform: first ray nobody has taken yet
+  uint32_t e0 = kRayEnd, e1 = kRayEnd, e2 = kRayEnd, e3 = kRayEnd;
+  bool strict = false;
+  float ox = 0.f, oy = 0.f, ux = 0.f, uy = 0.f;
+  int ci = 0;
+  uint32_t bs = kLbits, bf = kNoFeature;   // the hit held: float bits of s, feature
+  auto start_ray = [&](int ray) {
+    int a = 0;
+    if (TA) {
+#pragma unroll
+      for (int j = 1; j < (TA ? TA : 1); ++j) a += ray >= j * R ? 1 : 0;
+    } else a = __float2int_rz(((float)ray + 0.5f) * inv_R);
+    ci = ray - a * R;
+    const float2 o = *reinterpret_cast<const float2*>(pos + 2 * a);
+    ox = o.x; oy = o.y;
+    const float2 dv = *reinterpret_cast<const float2*>(m.dir + ci);
+    ux = dv.x; uy = dv.y;
+    const uint4 sl = slots[ray];
+    e0 = sl.x; e1 = sl.y; e2 = sl.z; e3 = sl.w;
+    bs = kLbits; bf = kNoFeature;
+  };
+  if (cur >= 0) start_ray(cur);
+#pragma unroll 1
+  while (__any_sync(0xFFFFFFFFu, cur >= 0)) {
+    bool fin = false;
+    if (cur >= 0) {
+      uint32_t ent = e0;
+      if ((int)ent < 0) {              // link: the list continues in a chunk of the overflow array
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(k.ray_ovf + (ent & 0x7FFFFFFFu)));
+        ent = c.x; e1 = c.y; e2 = c.z; e3 = c.w;
+      }
+      e0 = e1; e1 = e2; e2 = e3; e3 = kRayEnd;
+      if (__uint_as_float(bs) < __uint_as_float(ent & 0xFFFF0000u)) fin = true;   // (an empty list: its first entry is the end mark)
+      else {
+        const uint32_t el = ent & 0xFFFFu;
+        Ray r;
+        r.ox = ox; r.oy = oy; r.ux = ux; r.uy = uy; r.L = L;
+        int kind;
+        const float sHit = ray_edge(m.edge[el], m.edge_len[el], r, rsum, rs2, kind);
+        CAT_COUNT(4, 1);
+        const uint32_t sb = __float_as_uint(sHit), feat = el * 2u + (uint32_t)kind;
+        if (sHit < L && (sb < bs || (sb == bs && feat < bf))) {
+          bool ok = true;
+          if (strict) {
+            const float4 dv = m.dir[ci];
+            ok = thin_bb_hit(m.hull_bb[m.edge_hull[el]], ox, oy, dv.x == 0.f, dv.y == 0.f, dv.z * inv_L, dv.w * inv_L);
+          }
+          if (ok) { bs = sb; bf = feat; }
+        }
+        // nothing nearer can follow once the hit held is closer than the next entry's lower bound (a link reads as negative)
+        fin = __uint_as_float(bs) < __uint_as_float(e0 & 0xFFFF0000u);
+      }
+    }
+#ifdef CAT_STATS
+    if (lane == 0) CAT_COUNT(5, 1);
+#endif
+    if (__any_sync(0xFFFFFFFFu, fin)) {
+      bool take = false;
+      if (fin) {
+        bool redo = false;
+        if (!strict && bf != kNoFeature) {   // cpBBTree leaf rule on the winner
+          const float4 dv = m.dir[ci];
+          redo = !thin_bb_hit(m.hull_bb[m.edge_hull[bf >> 1]], ox, oy, dv.x == 0.f, dv.y == 0.f, dv.z * inv_L, dv.w * inv_L);
+        }
+        if (redo) {                    // grazing fat ray: walk the list again, leaf rule on every hit
+          start_ray(cur);
+          strict = true;
+        } else {
+          *reinterpret_cast<uint2*>(slots + cur) = make_uint2(bf, bs);   // = make_key(s, feature)
+          strict = false;
+          take = true;
+        }
+      }
+      const uint32_t tmask = __ballot_sync(0xFFFFFFFFu, take);
+      if (take) {
+        cur = next + __popc(tmask & lt);
+        if (cur >= nrays) cur = -1;
+        else start_ray(cur);
+      }
+      next += __popc(tmask);
+    }
+  }
+  __syncwarp();
+}
+
 // Sensor sweep of every agent of one world (entity.py:159-220) into shared memory.
 //
-// 90 rays from one origin are a 1-D depth buffer, so the walls are RASTERISED into it instead of each
-// ray searching the map: per agent, (1) lanes = rays: seed the buffer with the other agents' circles and
-// the alpha = 0 rules; (2) lanes = edges: keep edges that face the origin and lie within range, then
-// expand them into (edge, ray) pairs spread evenly over the lanes (raster_batch) and resolve the nearest
-// hit per ray with a 64-bit shared-memory atomicMin; (3) lanes = rays: hit point, float16 chain, type.
-// Work is proportional to what is actually in view (~2 edge tests per ray on agh-map), lanes stay
-// converged, and there is no per-ray traversal.
-__device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
-  const int A = k.A, R = k.R, lane = w.lane, E = k.n_edges;
+// Wall hits first, into the per-ray buffer w.best (key = distance bits << 32 | feature): from the per-(cell, ray)
+// candidate lists (sweep_lists, lanes = rays) or, without lists, by rasterising the edges in view into a 1-D depth
+// buffer per agent (rasterise_agent, lanes = edges then (edge, ray) pairs).  Then, lanes = rays: the other agents'
+// circles and the alpha = 0 rules are merged in, and the hit point goes through the float16 chain.
+template <int TA, int TR>
+__device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world, bool staged) {
+  const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane;
+  const bool lists = k.ray_slots != nullptr;
+  if (lists && !staged) stage_ray_slots<TA, TR>(k, w);
   const float* pos = w.rec;
   const float* tc = w.rec + k.o_tc;
   const uint32_t flags = reinterpret_cast<const uint32_t*>(w.rec)[k.o_flags];
   const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len;
   const float reach = k.agent_r + k.ray_r, reach2 = reach * reach, inv_reach = 1.f / reach;
-  const float range2 = (L + rsum) * (L + rsum);
   // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates.  The list is
   // part of the state record: the physics step that moved the body already measured its distance to every hull
   // in contact reach and stored it; it is recomputed here only after a re-spawn / set_state (flag bit set).
@@ -455,7 +705,10 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
           if (px < bb.x - k.ray_r || px > bb.z + k.ray_r || py < bb.y - k.ray_r || py > bb.w + k.ray_r) continue;
           float d, nx, ny;
           hull_closest(m, h, px, py, d, nx, ny);
-          if (d - k.wall_r <= k.ray_r && cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
+          if (d - k.wall_r <= k.ray_r) {
+            if (cnt < kNear) w.near[lane * kNear + cnt++] = (uint16_t)h;
+            else atomicAdd(k.overflow + 1, 1ull);
+          }
         }
       }
     } else {
@@ -467,6 +720,9 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
   }
   __syncwarp();
   if (lane == 0 && flags) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0u;   // lists are now valid for these positions
+
+  if (lists) sweep_lists<TA, TR>(k, m, w);
+  const int kstride = lists ? 2 : 1;   // the list walk leaves ray r's key in the first half of its 16-byte slot
 
   const int nsub = (R + 31) >> 5;
 #pragma unroll 1
@@ -481,97 +737,14 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
       if (ddx * ddx + ddy * ddy <= reach2) zero_agent = j;
     }
 
-    // ---- (1) clear the depth buffer (the dynamic shapes and the alpha = 0 rules are merged in step 3)
+    if (!lists) {
+      // ---- (1) clear the depth buffer (the dynamic shapes and the alpha = 0 rules are merged in step 3)
 #pragma unroll 1
-    for (int i = lane; i < R; i += 32) w.best[a * R + i] = make_key(L, kNoFeature);
-    __syncwarp();
-
-    // ---- (2) lanes = edges: candidates face the origin (plane i or the next plane, which share vertex v_i
-    //          and hence its bevel) and lie within sensor range of the origin
-    //          Batches of 32 edges (hulls are stored in Morton order, so a batch is compact) are visited NEAR TO FAR:
-    //          lane b measures the distance of batch b's bounding box once, a counting rank orders them, and
-    //          the walk stops at the first batch beyond sensor range.  Near walls are then already in the depth
-    //          buffer when the far edges are set up, which lets the rasteriser drop occluded edges.
-    int ncand = 0;
-    const int nb = (E + 31) >> 5;
-    // Preferred source of edges: the static list of this origin's grid cell (the edges that can be candidates
-    // for SOME origin in the cell, nearest first; global memory / L2, next batch prefetched) — on agh-map ~150
-    // of 496 edges.  Origins outside the grid, or environments created without lists, scan the batches.
-    int vq = 0, vq1 = 0;
-    const int vcell = k.view_off ? grid_cell(m, ox, oy) : -1;
-    const bool use_view = vcell >= 0;
-    uint32_t vnext = 0xFFFFu;
-    if (use_view) {
-      vq = __ldg(k.view_off + vcell); vq1 = __ldg(k.view_off + vcell + 1);
-      if (vq + lane < vq1) vnext = __ldg(k.view_edges + vq + lane);
-    }
-    const bool ordered = !use_view && nb <= 32;
-    float bdist = CUDART_INF_F;
-    int brank = 0;
-    if (ordered) {
-      if (lane < nb) {
-        const float4 bb = m.batch_bb[lane];
-        const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
-        bdist = fmaf(ddx, ddx, ddy * ddy);
-      }
-#pragma unroll 1
-      for (int j = 0; j < nb; ++j) {
-        const float dj = __shfl_sync(0xFFFFFFFFu, bdist, j);
-        brank += (dj < bdist || (dj == bdist && j < lane)) ? 1 : 0;
-      }
-    }
-#pragma unroll 1
-    for (int it = 0; ; ++it) {
-      int e;
-      if (use_view) {
-        if (vq >= vq1) break;
-        e = vnext == 0xFFFFu ? E : (int)vnext;
-        vq += 32;
-        vnext = vq + lane < vq1 ? (uint32_t)__ldg(k.view_edges + vq + lane) : 0xFFFFu;
-      } else {
-        if (it >= nb) break;
-        int base;
-        if (ordered) {
-          const int b = __ffs(__ballot_sync(0xFFFFFFFFu, lane < nb && brank == it)) - 1;
-          if (__shfl_sync(0xFFFFFFFFu, bdist, b) >= range2) break;   // this and every later batch is out of range
-          base = b << 5;
-        } else {
-          base = it << 5;
-          const float4 bb = m.batch_bb[it];
-          const float ddx = fmaxf(fmaxf(bb.x - ox, ox - bb.z), 0.f), ddy = fmaxf(fmaxf(bb.y - oy, oy - bb.w), 0.f);
-          if (fmaf(ddx, ddx, ddy * ddy) >= range2) continue;
-        }
-        e = base + lane;
-      }
-      bool is_cand = false;
-      if (e < E) {
-        const float4 ed = m.edge[e];
-        const float2 nn = m.next_n[e];
-        const float rx = ox - ed.x, ry = oy - ed.y;
-        const float pd = rx * ed.z + ry * ed.w;
-        const float pdn = rx * nn.x + ry * nn.y;
-        const float len = m.edge_len[e];
-        const float qa = fmaf(ry, ed.z, -rx * ed.w);       // position of o along A->B, relative to B
-        const float dq = qa - fminf(fmaxf(qa, -len), 0.f);
-        is_cand = (pd > 0.f || pdn > 0.f) && (fmaf(pd, pd, dq * dq) < range2);
-      }
-      const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
-      if (is_cand) w.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)e;
-      ncand += __popc(cmask);
+      for (int i = lane; i < R; i += 32) w.best[a * R + i] = make_key(L, kNoFeature);
       __syncwarp();
-      if (ncand >= 32) {
-        raster_batch(w.blob, w.best + a * R, w.cand, 32, ox, oy, rsum, L, R);
-        __syncwarp();
-        uint16_t t = 0;
-        if (lane + 32 < ncand) t = w.cand[lane + 32];
-        __syncwarp();
-        if (lane + 32 < ncand) w.cand[lane] = t;
-        ncand -= 32;
-        __syncwarp();
-      }
+      // ---- (2) rasterise the walls in view
+      rasterise_agent(k, w.blob, reinterpret_cast<unsigned char*>(w.rec), a, ox, oy);
     }
-    if (ncand > 0) raster_batch(w.blob, w.best + a * R, w.cand, ncand, ox, oy, rsum, L, R);
-    __syncwarp();
 
     // the other agents' cached centres relative to this origin, compacted (the candidate queue is free now)
     float4* others = reinterpret_cast<float4*>(w.cand);
@@ -588,7 +761,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
       if (i < R) {
         const int r = a * R + i;
         const float4 dv = m.dir[i];
-        unsigned long long key = w.best[r];     // nearest wall hit from the rasteriser
+        unsigned long long key = w.best[r * kstride];     // nearest wall hit
         {
           Ray rq;
           rq.ox = ox; rq.oy = oy; rq.ux = dv.x; rq.uy = dv.y; rq.L = L;
@@ -656,19 +829,49 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
   __syncwarp();
 }
 
-// Optional fp32 layouts (what skrl's wrapper would build on the host): per-agent flattened observation
-// and the flattened centralised-critic state.  Only called when the caller asked for them; kept out of
-// line so the native-dtype fast path stays small.
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float v) {   // round to nearest even
+  const uint32_t u = __float_as_uint(v);
+  return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+
+// Optional learner-facing layouts (what skrl's wrapper would build on the host): per-agent flattened observation,
+// the flattened centralised-critic state, the critic's 4-channel ray block (lstm_value_net.py:122-137), and bf16
+// copies.  Only called when the caller asked for them; kept out of line so the native-dtype fast path stays small.
 __device__ __noinline__ void write_flat_layouts(const KParams& k, const uint16_t* rdist, const uint8_t* rtype,
                                                 const float* pos, long long world) {
   const int A = k.A, R = k.R, lane = threadIdx.x & 31;
-  if (k.obs_f32) {  // [A][N][2R]: [distance | object_type] as skrl flattens the Dict (keys sorted)
+  if (k.obs_f32 || k.obs_bf16) {  // [A][N][2R]: [distance | object_type] as skrl flattens the Dict (keys sorted)
 #pragma unroll 1
     for (int a = 0; a < A; ++a) {
-      float* dst = k.obs_f32 + ((size_t)a * k.n_worlds + world) * (2 * R);
+      const size_t o = ((size_t)a * k.n_worlds + world) * (2 * R);
 #pragma unroll 1
-      for (int i = lane; i < 2 * R; i += 32)
-        dst[i] = i < R ? __half2float(__ushort_as_half(rdist[a * R + i])) : (float)rtype[a * R + i - R];
+      for (int i = lane; i < 2 * R; i += 32) {
+        const float v = i < R ? __half2float(__ushort_as_half(rdist[a * R + i])) : (float)rtype[a * R + i - R];
+        if (k.obs_f32) k.obs_f32[o + i] = v;
+        if (k.obs_bf16) k.obs_bf16[o + i] = f32_to_bf16_bits(v);
+      }
+    }
+  }
+  if (k.critic_f32 || k.critic_bf16) {
+    // LSTMValue's channel stack, cut from the FIRST agent's block of env.state():
+    // [own_obj_types | own_distances | object_type_shared | distance_shared] of cop_0; shared = first non-EMPTY of the cops
+    const size_t o = (size_t)world * 4 * R;
+#pragma unroll 1
+    for (int i = lane; i < 4 * R; i += 32) {
+      const int ch = i / R, ri = i - ch * R;
+      float v;
+      if (ch == 0) v = (float)rtype[ri];
+      else if (ch == 1) v = __half2float(__ushort_as_half(rdist[ri]));
+      else {
+        uint8_t t = TYPE_EMPTY;
+        uint16_t d = 0;
+#pragma unroll 1
+        for (int b = 0; b < k.nc; ++b)
+          if (t == TYPE_EMPTY) { t = rtype[b * R + ri]; d = rdist[b * R + ri]; }
+        v = ch == 2 ? (float)t : __half2float(__ushort_as_half(d));
+      }
+      if (k.critic_f32) k.critic_f32[o + i] = v;
+      if (k.critic_bf16) k.critic_bf16[o + i] = f32_to_bf16_bits(v);
     }
   }
   if (k.state_f32) {
@@ -701,11 +904,20 @@ __device__ __noinline__ void write_flat_layouts(const KParams& k, const uint16_t
   }
 }
 
-// Write the observation-side outputs of one world from shared memory (coalesced).
-__device__ __forceinline__ void write_observation(const KParams& k, const Warp& w, long long world) {
-  const int A = k.A, R = k.R, lane = w.lane, nrays = k.nrays;
+// Write the outputs of one world from shared memory (coalesced).  `flags_too`: the staged rewards / flags belong
+// to this launch (a step); reset / observe launches leave the caller's reward / flag arrays alone, except in record
+// mode, where the whole record is one block (their staged values are then 0 / 0 / 0 / -1).
+template <int TA, int TR>
+__device__ __forceinline__ void write_observation(const KParams& k, const Warp& w, long long world, bool flags_too) {
+  const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane, nrays = A * R;
   const float* pos = w.rec;
-  if (k.obs_vec) {
+  if (k.record) {
+    // one record per world, staged contiguously: [f16 distance | u8 type | f32 reward | flags], 16-byte stores
+    uint4* dst = reinterpret_cast<uint4*>(k.record + (size_t)world * k.record_stride);
+    const uint4* src = reinterpret_cast<const uint4*>(w.rdist);
+#pragma unroll 1
+    for (int i = lane; i < (k.r_bytes >> 4); i += 32) dst[i] = src[i];
+  } else if (k.obs_vec) {
     // 16-byte aligned world blocks (mapped pinned host memory): one or two 512-byte warp stores per array
     if (k.obs_dist) {
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(k.obs_dist) + (size_t)world * k.dist_stride);
@@ -746,6 +958,14 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
       }
     }
   }
+  if (!k.record && flags_too) {
+    if (lane < A && k.reward) k.reward[(size_t)world * A + lane] = w.rew[lane];
+    if (lane == 0) {
+      if (k.terminated) k.terminated[world] = w.flg[0];
+      if (k.truncated) k.truncated[world] = w.flg[1];
+      if (k.winner) k.winner[world] = (int8_t)w.flg[2];
+    }
+  }
   if (k.team_pos) {  // observation_spaces.py:92-95
 #pragma unroll 1
     for (int i = lane; i < 2 * A; i += 32)
@@ -768,7 +988,7 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
       }
     }
   }
-  if (k.obs_f32 || k.state_f32) write_flat_layouts(k, w.rdist, w.rtype, pos, world);
+  if (k.obs_f32 || k.state_f32 || k.critic_f32 || k.obs_bf16 || k.critic_bf16) write_flat_layouts(k, w.rdist, w.rtype, pos, world);
 }
 
 // cop.py:49-75 / thief.py:48-69 in fp32 from the f16 distance.
@@ -783,8 +1003,9 @@ __device__ __forceinline__ float agent_reward(const KParams& k, int a, uint32_t 
 }
 
 // cpSpaceStep(dt) for one world, state in shared memory.
+template <int TA>
 __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m, const Warp& w) {
-  const int A = k.A, P = k.P, lane = w.lane;
+  const int A = TA ? TA : k.A, P = TA ? TA * (TA - 1) / 2 : k.P, lane = w.lane;
   float* pos = w.rec;
   float* vel = w.rec + k.o_vel;
   float* vb = w.rec + k.o_vb;
@@ -845,6 +1066,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
       if (isnear) {
         const uint32_t rank = w.nearcnt[a] + __popc(nears & same & ((1u << lane) - 1u));
         if (rank < (uint32_t)kNear) w.near[a * kNear + rank] = (uint16_t)h;
+        else atomicAdd(k.overflow + 1, 1ull);   // never silent: cat_env_overflow_counts
       }
       if (hit) {
         const uint32_t rank = w.ccount[a] + __popc(hits & same & ((1u << lane) - 1u));
@@ -852,7 +1074,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
           float* c = w.con + (a * kSlots + rank) * 8;
           c[0] = nx; c[1] = ny; c[2] = d;
           reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)h;
-        }
+        } else atomicAdd(k.overflow, 1ull);       // a contact beyond CAT_WALL_SLOTS: counted, the world diverges from the uncapped solver
       }
       __syncwarp();
       if (hit && (hits & same & ((1u << lane) - 1u)) == 0) w.ccount[a] += __popc(hits & same);   // first hit lane of each agent
@@ -1059,48 +1281,58 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
   float* tc = w.rec + k.o_tc;
   uint32_t* ep = reinterpret_cast<uint32_t*>(w.rec + k.o_ep);
   const uint32_t episode = *ep + 1u;
-  float nx_ = 0.f, ny_ = 0.f;
-  if (lane < A) {
-    const int r0 = m.reg_off[lane], nr = m.reg_off[lane + 1] - r0;
-    if (nr > 0) {
-      const unsigned long long gid = (unsigned long long)(k.gid0 + world);
-      const uint32_t idx = cat_spawn_region_index(k.seed, gid, episode, (uint32_t)lane, (uint32_t)nr);
-      const float4 reg = m.regions[r0 + (int)idx];
-      nx_ = reg.x + reg.z / 2.f; ny_ = reg.y + reg.w / 2.f;  // base_env.py:163-166 fallback
+  // With pymunk's stale shape cache (A.10) every candidate is tested against the centres the OTHER agents had
+  // before this reset, so the A spawns are independent and run on A lanes at once.  With the cache kept fresh
+  // (stale_shape_cache = 0) agent j must see the new positions of agents i < j (base_env.py:313-332 resets them
+  // in order): one round per agent, the accepted position published before the next round.
+  const int rounds = k.stale ? 1 : A;
 #pragma unroll 1
-      for (uint32_t t = 0; t < 20; ++t) {
-        float ux, uy;
-        cat_spawn_uniforms(k.seed, gid, episode, (uint32_t)lane, t, &ux, &uy);
-        const float px = fmaf(reg.z, ux, reg.x), py = fmaf(reg.w, uy, reg.y);
-        // point_query_nearest(pos, 5, ray_filter): any shape with distance < 5
-        bool blocked = false;
-        const int cell = grid_cell(m, px, py);
-        if (cell >= 0) {
+  for (int round = 0; round < rounds; ++round) {
+    float nx_ = 0.f, ny_ = 0.f;
+    const bool mine = lane < A && (k.stale || lane == round);
+    if (mine) {
+      const int r0 = m.reg_off[lane], nr = m.reg_off[lane + 1] - r0;
+      if (nr > 0) {
+        const unsigned long long gid = (unsigned long long)(k.gid0 + world);
+        const uint32_t idx = cat_spawn_region_index(k.seed, gid, episode, (uint32_t)lane, (uint32_t)nr);
+        const float4 reg = m.regions[r0 + (int)idx];
+        nx_ = reg.x + reg.z / 2.f; ny_ = reg.y + reg.w / 2.f;  // base_env.py:163-166 fallback
 #pragma unroll 1
-          for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && !blocked; ++q) {
-            float d, ax, ay;
-            hull_closest(m, m.con_list[q], px, py, d, ax, ay);
-            if (d - k.wall_r < k.agent_r) blocked = true;
+        for (uint32_t t = 0; t < 20; ++t) {
+          float ux, uy;
+          cat_spawn_uniforms(k.seed, gid, episode, (uint32_t)lane, t, &ux, &uy);
+          const float px = fmaf(reg.z, ux, reg.x), py = fmaf(reg.w, uy, reg.y);
+          // point_query_nearest(pos, 5, ray_filter): any shape with distance < 5
+          bool blocked = false;
+          const int cell = grid_cell(m, px, py);
+          if (cell >= 0) {
+#pragma unroll 1
+            for (int q = m.con_off[cell]; q < m.con_off[cell + 1] && !blocked; ++q) {
+              float d, ax, ay;
+              hull_closest(m, m.con_list[q], px, py, d, ax, ay);
+              if (d - k.wall_r < k.agent_r) blocked = true;
+            }
           }
-        }
 #pragma unroll 1
-        for (int j = 0; j < A && !blocked; ++j) {
-          if (j == lane) continue;
-          const float dx = px - tc[2 * j], dy = py - tc[2 * j + 1];
-          if (sqrtf(dx * dx + dy * dy) - k.agent_r < k.agent_r) blocked = true;
+          for (int j = 0; j < A && !blocked; ++j) {
+            if (j == lane) continue;
+            const float dx = px - tc[2 * j], dy = py - tc[2 * j + 1];
+            if (sqrtf(dx * dx + dy * dy) - k.agent_r < k.agent_r) blocked = true;
+          }
+          if (!blocked) { nx_ = px; ny_ = py; break; }
         }
-        if (!blocked) { nx_ = px; ny_ = py; break; }
+      } else {
+        const float2 ip = m.init_pos[lane];  // base_env.py:328-332 -> Entity.reset() default
+        nx_ = ip.x; ny_ = ip.y;
       }
-    } else {
-      const float2 ip = m.init_pos[lane];  // base_env.py:328-332 -> Entity.reset() default
-      nx_ = ip.x; ny_ = ip.y;
     }
-  }
-  __syncwarp();  // every lane has finished reading the stale centres
-  if (lane < A) {
-    pos[2 * lane] = nx_; pos[2 * lane + 1] = ny_;       // entity.py:154-156
-    vel[2 * lane] = 0.f; vel[2 * lane + 1] = 0.f;        // entity.py:157
-    if (!k.stale) { tc[2 * lane] = nx_; tc[2 * lane + 1] = ny_; }
+    __syncwarp();  // every lane has finished reading the centres of this round
+    if (mine) {
+      pos[2 * lane] = nx_; pos[2 * lane + 1] = ny_;       // entity.py:154-156
+      vel[2 * lane] = 0.f; vel[2 * lane + 1] = 0.f;        // entity.py:157
+      if (!k.stale) { tc[2 * lane] = nx_; tc[2 * lane + 1] = ny_; }
+    }
+    __syncwarp();
   }
   if (lane == 0) {
     *ep = episode;
@@ -1110,7 +1342,10 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(const __grid_constant__ KParams k) {
+// TA / TR: agents per world and rays per agent as compile-time constants (the 2 cops + 1 thief x 90 rays of every
+// shipped map: <3, 90>), or 0 = read them from the parameters (any other configuration: <0, 0>).
+template <int TA, int TR>
+__global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_constant__ KParams k) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1168,12 +1403,16 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
   w.order = reinterpret_cast<uint8_t*>(scratch + k.s_order);
   w.best = reinterpret_cast<unsigned long long*>(scratch + k.s_best);
   w.cand = reinterpret_cast<uint16_t*>(scratch + k.s_cand);
+  w.rew = reinterpret_cast<float*>(scratch + k.s_rdist + k.r_off_reward);
+  w.flg = reinterpret_cast<uint8_t*>(scratch + k.s_rdist + k.r_off_flags);
+  w.rcell = reinterpret_cast<int32_t*>(scratch + k.s_rcell);
   w.blob = smem;
   w.lane = lane;
 
-  // the staging tails beyond A*R rays are shipped by the 16-byte store path: keep them zero
-  for (int i = k.nrays + lane; i < k.nrays_pad; i += 32) { w.rdist[i] = 0; w.rtype[i] = 0; }
-  const int A = k.A;
+  // the padding of the staged output record is shipped by the 16-byte store paths: keep it zero
+  for (int i = lane; i < (k.r_bytes >> 2); i += 32) reinterpret_cast<uint32_t*>(w.rdist)[i] = 0u;
+  __syncwarp();
+  const int A = TA ? TA : k.A;
   const int wpc = blockDim.x >> 5;   // warps per CTA: chosen per environment by the host (pick_launch_shape)
   const long long stride = (long long)gridDim.x * wpc;
 #pragma unroll 1
@@ -1216,6 +1455,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
 
     bool do_step = k.mode == MODE_STEP, do_reset = k.mode == MODE_RESET;
     bool captured = false, timeout = false;
+    // the sensor sweep reads the PRE-step positions, which are known now: start fetching the rays' candidate slots
+    bool staged = false;
+    if (do_step && k.ray_slots) { stage_ray_slots<TA, TR>(k, w); staged = true; }
     if (do_step) {  // ---------------- base_env.py:354-383 ----------------
       const float* pos = w.rec;
       float* vel = w.rec + k.o_vel;
@@ -1260,28 +1502,31 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) cat_world_kernel(cons
     //   OBSERVE : observe -> write
 #pragma unroll 1
     for (;;) {
-      if (do_reset) { reset_world(k, m, w, world); do_reset = false; }
+      if (do_reset) { reset_world(k, m, w, world); do_reset = false; staged = false; }
       // entity.py:143 — observation of the pre-physics state.  A world that ends on this step and
       // is re-spawned in it emits the NEW episode's observation (C-10) and a terminal reward that does not depend
       // on what is seen, so its terminal sensor sweep would be thrown away: skip it.  With one world per warp the
       // launch lasts as long as its slowest warp, and a second sweep made every finishing world that warp.
-      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world(k, m, w, world);
+      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world<TA, TR>(k, m, w, world, staged);
       bool again = false;
       if (do_step) {
-        if (lane < A && k.reward)
-          k.reward[(size_t)world * A + lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
+        if (lane < A) w.rew[lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
         const bool done = captured || timeout;
         if (lane == 0) {
-          if (k.terminated) k.terminated[world] = done ? 1 : 0;  // entity.py:146
-          if (k.truncated) k.truncated[world] = timeout ? 1 : 0;   // base_env.py:397
-          if (k.winner) k.winner[world] = done ? (captured ? 0 : 1) : -1;
+          w.flg[0] = done ? 1 : 0;                                      // terminated, entity.py:146
+          w.flg[1] = timeout ? 1 : 0;                                   // truncated, base_env.py:397
+          w.flg[2] = (uint8_t)(done ? (captured ? 0 : 1) : -1);         // winner
         }
         again = done && k.auto_reset;  // emit the observation of the re-spawned state instead
+      } else if (k.mode != MODE_STEP) {
+        if (lane < A) w.rew[lane] = 0.f;
+        if (lane == 0) { w.flg[0] = 0; w.flg[1] = 0; w.flg[2] = 0xFF; }
       }
-      if (!again) write_observation(k, w, world);
+      __syncwarp();
+      if (!again) write_observation<TA, TR>(k, w, world, k.mode == MODE_STEP);
       __syncwarp();
       if (do_step) {
-        physics_world(k, m, w);  // base_env.py:392
+        physics_world<TA>(k, m, w);  // base_env.py:392
         do_step = false;
         if (again) { do_reset = true; continue; }
       }

@@ -158,8 +158,10 @@ class BaseEnv(_EnvCommon):
     # ------------------------------------------------------------------ PettingZoo API
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):  # base_env.py:286-352
         if seed is not None:
+            # base_env.py:307-311 re-creates np_random, so reset(seed=s) reproduces the same spawn every time:
+            # re-key Philox AND restart the episode counter that is part of its key
             self._np_random_seed = seed
-            self._w.set_seed(seed)
+            self._w.set_seed(seed, restart_episodes=True)
         self.agents = self.possible_agents[:]
         self._w.reset()
         self._w.synchronize()
@@ -285,7 +287,7 @@ class BatchedCopsThievesEnv(_EnvCommon):
 
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
         if seed is not None:
-            self._w.set_seed(seed)
+            self._w.set_seed(seed, restart_episodes=True)
         self._w.reset()
         return self._obs_dict(), {a: {} for a in self.possible_agents}
 

@@ -341,6 +341,113 @@ def view_lists(vert: np.ndarray, normal: np.ndarray, hull_off: np.ndarray, gx0: 
     return off, flat
 
 
+def _clip_interval(p0: np.ndarray, dp: np.ndarray, lo: np.ndarray, hi: np.ndarray):
+    """Parameter interval of ``p0 + lam * dp`` (lam in R) inside the slab [lo, hi]; empty slabs give lo > hi."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a, b = (lo - p0) / dp, (hi - p0) / dp
+    l0, l1 = np.minimum(a, b), np.maximum(a, b)
+    par = dp == 0.0
+    inside = (p0 >= lo) & (p0 <= hi)
+    l0 = np.where(par, np.where(inside, -np.inf, np.inf), l0)
+    l1 = np.where(par, np.where(inside, np.inf, -np.inf), l1)
+    return l0, l1
+
+
+RAY_LIST_LB_SCALE = 64.0     # the lower bounds stored with the list entries are in 1/64 units, rounded down
+
+
+def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, eps: float = 1e-2
+              ) -> Tuple[np.ndarray, np.ndarray]:
+    """Per (grid cell, ray index): the edges ray ``i`` cast from ANY origin inside the cell can touch, nearest first.
+
+    The sensor's rays have fixed directions (``entity.py:182``), so for one direction the fat rays of every origin in
+    a cell sweep the cell translated along that direction — in the ray's own frame (t along, w across) a region inside
+    the rectangle ``[t0, t1 + L] x [w0, w1]`` of the cell's projections.  An edge (its plane offset by ``rsum`` and the
+    bevel circle of radius ``rsum`` at its end vertex) can only be hit if its segment comes within ``rsum`` of that
+    region, if the ray runs against its normal or the next edge's (the bevel's exposed arc spans the two), and if some
+    point of the cell lies in front of one of those two planes.  Each entry carries a lower bound of the hit distance
+    (quantised downwards): entries are sorted by it and the kernel stops walking a list as soon as the nearest hit it
+    holds is closer than the next bound.  The list is a conservative superset and every listed edge still gets the
+    exact ``cpPolyShapeSegmentQuery`` arithmetic, so results do not depend on it.
+
+    Returns ``(off int32 [ncell * R + 1], ent uint32)`` with ``ent = (lb_q << 16) | edge``.
+    """
+    E, R, L = cmap.n_edges, int(n_rays), float(ray_length)
+    assert E < 65536
+    rs = rsum + eps
+    vert, normal = cmap.vert, cmap.normal
+    prev = np.zeros(E, np.int64)
+    nxt = np.zeros(E, np.int64)
+    for h in range(cmap.n_hulls):
+        o, e = int(cmap.hull_off[h]), int(cmap.hull_off[h + 1])
+        idx = np.arange(o, e)
+        prev[o:e] = np.roll(idx, 1)
+        nxt[o:e] = np.roll(idx, -1)
+    A, B, n, nn = vert[prev], vert, normal, normal[nxt]
+    nx, ny, cell = cmap.nx, cmap.ny, cmap.cell
+    ncell = nx * ny
+    cxs, cys = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    cl = (cmap.grid_x0 + cxs.ravel() * cell - 0.05)[:, None]      # the kernel bins the origin in fp32: grow a little
+    cb = (cmap.grid_y0 + cys.ravel() * cell - 0.05)[:, None]
+    cr, ct = cl + cell + 0.1, cb + cell + 0.1
+    corners = [(cl, cb), (cr, cb), (cr, ct), (cl, ct)]
+    # ---- per (cell, edge), direction independent
+    pd = np.full((ncell, E), -np.inf)
+    pdn = np.full((ncell, E), -np.inf)
+    for x, y in corners:
+        pd = np.maximum(pd, (x - B[None, :, 0]) * n[None, :, 0] + (y - B[None, :, 1]) * n[None, :, 1])
+        pdn = np.maximum(pdn, (x - B[None, :, 0]) * nn[None, :, 0] + (y - B[None, :, 1]) * nn[None, :, 1])
+    in_front = (pd > -eps) | (pdn > -eps)
+    # Euclidean distance cell rectangle <-> segment AB (0 if they intersect)
+    AB = B - A
+    L2 = np.maximum((AB ** 2).sum(1), 1e-300)
+
+    def to_rect(P):
+        dx = np.maximum(np.maximum(cl - P[None, :, 0], P[None, :, 0] - cr), 0.0)
+        dy = np.maximum(np.maximum(cb - P[None, :, 1], P[None, :, 1] - ct), 0.0)
+        return np.hypot(dx, dy)
+    dist = np.minimum(to_rect(A), to_rect(B))
+    for x, y in corners:
+        tt = np.clip(((x - A[None, :, 0]) * AB[None, :, 0] + (y - A[None, :, 1]) * AB[None, :, 1]) / L2[None, :], 0.0, 1.0)
+        dist = np.minimum(dist, np.hypot(x - (A[None, :, 0] + AB[None, :, 0] * tt), y - (A[None, :, 1] + AB[None, :, 1] * tt)))
+    x0, x1 = _clip_interval(A[None, :, 0], AB[None, :, 0], cl, cr)
+    y0, y1 = _clip_interval(A[None, :, 1], AB[None, :, 1], cb, ct)
+    crosses = np.maximum(np.maximum(x0, y0), 0.0) <= np.minimum(np.minimum(x1, y1), 1.0)
+    dist = np.where(crosses, 0.0, dist)
+    lb_euclid = dist - rs
+
+    cells_all, rays_all, lbs_all, edges_all = [], [], [], []
+    for i in range(R):
+        th = i * (2.0 * math.pi / R)
+        ux, uy = math.cos(th), math.sin(th)
+        runs_against = ((ux * n[:, 0] + uy * n[:, 1]) < 1e-4) | ((ux * nn[:, 0] + uy * nn[:, 1]) < 1e-4)      # [E]
+        tA, wA = A[:, 0] * ux + A[:, 1] * uy, -A[:, 0] * uy + A[:, 1] * ux
+        tB, wB = B[:, 0] * ux + B[:, 1] * uy, -B[:, 0] * uy + B[:, 1] * ux
+        tc = np.stack([x * ux + y * uy for x, y in corners])       # [4, ncell, 1]
+        wc = np.stack([-x * uy + y * ux for x, y in corners])
+        t0, t1, w0, w1 = tc.min(0), tc.max(0), wc.min(0), wc.max(0)
+        a0, a1 = _clip_interval(tA[None, :], (tB - tA)[None, :], t0 - rs, t1 + L + rs)
+        b0, b1 = _clip_interval(wA[None, :], (wB - wA)[None, :], w0 - rs, w1 + rs)
+        l0, l1 = np.maximum(np.maximum(a0, b0), 0.0), np.minimum(np.minimum(a1, b1), 1.0)
+        hit = (l0 <= l1) & in_front & runs_against[None, :]
+        tmin = np.minimum(tA[None, :] + l0 * (tB - tA)[None, :], tA[None, :] + l1 * (tB - tA)[None, :])
+        lb = np.maximum(np.maximum(tmin - rs - t1, lb_euclid), 0.0)
+        hit &= lb < L
+        c_idx, e_idx = np.nonzero(hit)
+        cells_all.append(c_idx.astype(np.int64))
+        rays_all.append(np.full(len(c_idx), i, np.int64))
+        lbs_all.append(np.clip(np.floor(lb[c_idx, e_idx] * RAY_LIST_LB_SCALE) - 1.0, 0, 65535).astype(np.int64))
+        edges_all.append(e_idx.astype(np.int64))
+    cells_all, rays_all = np.concatenate(cells_all), np.concatenate(rays_all)
+    lbs_all, edges_all = np.concatenate(lbs_all), np.concatenate(edges_all)
+    key = cells_all * R + rays_all
+    order = np.lexsort((edges_all, lbs_all, key))
+    ent = ((lbs_all[order] << 16) | edges_all[order]).astype(np.uint32)
+    off = np.zeros(ncell * R + 1, np.int64)
+    np.cumsum(np.bincount(key, minlength=ncell * R), out=off[1:])
+    return off.astype(np.int32), ent
+
+
 def compile_map(m: Map, *, cell: Optional[float] = None,
                 contact_reach: float = 6.0, slack: float = 0.05, name: Optional[str] = None,
                 spawn_override: Optional[Dict[str, List[dict]]] = None, view_range: float = 402.0) -> CompiledMap:

@@ -33,6 +33,7 @@ class EnvParams:
     stale_shape_cache: int = 1             # pymunk behaviour, SURVEY.md A.10 / C-4
     auto_reset: int = 1                    # batched env: re-spawn inside the step
     seed: int = 0
+    ray_list_cell: float = 0.0             # sensor-sweep candidate lists: cell size (0 = automatic, < 0 = rasterise instead)
 
     def as_dict(self) -> dict:
         return asdict(self)

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CatEnvInfo, CatMapDesc, CatParams, CatStateView, CatStepIO, CAT_WALL_SLOTS
+from ._lib import CatEnvInfo, CatMapDesc, CatParams, CatRecordLayout, CatStateView, CatStepIO, CAT_WALL_SLOTS
 from .maps import CompiledMap
 from .params import EnvParams
 
@@ -31,10 +31,13 @@ def _require_cuda(device: torch.device) -> None:
 class CatWorlds:
     def __init__(self, cmap: CompiledMap, n_worlds: int, *, device: Union[str, torch.device] = "cuda:0",
                  gid0: int = 0, params: Optional[EnvParams] = None, want_f32: bool = True,
-                 want_shared: bool = True, want_hits: bool = False, pinned_outputs: bool = False, **overrides):
+                 want_shared: bool = True, want_hits: bool = False, pinned_outputs: bool = False,
+                 want_critic: bool = False, want_bf16: bool = False, **overrides):
         """``pinned_outputs=True`` places every output tensor in mapped pinned HOST memory: the kernel stores its
         results there directly and the host reads them (``tensor.numpy()``) after one stream synchronisation —
-        the layout for callers that consume every step on the CPU, like the single-world PettingZoo face."""
+        the layout for callers that consume every step on the CPU, like the single-world PettingZoo face.
+        ``want_critic``: also emit the critic's 4-channel ray block ``critic_f32 (N, 4, R)``
+        (``lstm_value_net.py:122-137``); ``want_bf16``: bf16 copies of ``obs_f32`` / ``critic_f32``."""
         self.device = torch.device(device)
         _require_cuda(self.device)
         self.L = _lib.load()
@@ -83,31 +86,24 @@ class CatWorlds:
         N, A, R, dev = self.n_worlds, self.A, self.R, self.device
         nbytes = int(self.L.cat_env_state_bytes(self._h))
         self.state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)   # packed per-world records
-        # The per-step results live in ONE device buffer so the host-facing path needs a single D2H copy.
-        def carve(nbytes_, off=[0]):
-            o = off[0]
-            off[0] = (o + nbytes_ + 255) // 256 * 256
-            return o
-        sizes = dict(obs_dist=N * A * R * 2, obs_type=N * A * R, reward=N * A * 4, terminated=N, truncated=N, winner=N)
-        offs = {k_: carve(v) for k_, v in sizes.items()}
-        total = carve(0)
+        # The per-step results are ONE record per world (include/cat_b200.h CatRecordLayout):
+        #   [f16 distance A*R | u8 type A*R | f32 reward A | u8 terminated | u8 truncated | i8 winner], 16-byte aligned,
+        # written by the kernel with 16-byte stores; the tensors below are strided views of the record buffer, so the
+        # host-facing path moves any range of worlds with a single copy.
+        rl = CatRecordLayout()
+        _lib.check(self.L.cat_env_record_layout(self._h, C.byref(rl)), "cat_env_record_layout")
+        self.record_layout = rl
+        self.record_bytes = int(rl.bytes)
         self.pinned_outputs = bool(pinned_outputs)
 
         def alloc(shape, dtype):
             if self.pinned_outputs:
                 return torch.zeros(shape, dtype=dtype).pin_memory()
             return torch.zeros(shape, dtype=dtype, device=dev)
-        self._out = alloc(total, torch.uint8)
-
-        def view(name, dtype, shape):
-            return self._out[offs[name]:offs[name] + sizes[name]].view(dtype).view(shape)
-        self._out_layout = (offs, sizes, total)
-        self.obs_dist = view("obs_dist", torch.float16, (N, A, R))
-        self.obs_type = view("obs_type", torch.uint8, (N, A, R))
-        self.reward = view("reward", torch.float32, (N, A))
-        self.terminated = view("terminated", torch.uint8, (N,))
-        self.truncated = view("truncated", torch.uint8, (N,))
-        self.winner = view("winner", torch.int8, (N,))
+        self._out = alloc(N * self.record_bytes, torch.uint8)
+        views = self._record_views(self._out)
+        self.obs_dist, self.obs_type, self.reward = views["obs_dist"], views["obs_type"], views["reward"]
+        self.terminated, self.truncated, self.winner = views["terminated"], views["truncated"], views["winner"]
         self.winner.fill_(-1)
         self.shared_dist = alloc((N, 2, R), torch.float16) if want_shared else None
         self.shared_type = alloc((N, 2, R), torch.uint8) if want_shared else None
@@ -115,6 +111,9 @@ class CatWorlds:
         self.obs_f32 = alloc((A, N, 2 * R), torch.float32) if want_f32 else None
         self.state_f32 = alloc((N, self.S), torch.float32) if want_f32 else None
         self.hit_point = alloc((N, A, R, 2), torch.float32) if want_hits else None
+        self.critic_f32 = alloc((N, 4, R), torch.float32) if want_critic else None
+        self.obs_bf16 = alloc((A, N, 2 * R), torch.bfloat16) if want_bf16 and want_f32 else None
+        self.critic_bf16 = alloc((N, 4, R), torch.bfloat16) if want_bf16 and want_critic else None
         self._host = None
         self._io = self._make_io()
         self._ptr_table = (C.c_void_p * 8)()
@@ -124,12 +123,32 @@ class CatWorlds:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _make_io(self) -> CatStepIO:
+    def _record_views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Strided tensor views of a record buffer (``N * record_bytes`` uint8, device or pinned host)."""
+        N, A, R, rl, rb = self.n_worlds, self.A, self.R, self.record_layout, self.record_bytes
+        f16, f32 = buf.view(torch.float16), buf.view(torch.float32)
+        return dict(
+            obs_dist=f16.as_strided((N, A, R), (rb // 2, R, 1), rl.off_dist // 2),
+            obs_type=buf.as_strided((N, A, R), (rb, R, 1), rl.off_type),
+            reward=f32.as_strided((N, A), (rb // 4, 1), rl.off_reward // 4),
+            terminated=buf.as_strided((N,), (rb,), rl.off_terminated),
+            truncated=buf.as_strided((N,), (rb,), rl.off_truncated),
+            winner=buf.view(torch.int8).as_strided((N,), (rb,), rl.off_winner))
+
+    def _make_io(self, record: Optional[torch.Tensor] = None, extras: bool = True) -> CatStepIO:
         def dp(t):
-            return None if t is None else t.data_ptr()
-        return CatStepIO(None, 0, None, dp(self.obs_dist), dp(self.obs_type), dp(self.reward), dp(self.terminated),
-                         dp(self.truncated), dp(self.winner), dp(self.shared_dist), dp(self.shared_type),
-                         dp(self.team_pos), dp(self.obs_f32), dp(self.state_f32), dp(self.hit_point), 0, 0)
+            return None if t is None or not extras else t.data_ptr()
+        rec = self._out if record is None else record
+        return CatStepIO(None, 0, None, None, None, None, None, None, None, dp(self.shared_dist), dp(self.shared_type),
+                         dp(self.team_pos), dp(self.obs_f32), dp(self.state_f32), dp(self.hit_point), 0, 0,
+                         rec.data_ptr(), self.record_bytes, dp(self.critic_f32), dp(self.obs_bf16), dp(self.critic_bf16))
+
+    def overflow_counts(self, reset: bool = False):
+        """(wall contacts beyond CAT_WALL_SLOTS, near hulls beyond CAT_NEAR_SLOTS) since creation / the last reset
+        of the counters — the fixed capacities the reference does not have; zero means they never mattered."""
+        out = (C.c_uint64 * 2)()
+        _lib.check(self.L.cat_env_overflow_counts(self._h, C.byref(out), int(reset)), "cat_env_overflow_counts")
+        return int(out[0]), int(out[1])
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -142,9 +161,14 @@ class CatWorlds:
         except Exception:
             pass
 
-    def set_seed(self, seed: int) -> None:
+    def set_seed(self, seed: int, restart_episodes: bool = False) -> None:
+        """Re-key the spawn RNG.  ``restart_episodes`` also zeroes the per-world episode counters (part of the RNG
+        key), so that ``reset(seed=s)`` reproduces the same spawns every time, like re-creating the reference's
+        ``np_random`` (``base_env.py:307-311``)."""
         _lib.check(self.L.cat_env_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), "cat_env_set_seed")
         self.params["seed"] = int(seed)
+        if restart_episodes:
+            self.set_state(episode=torch.zeros(self.n_worlds, dtype=torch.int32))
 
     # ------------------------------------------------------------------ the three launches
     def reset(self, mask: Optional[torch.Tensor] = None) -> None:
@@ -186,125 +210,73 @@ class CatWorlds:
 
     @property
     def d2h_bytes_per_step(self) -> int:
-        """Bytes of results that cross to the host per ``step_host`` (observations, rewards, flags)."""
-        return self.n_worlds * (self.A * self.R * 3 + self.A * 4 + 3)
+        """Bytes that cross to the host per ``step_host``: one output record per world (observations, rewards,
+        flags and the record's alignment padding — 832 B of which 825 are payload for 3 agents x 90 rays)."""
+        return self.n_worlds * self.record_bytes
 
-    def _host_buffers(self, zero_copy: bool) -> Dict[str, torch.Tensor]:
-        key = "zc" if zero_copy else "staged"
+    def _host_buffers(self) -> Dict[str, torch.Tensor]:
+        """Pinned host record buffer (same layout as the device one), its strided views, and the I/O table that
+        points the kernel straight at it (pinned memory is mapped into the device's address space)."""
         if self._host is None:
-            self._host = {}
-        if key in self._host:
-            return self._host[key]
-        N, A, R = self.n_worlds, self.A, self.R
-        if not zero_copy:
-            offs, sizes, total = self._out_layout
-            hb = torch.zeros(total, dtype=torch.uint8).pin_memory()
-
-            def hview(name, dtype, shape):
-                return hb[offs[name]:offs[name] + sizes[name]].view(dtype).view(shape)
+            N, A = self.n_worlds, self.A
+            hb = torch.zeros(N * self.record_bytes, dtype=torch.uint8).pin_memory()
             h = dict(blob=hb, actions_dev=torch.zeros((N, A), dtype=torch.uint8, device=self.device),
-                     actions_pinned=torch.zeros((N, A), dtype=torch.uint8).pin_memory(),
-                     obs_dist=hview("obs_dist", torch.float16, (N, A, R)),
-                     obs_type=hview("obs_type", torch.uint8, (N, A, R)),
-                     reward=hview("reward", torch.float32, (N, A)),
-                     terminated=hview("terminated", torch.uint8, (N,)),
-                     truncated=hview("truncated", torch.uint8, (N,)),
-                     winner=hview("winner", torch.int8, (N,)))
-            h["io"] = CatStepIO(None, 0, None, h["obs_dist"].data_ptr(), h["obs_type"].data_ptr(), h["reward"].data_ptr(),
-                                h["terminated"].data_ptr(), h["truncated"].data_ptr(), h["winner"].data_ptr(),
-                                None, None, None, None, None, None, 0, 0)
-            h["dev_io"] = CatStepIO(None, 0, None, self.obs_dist.data_ptr(), self.obs_type.data_ptr(), self.reward.data_ptr(),
-                                    self.terminated.data_ptr(), self.truncated.data_ptr(), self.winner.data_ptr(),
-                                    None, None, None, None, None, None, 0, 0)
-        else:
-            # Pinned host memory is mapped into the device's address space (unified virtual addressing), so the
-            # kernel can read the actions from it and store its results straight into it.  Each world's
-            # observation block starts on a 16-byte boundary (world stride rounded up), so the kernel ships it
-            # with 512-byte warp stores, which the PCIe root port sees as full-size writes; the (N, A, R)
-            # tensors handed back are strided views of that buffer.
-            layout = getattr(self, "_zc_layout", "record128")
-            d16, t16 = (A * R * 2 + 15) // 16 * 16, (A * R + 15) // 16 * 16
-            if layout.startswith("record"):
-                # one record per world: [distance f16 | type u8 | pad], record size a multiple of 128 B
-                al = int(layout[6:] or 128)
-                ds = ts = (d16 + t16 + al - 1) // al * al
-                sizes = dict(obs=N * ds, reward=N * A * 4, terminated=N, truncated=N, winner=N)
-            else:                                        # "split<align>": two arrays, world stride rounded up
-                al = int(layout[5:] or 16)
-                ds, ts = (d16 + al - 1) // al * al, (t16 + al - 1) // al * al
-                sizes = dict(obs_dist=N * ds, obs_type=N * ts, reward=N * A * 4, terminated=N, truncated=N, winner=N)
-            offs, total = {}, 0
-            for name, nb in sizes.items():
-                offs[name] = total
-                total = (total + nb + 255) // 256 * 256
-            hb = torch.zeros(total, dtype=torch.uint8).pin_memory()
-
-            def flat(name, dtype, skip=0):
-                return hb[offs[name] + skip:offs[name] + sizes[name]].view(dtype)
-            if layout.startswith("record"):
-                od = hb[offs["obs"]:offs["obs"] + sizes["obs"]].view(torch.float16).as_strided((N, A, R), (ds // 2, R, 1))
-                ot = hb[offs["obs"]:offs["obs"] + sizes["obs"]].as_strided((N, A, R), (ts, R, 1), d16)
-            else:
-                od = flat("obs_dist", torch.float16).as_strided((N, A, R), (ds // 2, R, 1))
-                ot = flat("obs_type", torch.uint8).as_strided((N, A, R), (ts, R, 1))
-            h = dict(blob=hb, actions_pinned=torch.zeros((N, A), dtype=torch.uint8).pin_memory(),
-                     obs_dist=od, obs_type=ot,
-                     reward=flat("reward", torch.float32).view(N, A),
-                     terminated=flat("terminated", torch.uint8), truncated=flat("truncated", torch.uint8),
-                     winner=flat("winner", torch.int8))
-            h["io"] = CatStepIO(None, 0, None, h["obs_dist"].data_ptr(), h["obs_type"].data_ptr(), h["reward"].data_ptr(),
-                                h["terminated"].data_ptr(), h["truncated"].data_ptr(), h["winner"].data_ptr(),
-                                None, None, None, None, None, None, ds, ts)
-        self._host[key] = h
-        return h
+                     actions_pinned=torch.zeros((N, A), dtype=torch.uint8).pin_memory(), **self._record_views(hb))
+            h["io"] = self._make_io(record=hb, extras=False)
+            if self.pinned_outputs:
+                raise _lib.CatError("step_host needs device-resident outputs (pinned_outputs=False)")
+            self._host = h
+        return self._host
 
     def default_chunks(self) -> int:
-        """Chunks for the pipelined host path.  Every chunk costs six small DMA copies (~8 us each), so chunking
-        only pays once a chunk's kernel is long; measured on B200 (gpurun_out/zc_layouts2.log): never below 8192
-        worlds, 2 chunks at 16384 agh-map worlds."""
-        return 2 if self.n_worlds >= 16384 else 1
+        """Chunks for the pipelined host path: each chunk is one launch + one DMA copy of its records, the copy of
+        chunk i overlapping the launch of chunk i + 1 (measured on B200, profiles/r2_notes.md)."""
+        return 4 if self.n_worlds >= 2048 else 1
 
-    def step_host(self, host_actions: torch.Tensor, mode: str = "zero_copy", chunks: Optional[int] = None,
-                  zero_copy: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+    def step_host(self, host_actions: torch.Tensor, mode: str = "pipelined", chunks: Optional[int] = None
+                  ) -> Dict[str, torch.Tensor]:
         """``step`` for a caller whose buffers live in host memory (the reference's own calling convention):
         uint8 actions ``(N, A)`` in, and the step's observations, rewards and flags in pinned host memory
-        when the call returns.  Three ways to move the results, same bytes, same values:
+        when the call returns (strided views of one record buffer).  Three ways to move the results, same bytes,
+        same values:
 
-        * ``"zero_copy"`` (default, fastest measured: 116 us for 4096 squarinth worlds, 435 us for 16384 agh-map
-          worlds) — one launch whose 16-byte stores go straight into mapped pinned host memory, so the
-          transfer of one world's results overlaps the computation of the others; SM-issued PCIe writes
-          sustain ~30 GB/s.
-        * ``"pipelined"`` — ``cat_env_step_host``: the worlds are stepped in ``chunks`` launches and each chunk's
-          results are DMA-copied (~50 GB/s, but ~8 us fixed cost per copy, six arrays per chunk) on a second
-          stream while the next chunk computes; the kernel reads the actions straight from the pinned buffer
-          (143 us / 506 us on the same two workloads).
-        * ``"staged"`` — H2D copy, one launch, one D2H copy of the output blob, strictly in sequence
-          (135 us / 544 us).
+        * ``"pipelined"`` (default) — ``cat_env_step_host``: the worlds are stepped in ``chunks`` launches; each
+          chunk's block of records is DMA-copied with ONE ``cudaMemcpyAsync`` on a second stream while the next
+          chunk computes; the kernel reads the actions straight from the pinned buffer.
+        * ``"zero_copy"`` — one launch whose 16-byte stores go straight into mapped pinned host memory, so the
+          transfer of one world's results overlaps the computation of the others (SM-issued PCIe writes).
+        * ``"staged"`` — H2D copy, one launch, one D2H copy of the record buffer, strictly in sequence.
         """
-        if zero_copy is not None:                       # older spelling
-            mode = "zero_copy" if zero_copy else "staged"
         if mode not in ("pipelined", "zero_copy", "staged"):
             raise ValueError(f"unknown step_host mode {mode!r}")
-        h = self._host_buffers(mode == "zero_copy")
+        h = self._host_buffers()
         if mode != "staged":
             if not host_actions.is_pinned():
                 h["actions_pinned"].copy_(host_actions)
                 host_actions = h["actions_pinned"]
             if host_actions.dtype != torch.uint8 or not host_actions.is_contiguous() or host_actions.numel() != self.n_worlds * self.A:
                 raise ValueError("host actions must be a contiguous uint8 (N, A) tensor")
-            io = h["io"]
-            io.actions, io.actions_kind = host_actions.data_ptr(), 0
             if mode == "zero_copy":
+                io = h["io"]
+                io.actions, io.actions_kind = host_actions.data_ptr(), 0
                 _lib.check(self.L.cat_env_step(self._h, self.state.data_ptr(), C.byref(io), self._stream()), "cat_env_step")
             else:
-                _lib.check(self.L.cat_env_step_host(self._h, self.state.data_ptr(), C.byref(h["dev_io"]), C.byref(io),
+                _lib.check(self.L.cat_env_step_host(self._h, self.state.data_ptr(), host_actions.data_ptr(),
+                                                    self._out.data_ptr(), h["blob"].data_ptr(), self.record_bytes,
                                                     int(chunks or self.default_chunks()), self._stream()), "cat_env_step_host")
         else:
             h["actions_dev"].copy_(host_actions, non_blocking=True)
-            self.step(h["actions_dev"])
+            io = self._io_bare()
+            io.actions, io.actions_kind = h["actions_dev"].data_ptr(), 0
+            _lib.check(self.L.cat_env_step(self._h, self.state.data_ptr(), C.byref(io), self._stream()), "cat_env_step")
             h["blob"].copy_(self._out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return h
+
+    def _io_bare(self) -> CatStepIO:
+        if getattr(self, "_io_bare_cached", None) is None:
+            self._io_bare_cached = self._make_io(extras=False)
+        return self._io_bare_cached
 
     def synchronize(self) -> None:
         """Wait for the launches enqueued so far (needed before reading ``pinned_outputs`` tensors on the host)."""

@@ -39,10 +39,12 @@
 extern "C" {
 #endif
 
-#define CAT_ABI_VERSION 3
+#define CAT_ABI_VERSION 4
 #define CAT_MAX_AGENTS 8
 #define CAT_MAX_RAYS 128
-#define CAT_WALL_SLOTS 4 /* cached wall arbiters kept per agent */
+#define CAT_WALL_SLOTS 4 /* cached wall arbiters / simultaneous wall contacts kept per agent; a 5th is counted by
+                            cat_env_overflow_counts, never dropped silently */
+#define CAT_NEAR_SLOTS 4 /* hulls whose reach can contain a ray origin (alpha = 0 rule) kept per agent; same rule */
 
 typedef enum {
   CAT_OK = 0,
@@ -91,6 +93,12 @@ typedef struct {
   int32_t stale_shape_cache; /* 1 = pymunk behaviour: reset leaves the query centres of the shapes stale */
   int32_t auto_reset;        /* 1 = done worlds are re-spawned inside the step and emit the reset observation */
   uint64_t seed;
+  /* Sensor-sweep acceleration (never changes a result, tests/test_parity_gpu.py::test_candidate_lists_do_not_change_results):
+   * the library builds, per cell of a uniform grid over the walls' reach and per ray index, the list of edges that
+   * ray can touch from any origin in the cell, nearest first.  ray_list_cell = edge length of those cells in map
+   * units; 0 = choose automatically (about 8192 cells, not below 12 units); < 0 = no lists: every sweep rasterises
+   * the map's edges into the per-agent depth buffer (the slower, any-map path). */
+  double ray_list_cell;
 } CatParams;
 
 typedef struct {
@@ -114,11 +122,34 @@ typedef struct {
   float* hit_point;
   /* bytes between consecutive worlds in obs_dist / obs_type; 0 = dense (A*R*2 and A*R).  A stride that is a
    * multiple of 16 (with a 16-byte aligned base) lets the kernel store each world's observation with 16-byte
-   * vector stores (the world's block is then written up to the next multiple of 16 bytes, padding included):
-   * the layout CatWorlds.step_host uses for mapped pinned host memory, where wide stores make wide PCIe writes. */
+   * vector stores (the world's block is then written up to the next multiple of 16 bytes, padding included). */
   int32_t obs_dist_world_stride;
   int32_t obs_type_world_stride;
+  /* RECORD OUTPUT (preferred): one contiguous record per world, CatRecordLayout below —
+   *   [ f16 distance A*R | pad to 16 | u8 type A*R | pad to 4 | f32 reward A | u8 terminated | u8 truncated | i8 winner | pad to 16 ]
+   * written with 16-byte stores (device memory or mapped pinned host memory).  When `record` is non-NULL the six
+   * pointers obs_dist, obs_type, reward, terminated, truncated, winner above are ignored: one world = one block,
+   * so a host-facing caller moves a range of worlds with ONE copy.  record must be 16-byte aligned and
+   * record_world_stride a multiple of 16 that is >= CatRecordLayout.bytes (0 = exactly that). */
+  void* record;
+  int32_t record_world_stride;
+  /* critic front end (lstm_value_net.py:122-137): the 4 ray channels LSTMValue cuts from the first agent's block of
+   * env.state(), in the order it stacks them — [own_obj_types | own_distances | object_type_shared | distance_shared]
+   * of cop_0 — f32 [N][4][R] */
+  float* critic_f32;
+  /* bf16 copies of obs_f32 ([A][N][2R]) and critic_f32 ([N][4][R]) for mixed-precision learners (optional) */
+  uint16_t* obs_bf16;
+  uint16_t* critic_bf16;
 } CatStepIO;
+
+/* byte offsets inside one world's output record (cat_env_record_layout) */
+typedef struct {
+  int32_t bytes;        /* record size = default world stride (multiple of 16) */
+  int32_t off_dist;     /* f16 [A][R] */
+  int32_t off_type;     /* u8  [A][R] */
+  int32_t off_reward;   /* f32 [A] */
+  int32_t off_terminated, off_truncated, off_winner; /* u8, u8, i8 */
+} CatRecordLayout;
 
 typedef struct {
   int32_t n_worlds, n_agents, n_cops, n_thieves, n_rays, n_hulls, n_edges;
@@ -129,6 +160,10 @@ typedef struct {
   int32_t warps_per_cta;
   int32_t grid;               /* CTAs launched by cat_env_step */
   int32_t n_pairs;
+  int32_t ray_list_cells;     /* cells of the (cell, ray) candidate-list grid, 0 = lists disabled */
+  int32_t ray_list_nx, ray_list_ny;
+  float ray_list_cell;
+  int64_t ray_list_bytes;     /* device bytes held by the lists (slots + overflow) */
 } CatEnvInfo;
 
 /* SoA view of the world state for get/set (device pointers; any may be NULL = skip). */
@@ -157,6 +192,12 @@ int cat_env_create(const CatMapDesc* map, const CatParams* params, int32_t n_wor
                    int32_t device, CatEnv** out);
 int cat_env_destroy(CatEnv* env);
 int cat_env_info(const CatEnv* env, CatEnvInfo* info);
+int cat_env_record_layout(const CatEnv* env, CatRecordLayout* layout);
+/* Fixed-capacity bookkeeping that the reference (Chipmunk) does not have: out[0] = wall contacts beyond
+ * CAT_WALL_SLOTS per agent, out[1] = near hulls beyond CAT_NEAR_SLOTS per agent, summed over every launch since
+ * creation (or since the last call with reset != 0).  Synchronises the device.  Zero means no world ever diverged
+ * from the uncapped algorithm for this reason. */
+int cat_env_overflow_counts(CatEnv* env, uint64_t out[2], int32_t reset);
 /* reset(seed=...) (base_env.py:307-311): re-key the spawn RNG of this environment */
 int cat_env_set_seed(CatEnv* env, uint64_t seed);
 /* bytes of the caller-owned packed state buffer (`state_dev` below) */
@@ -169,13 +210,13 @@ int cat_env_reset(CatEnv* env, void* state_dev, const CatStepIO* io, void* strea
 /* BaseEnv.step (base_env.py:354-413) for every world, one launch */
 int cat_env_step(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);
 /* BaseEnv.step for a caller whose buffers live in pinned HOST memory (the reference's own calling convention:
- * numpy in, numpy out), pipelined: the worlds are stepped in n_chunks consecutive launches on `stream`, and
- * each chunk's slice of obs_dist / obs_type / reward / terminated / truncated / winner is copied from the
- * dense device arrays in `dev` to the dense pinned host arrays in `host` on an internal copy stream while the
- * next chunk computes.  host->actions: u8 [N][A] in pinned host memory (actions_kind 0), read by the kernel
+ * numpy in, numpy out), pipelined: the worlds are stepped in n_chunks consecutive launches on `stream` that write
+ * record output (CatRecordLayout, stride record_world_stride) into `records_dev`; as soon as a chunk's launch has
+ * finished its block of records is moved to `records_host` (pinned) with ONE cudaMemcpyAsync on an internal copy
+ * stream while the next chunk computes.  host_actions: u8 [N][A] in pinned host memory, read by the kernel
  * directly.  `stream` waits for the copies: one cudaStreamSynchronize(stream) makes every result visible. */
-int cat_env_step_host(CatEnv* env, void* state_dev, const CatStepIO* dev, const CatStepIO* host, int32_t n_chunks,
-                      void* stream);
+int cat_env_step_host(CatEnv* env, void* state_dev, const uint8_t* host_actions, void* records_dev,
+                      void* records_host, int32_t record_world_stride, int32_t n_chunks, void* stream);
 /* Entity.get_observation + get_shared_observations of the current state (entity.py:159-220,
  * observation_spaces.py:67-131) without stepping */
 int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);

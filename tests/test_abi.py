@@ -48,8 +48,9 @@ def test_struct_layouts_match_what_a_c_compiler_sees(tmp_path):
 #include <stddef.h>
 #include "cat_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu\n", sizeof(CatMapDesc), sizeof(CatParams), sizeof(CatStepIO), sizeof(CatEnvInfo), sizeof(CatStateView));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(CatMapDesc), sizeof(CatParams), sizeof(CatStepIO), sizeof(CatEnvInfo), sizeof(CatStateView), sizeof(CatRecordLayout));
   printf("%zu %zu %zu %zu\n", offsetof(CatMapDesc, grid_x0), offsetof(CatParams, seed), offsetof(CatStepIO, obs_dist), offsetof(CatStateView, pair_jn));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(CatParams, ray_list_cell), offsetof(CatStepIO, record), offsetof(CatStepIO, critic_bf16), offsetof(CatEnvInfo, ray_list_bytes), offsetof(CatRecordLayout, off_winner));
   return 0;
 }""")
     exe = tmp_path / "probe"
@@ -57,8 +58,10 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     got = [int(x) for x in out]
     want = [C.sizeof(_lib.CatMapDesc), C.sizeof(_lib.CatParams), C.sizeof(_lib.CatStepIO), C.sizeof(_lib.CatEnvInfo),
-            C.sizeof(_lib.CatStateView), _lib.CatMapDesc.grid_x0.offset, _lib.CatParams.seed.offset,
-            _lib.CatStepIO.obs_dist.offset, _lib.CatStateView.pair_jn.offset]
+            C.sizeof(_lib.CatStateView), C.sizeof(_lib.CatRecordLayout), _lib.CatMapDesc.grid_x0.offset, _lib.CatParams.seed.offset,
+            _lib.CatStepIO.obs_dist.offset, _lib.CatStateView.pair_jn.offset, _lib.CatParams.ray_list_cell.offset,
+            _lib.CatStepIO.record.offset, _lib.CatStepIO.critic_bf16.offset, _lib.CatEnvInfo.ray_list_bytes.offset,
+            _lib.CatRecordLayout.off_winner.offset]
     assert got == want
 
 
@@ -96,6 +99,9 @@ def test_argument_validation_returns_error_codes_not_crashes():
     assert L.cat_gae(None, None, None, None, None, None, None, 4, 4, 0.99, 0.95, None) == -1
     assert L.cat_env_destroy(None) == 0
     assert L.cat_env_state_bytes(None) == 0
+    assert L.cat_env_record_layout(None, None) == -1
+    assert L.cat_env_overflow_counts(None, None, 0) == -1
+    assert L.cat_env_step_host(None, None, None, None, None, 0, 1, None) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

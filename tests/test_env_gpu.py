@@ -157,7 +157,7 @@ def test_host_buffer_step_modes_are_equivalent(cuda_device):
                "staged": envs["staged"].step_host(a.pin_memory(), mode="staged")}
         ref = envs["staged"]
         for k in ("obs_dist", "obs_type", "reward", "terminated", "truncated", "winner"):
-            want = getattr(ref, k).cpu().view(torch.uint8)
+            want = getattr(ref, k).cpu().contiguous().view(torch.uint8)
             for m, h in out.items():
                 assert h[k].shape == getattr(ref, k).shape
                 assert torch.equal(h[k].contiguous().view(torch.uint8), want), (i, k, m)

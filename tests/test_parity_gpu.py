@@ -194,16 +194,21 @@ def test_ragged_configuration_parity(cuda_device, tmp_path, n_rays, dt):
     cw.close()
 
 
-@pytest.mark.parametrize("name,free", [("agh-map", True), ("labyrinth", True), ("squarinth", False)])
-def test_view_lists_do_not_change_results(cuda_device, name, free):
-    """The per-cell candidate lists only shorten the edge scan: stepping with them, without them (every edge
-    scanned) and with lists built for a too-short range (ignored by the library) must agree bit for bit."""
+@pytest.mark.parametrize("name,free", [("agh-map", True), ("agh-map", False), ("labyrinth", True), ("squarinth", False)])
+def test_candidate_lists_do_not_change_results(cuda_device, name, free):
+    """The candidate lists only shorten the search for the first hit.  Stepping with the per-(cell, ray) lists the
+    library builds (automatic cell size, and two other cell sizes), without them (edges rasterised, with the
+    per-cell view lists, without any list, and with view lists built for a too-short range, which the library
+    ignores) must agree bit for bit — state records and every output."""
     import dataclasses
     cmap = pu.named_cmap(name, free_spawn=free)
     bare = dataclasses.replace(cmap, view_cell_off=np.zeros(0, np.int32), view_cell_edges=np.zeros(0, np.int32))
     short = dataclasses.replace(cmap, view_range=100.0)
     N = 1024
-    ws = [CatWorlds(c, N, device=cuda_device, seed=9, want_hits=True) for c in (cmap, bare, short)]
+    variants = [(cmap, {}), (cmap, dict(ray_list_cell=37.0)), (cmap, dict(ray_list_cell=90.0)),
+                (cmap, dict(ray_list_cell=-1.0)), (bare, dict(ray_list_cell=-1.0)), (short, dict(ray_list_cell=-1.0))]
+    ws = [CatWorlds(c, N, device=cuda_device, seed=9, want_hits=True, **kw) for c, kw in variants]
+    assert ws[0].info.ray_list_cells > 0 and ws[3].info.ray_list_cells == 0
     g = torch.Generator().manual_seed(2)
     for w in ws:
         w.reset()
@@ -214,10 +219,41 @@ def test_view_lists_do_not_change_results(cuda_device, name, free):
     torch.cuda.synchronize()
     for w in ws[1:]:
         assert torch.equal(w.state, ws[0].state)
-        for k in ("obs_dist", "obs_type", "reward", "terminated", "winner", "hit_point", "state_f32"):
+        assert torch.equal(w._out, ws[0]._out)
+        for k in ("hit_point", "state_f32", "obs_f32"):
             assert torch.equal(getattr(w, k).view(torch.uint8), getattr(ws[0], k).view(torch.uint8)), k
     for w in ws:
         w.close()
+
+
+def test_specialised_and_generic_kernels_agree(cuda_device, monkeypatch):
+    """cat_world_kernel<3, 90> (agents / rays as compile-time constants: every shipped map) and
+    cat_world_kernel<0, 0> (any shape) are the same algorithm: bit-identical state and outputs."""
+    cmap = pu.named_cmap("agh-map", free_spawn=True)
+    N = 1024
+    fast = CatWorlds(cmap, N, device=cuda_device, seed=4, want_hits=True, want_critic=True, want_bf16=True)
+    monkeypatch.setenv("CAT_GENERIC_KERNEL", "1")
+    slow = CatWorlds(cmap, N, device=cuda_device, seed=4, want_hits=True, want_critic=True, want_bf16=True)
+    monkeypatch.delenv("CAT_GENERIC_KERNEL")
+    g = torch.Generator().manual_seed(8)
+    for w in (fast, slow):
+        w.reset()
+    for _ in range(150):
+        a = torch.randint(0, 4, (N, 3), dtype=torch.uint8, generator=g).to(cuda_device)
+        fast.step(a)
+        slow.step(a)
+    torch.cuda.synchronize()
+    assert torch.equal(fast.state, slow.state) and torch.equal(fast._out, slow._out)
+    for k in ("hit_point", "state_f32", "obs_f32", "critic_f32", "obs_bf16", "critic_bf16", "shared_dist", "team_pos"):
+        assert torch.equal(getattr(fast, k).view(torch.uint8), getattr(slow, k).view(torch.uint8)), k
+    # the critic block is the first agent's block of env.state(), re-ordered (lstm_value_net.py:124-137)
+    R = fast.R
+    st = fast.state_f32
+    want = torch.stack([st[:, 3 * R:4 * R], st[:, 2 * R:3 * R], st[:, R:2 * R], st[:, :R]], dim=1)
+    assert torch.equal(fast.critic_f32, want)
+    assert torch.equal(fast.obs_bf16, fast.obs_f32.to(torch.bfloat16)) and torch.equal(fast.critic_bf16, want.to(torch.bfloat16))
+    fast.close()
+    slow.close()
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])

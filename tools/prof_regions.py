@@ -67,6 +67,12 @@ marks = [("hull_closest", find("__device__ __noinline__ float3 hull_closest_impl
          ("make_ray/los", find("__device__ __forceinline__ Ray make_ray")),
          ("grid_cell", find("__device__ __forceinline__ int grid_cell")),
          ("raster_batch", find("__device__ __noinline__ void raster_batch")), ("raster:pairs", find("for (int p0 = 0; p0 < total; p0 += 32)")), ("observe:near", ob),
+         ("rasterise_agent", find("__device__ __noinline__ void rasterise_agent")),
+         ("stage_ray_slots", find("__device__ __forceinline__ void stage_ray_slots")),
+         ("sweep_lists", find("__device__ __noinline__ void sweep_lists")),
+         ("sweep:walk", find("while (__any_sync(0xFFFFFFFFu, cur >= 0))")),
+         ("sweep:finish", find("if (__any_sync(0xFFFFFFFFu, fin))")),
+         ("write_flat", find("__device__ __noinline__ void write_flat_layouts")),
          ("observe:agent-uniform", find("// ---- warp-uniform, per agent", ob)), ("observe:clear", find("// ---- (1) clear the depth buffer", ob)), ("observe:candidates", find("// ---- (2) lanes = edges", ob)), ("observe:epilogue3", find("// ---- (3) lanes = rays", ob)),
          ("observe:rayinit", find("for (int sub = 0; sub < nsub; ++sub)", ob)),
          ("observe:gridsetup", find("// ---- uniform-grid walk set-up", ob)),

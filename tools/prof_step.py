@@ -19,10 +19,11 @@ ap.add_argument("--steps", type=int, default=60)
 ap.add_argument("--free", type=int, default=0)
 ap.add_argument("--cell", type=float, default=None)
 ap.add_argument("--flush", default="none", choices=["none", "read", "write"])
+ap.add_argument("--ray-cell", type=float, default=0.0, help="ray_list_cell: 0 auto, < 0 rasterise")
 a = ap.parse_args()
 kw = {} if a.cell is None else {"cell": a.cell}
 cmap = pu.named_cmap(a.map, free_spawn=bool(a.free), **kw)
-cw = CatWorlds(cmap, a.worlds, want_f32=False, want_shared=False)
+cw = CatWorlds(cmap, a.worlds, want_f32=False, want_shared=False, ray_list_cell=a.ray_cell)
 cw.reset()
 acts = [torch.randint(0, 4, (a.worlds, cw.A), dtype=torch.uint8, device="cuda") for _ in range(8)]
 for i in range(a.steps):
@@ -48,4 +49,5 @@ else:
     ts = sorted(x.elapsed_time(y) for x, y in ev)
     ms = sum(ts) / len(ts)
     print(f"flush={a.flush}: min {ts[0]*1e3:.1f} median {ts[25]*1e3:.1f} max {ts[-1]*1e3:.1f} us")
+print(f"ray lists: {cw.info.ray_list_nx}x{cw.info.ray_list_ny} cells of {cw.info.ray_list_cell:.1f}, {cw.info.ray_list_bytes/1e6:.1f} MB; overflow counts {cw.overflow_counts()}")
 print(f"{a.map} N={a.worlds} cell={cmap.cell:.1f}: {ms*1e3:.1f} us/step {a.worlds*cw.A/ms*1e3:.3e} agent-steps/s grid {cw.info.grid} x {cw.info.warps_per_cta} warps")

@@ -34,5 +34,6 @@ for mp, free, N in (("squarinth", False, 4096), ("labyrinth", True, 4096), ("agh
     L.cat_debug_stats(buf, 1)
     sweeps = N * 3 * K
     print(f"{mp}: per agent sweep: candidates {buf[0]/sweeps:.1f}, pairs {buf[1]/sweeps:.1f}, narrow (<=3 rays) {buf[2]/sweeps:.1f}, "
-          f"occlusion-culled {buf[3]/sweeps:.1f}")
+          f"occlusion-culled {buf[3]/sweeps:.1f}; list walk: {buf[4]/sweeps:.1f} edge tests per sweep ({buf[4]/sweeps/cw.R:.2f} per ray), "
+          f"{buf[5]/(N*K):.1f} warp iterations per world-step, lane efficiency {buf[4]/max(buf[5],1)/32:.2f}")
     cw.close()
