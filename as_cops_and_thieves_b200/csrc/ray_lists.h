@@ -78,7 +78,9 @@ static void build_ray_lists(const CatMapDesc* map, int R, double L, double rsum,
     br = std::max(br, map->hull_bb[4 * h + 2]); bt = std::max(bt, map->hull_bb[4 * h + 3]);
   }
   const double gx0 = bl - reach, gy0 = bb - reach, gw = br - bl + 2 * reach, gh = bt - bb + 2 * reach;
-  if (!(cell > 0.0)) cell = std::max(12.0, sqrt(gw * gh / 8192.0));
+  // automatic: about 16k cells (narrower strips = shorter lists = fewer edge tests per ray; measured on agh-map x 16384:
+  // 308 / 248 / 208 / 198 / 187 us per step at 48 / 32 / 19 / 16 / 12 units), not below 12 units
+  if (!(cell > 0.0)) cell = std::max(12.0, sqrt(gw * gh / 16384.0));
   const int nx = std::max(1, (int)ceil(gw / cell)), ny = std::max(1, (int)ceil(gh / cell));
   out->g.x0 = (float)gx0; out->g.y0 = (float)gy0; out->g.cell = (float)cell; out->g.inv_cell = (float)(1.0 / cell);
   out->g.nx = nx; out->g.ny = ny;

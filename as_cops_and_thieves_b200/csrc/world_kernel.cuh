@@ -335,7 +335,7 @@ struct Warp {
   uint16_t* cand;   // candidate edge ids awaiting rasterisation
   float* rew;       // staged rewards [A] and flags {terminated, truncated, winner} of the world's output record
   uint8_t* flg;
-  int32_t* rcell;   // per agent: first slot of its ray-list cell, -1 = outside the grid (no wall in reach)
+  unsigned long long* mbar;   // the warp's own mbarrier: completion of the staged ray slots
   const unsigned char* blob;  // the map blob in shared memory
   int lane;
 };
@@ -534,34 +534,61 @@ __device__ __noinline__ void rasterise_agent(const KParams& k, const unsigned ch
   __syncwarp();
 }
 
-// Stage the (cell, ray) slots of every ray of the world into shared memory: one 16-byte cp.async per ray, no
-// registers held, issued as early as the positions are known so that the L2 / HBM latency hides behind the
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+// Per-warp state of the slot staging: which phase of the warp's mbarrier the next wait is for, and whether a
+// staging is in flight (a world that ends and re-spawns in one step stages twice before it sweeps once).
+struct SlotStage { uint32_t phase; bool pending; };
+
+// Stage the (cell, ray) slots of every ray of the world into shared memory.  The R slots of one agent are
+// contiguous in global memory (slot index = cell * R + ray), so each agent is ONE TMA bulk copy (cp.async.bulk,
+// 16 R bytes) issued by lane 0 and completing on the warp's own mbarrier — no registers, no per-ray address
+// arithmetic — started as early as the positions are known so that the L2 / HBM latency hides behind the
 // termination test and the action impulses.  Slot r lands at w.best + 2 r (16-byte stride); the walk later writes
 // ray r's result key over the first half of its own slot.
 template <int TA, int TR>
-__device__ __forceinline__ void stage_ray_slots(const KParams& k, const Warp& w) {
+__device__ __forceinline__ void stage_ray_slots(const KParams& k, const Warp& w, SlotStage& st) {
   const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane;
   const float* pos = w.rec;
-  asm volatile("cp.async.wait_all;" ::: "memory");   // (a world that ends and re-spawns in one step stages twice)
+  const uint32_t bar = smem_u32(w.mbar);
+  if (st.pending) { mbar_wait(bar, st.phase); st.phase ^= 1u; }
+  int base = -1;   // outside the grid: farther than the sensor reach from every wall
   if (lane < A) {
     const float gx = (pos[2 * lane] - k.rg_x0) * k.rg_inv_cell, gy = (pos[2 * lane + 1] - k.rg_y0) * k.rg_inv_cell;
-    int base = -1;   // outside the grid: farther than the sensor reach from every wall
     if (gx >= 0.f && gy >= 0.f && gx < (float)k.rg_nx && gy < (float)k.rg_ny) base = ((int)gy * k.rg_nx + (int)gx) * R;
-    w.rcell[lane] = base;
   }
-  __syncwarp();
+  const uint32_t inside = __ballot_sync(0xFFFFFFFFu, base >= 0);   // (also orders the previous world's reads of the slot area)
+  if (lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of the area before the async-proxy writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(__popc(inside) * R * 16) : "memory");
+  }
 #pragma unroll 1
   for (int a = 0; a < A; ++a) {
-    const int base = w.rcell[a];
+    const int ba = __shfl_sync(0xFFFFFFFFu, base, a);
+    uint4* dst = reinterpret_cast<uint4*>(w.best) + a * R;
+    if (ba >= 0) {
+      if (lane == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                     "l"(k.ray_slots + ba), "r"(R * 16), "r"(bar)
+                     : "memory");
+    } else {
 #pragma unroll 1
-    for (int i = lane; i < R; i += 32) {
-      uint4* dst = reinterpret_cast<uint4*>(w.best) + (a * R + i);
-      if (base >= 0)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(k.ray_slots + base + i) : "memory");
-      else *dst = make_uint4(kRayEnd, kRayEnd, kRayEnd, kRayEnd);
+      for (int i = lane; i < R; i += 32) dst[i] = make_uint4(kRayEnd, kRayEnd, kRayEnd, kRayEnd);
     }
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  st.pending = true;
 }
 
 // Wall hits of EVERY ray of the world from the per-(cell, ray) candidate lists (ray_lists.h).
@@ -576,13 +603,14 @@ __device__ __forceinline__ void stage_ray_slots(const KParams& k, const Warp& w)
 //   Hit key = (float bits of s, feature): smaller s first, then smaller feature — the order of the rasteriser's
 // 64-bit atomicMin, so both paths pick the same hit bit for bit.
 template <int TA, int TR>
-__device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, const Warp& w) {
+__device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, const Warp& w, SlotStage& st) {
   const int A = TA ? TA : k.A, R = TR ? TR : k.R, nrays = A * R, lane = w.lane;
   const float L = k.ray_len, rsum = k.wall_r + k.ray_r, rs2 = rsum * rsum, inv_L = 1.f / k.ray_len;
   const float inv_R = 1.f / (float)R;
   const float* pos = w.rec;
   uint4* slots = reinterpret_cast<uint4*>(w.best);
-  asm volatile("cp.async.wait_all;" ::: "memory");
+  mbar_wait(smem_u32(w.mbar), st.phase);   // the staged slots have landed
+  st.phase ^= 1u; st.pending = false;
   __syncwarp();
   const uint32_t kLbits = __float_as_uint(L);
   const uint32_t lt = (1u << lane) - 1u;
@@ -606,6 +634,8 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
     ux = dv.x; uy = dv.y;
     const uint4 sl = slots[ray];
     e0 = sl.x; e1 = sl.y; e2 = sl.z; e3 = sl.w;
+    // a list longer than the slot continues in the overflow array: start pulling that chunk towards L1 now
+    if ((int)e3 < 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(k.ray_ovf + (e3 & 0x7FFFFFFFu)));
     bs = kLbits; bf = kNoFeature;
   };
   if (cur >= 0) start_ray(cur);
@@ -614,7 +644,7 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
     bool fin = false;
     if (cur >= 0) {
       uint32_t ent = e0;
-      if ((int)ent < 0) {              // link: the list continues in a chunk of the overflow array
+      if (__builtin_expect((int)ent < 0, 0)) {   // link: the list continues in a chunk of the overflow array
         const uint4 c = __ldg(reinterpret_cast<const uint4*>(k.ray_ovf + (ent & 0x7FFFFFFFu)));
         ent = c.x; e1 = c.y; e2 = c.z; e3 = c.w;
       }
@@ -648,8 +678,14 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
       if (fin) {
         bool redo = false;
         if (!strict && bf != kNoFeature) {   // cpBBTree leaf rule on the winner
-          const float4 dv = m.dir[ci];
-          redo = !thin_bb_hit(m.hull_bb[m.edge_hull[bf >> 1]], ox, oy, dv.x == 0.f, dv.y == 0.f, dv.z * inv_L, dv.w * inv_L);
+          // the ray's centre at first touch lies on the thin ray: well inside the hull's box means the thin ray enters
+          // it — decided by 4 compares; only hits near the box's border (grazing rays) pay for the exact slab test
+          const float4 bb = m.hull_bb[m.edge_hull[bf >> 1]];
+          const float s = __uint_as_float(bs), px = fmaf(s, ux, ox), py = fmaf(s, uy, oy);
+          if (!(px > bb.x + 0.05f && px < bb.z - 0.05f && py > bb.y + 0.05f && py < bb.w - 0.05f)) {
+            const float4 dv = m.dir[ci];
+            redo = !thin_bb_hit(bb, ox, oy, dv.x == 0.f, dv.y == 0.f, dv.z * inv_L, dv.w * inv_L);
+          }
         }
         if (redo) {                    // grazing fat ray: walk the list again, leaf rule on every hit
           start_ray(cur);
@@ -679,10 +715,11 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
 // buffer per agent (rasterise_agent, lanes = edges then (edge, ray) pairs).  Then, lanes = rays: the other agents'
 // circles and the alpha = 0 rules are merged in, and the hit point goes through the float16 chain.
 template <int TA, int TR>
-__device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world, bool staged) {
+__device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world, bool staged,
+                                              SlotStage& st) {
   const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane;
   const bool lists = k.ray_slots != nullptr;
-  if (lists && !staged) stage_ray_slots<TA, TR>(k, w);
+  if (lists && !staged) stage_ray_slots<TA, TR>(k, w, st);
   const float* pos = w.rec;
   const float* tc = w.rec + k.o_tc;
   const uint32_t flags = reinterpret_cast<const uint32_t*>(w.rec)[k.o_flags];
@@ -721,7 +758,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
   __syncwarp();
   if (lane == 0 && flags) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0u;   // lists are now valid for these positions
 
-  if (lists) sweep_lists<TA, TR>(k, m, w);
+  if (lists) sweep_lists<TA, TR>(k, m, w, st);
   const int kstride = lists ? 2 : 1;   // the list walk leaves ray r's key in the first half of its 16-byte slot
 
   const int nsub = (R + 31) >> 5;
@@ -1405,9 +1442,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   w.cand = reinterpret_cast<uint16_t*>(scratch + k.s_cand);
   w.rew = reinterpret_cast<float*>(scratch + k.s_rdist + k.r_off_reward);
   w.flg = reinterpret_cast<uint8_t*>(scratch + k.s_rdist + k.r_off_flags);
-  w.rcell = reinterpret_cast<int32_t*>(scratch + k.s_rcell);
+  w.mbar = reinterpret_cast<unsigned long long*>(scratch + k.s_rcell);
   w.blob = smem;
   w.lane = lane;
+  SlotStage slot_stage{0u, false};
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(w.mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
 
   // the padding of the staged output record is shipped by the 16-byte store paths: keep it zero
   for (int i = lane; i < (k.r_bytes >> 2); i += 32) reinterpret_cast<uint32_t*>(w.rdist)[i] = 0u;
@@ -1417,12 +1460,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   const long long stride = (long long)gridDim.x * wpc;
 #pragma unroll 1
   for (long long wbase = k.world_begin + (long long)blockIdx.x * wpc; wbase < k.world_end; wbase += stride) {
-#ifndef CAT_NO_WORLD_SYNC
-    // Re-align the CTA's warps once per world.  Nothing is shared between them — the point is the instruction
-    // cache: the kernel is ~70 KB of SASS, and warps that drift apart each pull a different part of it (ncu: 2.4
-    // warps per issue slot stalled on `no_instruction`).  Starting every world together keeps them in the same
-    // code for most of it: -3 ... 4.5 % step time on every map; finer barriers (per agent sweep) lose more to
-    // waiting than they gain (profiles/r1_notes.md).  Every warp of the CTA walks the same wbase sequence.
+#ifdef CAT_WORLD_SYNC
+    // (Round 1 re-aligned the CTA's warps here once per world for the instruction cache — the rasteriser's hot code
+    // was 38 KB.  The list walk's hot loop is ~3 KB and the barrier now costs more than it saves: 221 -> 207 us on
+    // agh-map x 16384 with 32-warp CTAs, profiles/r2_notes.md.  Kept as a build option.)
     __syncthreads();
 #endif
     const long long world = wbase + warp;
@@ -1457,7 +1498,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     bool captured = false, timeout = false;
     // the sensor sweep reads the PRE-step positions, which are known now: start fetching the rays' candidate slots
     bool staged = false;
-    if (do_step && k.ray_slots) { stage_ray_slots<TA, TR>(k, w); staged = true; }
+    if (do_step && k.ray_slots) { stage_ray_slots<TA, TR>(k, w, slot_stage); staged = true; }
     if (do_step) {  // ---------------- base_env.py:354-383 ----------------
       const float* pos = w.rec;
       float* vel = w.rec + k.o_vel;
@@ -1507,7 +1548,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
       // is re-spawned in it emits the NEW episode's observation (C-10) and a terminal reward that does not depend
       // on what is seen, so its terminal sensor sweep would be thrown away: skip it.  With one world per warp the
       // launch lasts as long as its slowest warp, and a second sweep made every finishing world that warp.
-      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world<TA, TR>(k, m, w, world, staged);
+      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world<TA, TR>(k, m, w, world, staged, slot_stage);
       bool again = false;
       if (do_step) {
         if (lane < A) w.rew[lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
