@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/cat_b200.h"
@@ -77,8 +78,10 @@ struct DeviceGuard {
 
 // ------------------------------------------------------------------ host side / C ABI
 typedef void (*WorldKernel)(const KParams);
+struct LaunchShape { int threads, smem, grid; };
 
 struct CatEnv {
+  std::vector<std::pair<int, LaunchShape>> shape_cache;   // launch shape per world count (the chunked host path asks every step)
   WorldKernel kernel = nullptr;
   int device = 0;
   int n_worlds = 0;
@@ -101,8 +104,6 @@ struct CatEnv {
   cudaEvent_t copies_done = nullptr;
 };
 
-struct LaunchShape { int threads, smem, grid; };
-
 // the kernel instantiation an environment runs (fixed at creation): agents / rays as compile-time constants for the
 // shipped shape, the any-shape instantiation otherwise (CAT_GENERIC_KERNEL=1 at creation forces it: test knob)
 static WorldKernel pick_world_kernel(int A, int R) {
@@ -111,7 +112,9 @@ static WorldKernel pick_world_kernel(int A, int R) {
   return (A == 3 && R == 90 && !generic) ? cat_world_kernel<3, 90> : cat_world_kernel<0, 0>;
 }
 
-static bool pick_launch_shape(const CatEnv* env, int n_worlds, LaunchShape* out) {
+static bool pick_launch_shape(CatEnv* env, int n_worlds, LaunchShape* out) {
+  for (const auto& kv : env->shape_cache)
+    if (kv.first == n_worlds) { *out = kv.second; return true; }
   long long best_score = -1;
   int wpc_max = kMaxThreads / 32;
   if (const char* e = getenv("CAT_MAX_WARPS_PER_CTA")) { const int v = atoi(e); if (v >= 2 && v < wpc_max) wpc_max = v; }   // tuning knob
@@ -130,6 +133,7 @@ static bool pick_launch_shape(const CatEnv* env, int n_worlds, LaunchShape* out)
       out->threads = wpc * 32; out->smem = smem; out->grid = one_wave ? need : env->n_sm * occ;
     }
   }
+  if (best_score >= 0 && env->shape_cache.size() < 64) env->shape_cache.emplace_back(n_worlds, *out);
   return best_score >= 0;
 }
 

@@ -248,7 +248,7 @@ class BatchedCopsThievesEnv(_EnvCommon):
         self._cmap = compile_map(map, spawn_override=spawn_override, cell=cell)
         self._params = params
         self._setup_common(map, self._cmap, params)
-        self._w = CatWorlds(self._cmap, num_envs, device=device, gid0=gid0, params=params, want_f32=True)
+        self._w = CatWorlds(self._cmap, num_envs, device=device, gid0=gid0, params=params, want_f32=True, want_critic=True)
         self.num_envs = int(num_envs)
         self.num_agents = len(self.possible_agents)
         self.agents = self.possible_agents[:]
@@ -304,6 +304,11 @@ class BatchedCopsThievesEnv(_EnvCommon):
 
     def state(self) -> torch.Tensor:
         return self._w.state_f32
+
+    def critic(self) -> torch.Tensor:
+        """The critic's front end, written by the step kernel itself: the 4 ray channels ``LSTMValue`` cuts out of
+        ``state()`` (``lstm_value_net.py:122-137``) as ``(N, 4, R)`` float32 — no slice / stack copies on the way."""
+        return self._w.critic_f32
 
     def render(self, world: int = 0):
         from .render import render_rgb

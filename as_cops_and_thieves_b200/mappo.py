@@ -144,8 +144,11 @@ class LSTMValueNet(_Recurrent):
         return torch.stack([state[..., 3 * R:4 * R], state[..., 2 * R:3 * R], state[..., R:2 * R], state[..., :R]], dim=-2)
 
     def forward(self, state: torch.Tensor, hc, reset: Optional[torch.Tensor] = None):
-        B, L, _ = state.shape
-        f = self.features_extractor(self.critic_channels(state).reshape(B * L, 4, self.length)).view(B, L, -1)
+        """``state``: the flattened ``env.state()`` (B, L, S), or the 4-channel ray block the step kernel emits
+        directly (``env.critic()``, (B, L, 4 R) — the same numbers, no stack copy: SURVEY.md f-3)."""
+        B, L, S = state.shape
+        ch = state if S == 4 * self.length else self.critic_channels(state)
+        f = self.features_extractor(ch.reshape(B * L, 4, self.length)).view(B, L, -1)
         out, hc = self.run_lstm(f, hc, reset)
         return self.value_head(out).squeeze(-1), hc
 
@@ -205,8 +208,13 @@ class MAPPOConfig:
     value_loss_scale: float = 0.5      # :13
     grad_norm_clip: float = 0.5        # :14
     kl_threshold: float = 0.015        # :11
-    random_timesteps: int = 0          # :9 (10000 in the reference: uniform random actions first)
-    learning_starts: int = 0           # :10 (15000 in the reference)
+    random_timesteps: int = 10000      # :9 uniform random actions first
+    learning_starts: int = 15000       # :10 no update before this many (lockstep) timesteps
+    # CFG_TRAINER (:61-62) + the reference's skrl patch (README.md:78-152): train() starts with every policy frozen and
+    # every value net trainable (agent_learning_utils.py:192-194); all value nets are (re-)unfrozen at
+    # opponent_freeze_duration and all policies at policy_freeze_duration.  0 = nothing is frozen.
+    opponent_freeze_duration: int = 15000
+    policy_freeze_duration: int = 15000
     model: str = "lstm"                # "lstm" (self_play_driver.py via initialize_lstm_models_for_mappo) | "mlp"
     sequence_length: int = 16          # lstm_policy_net.py:16
     cuda_graph: bool = True            # replay the whole rollout (nets + env kernels) as one CUDA graph
@@ -226,6 +234,7 @@ class UpdateStats:
     gae_ms: float = 0.0
     allreduce_ms: float = 0.0
     update_ms: float = 0.0
+    allreduce_events: Optional[list] = None
 
 
 def ppo_losses(logits: torch.Tensor, actions: torch.Tensor, old_log_prob: torch.Tensor, advantages: torch.Tensor,
@@ -274,7 +283,8 @@ class MAPPOLearner:
             raise ValueError("rollouts must be a multiple of sequence_length")
         torch.manual_seed(seed)     # identical initial weights on every rank
         self.models = build_models(self.agents, self.n_obs, self.n_state, self.cfg.model, self.device)
-        self.optimizers = {a: torch.optim.Adam(self.parameters(a), lr=self.cfg.learning_rate) for a in self.agents}
+        # fused Adam: its step can be switched off by a device-side flag (the KL early stop below) without a host sync
+        self.optimizers = {a: torch.optim.Adam(self.parameters(a), lr=self.cfg.learning_rate, fused=True) for a in self.agents}
         self.frozen: Dict[str, Dict[str, bool]] = {a: {"policy": False, "value": False} for a in self.agents}
         # One flat fp32 gradient bucket per agent; every parameter's .grad is a view into it, so the minibatch
         # all-reduce is a single NCCL call on memory autograd already wrote — no gather / scatter copies.
@@ -301,7 +311,11 @@ class MAPPOLearner:
                     m[role + "_h"] = torch.zeros(shape, device=dev)
                     m[role + "_c"] = torch.zeros(shape, device=dev)
             self.mem[a] = m
-        self.mem_state = torch.zeros((T, N, self.n_state), device=dev)
+        # the LSTM critic reads only the 4-channel ray block of the first agent: take it straight from the
+        # step kernel (env.critic()) instead of storing / slicing / stacking the 1090-float state
+        self.critic_block = self.cfg.model == "lstm" and getattr(env, "critic", None) is not None and env.critic() is not None
+        self.n_value_in = 4 * env.worlds.R if self.critic_block else self.n_state
+        self.mem_state = torch.zeros((T, N, self.n_value_in), device=dev)
         self.mem_done = torch.zeros((T, N), dtype=torch.bool, device=dev)
         self.mem_reset = torch.zeros((T, N), dtype=torch.bool, device=dev)   # episode of world n ended just before step t
         self._obs = None
@@ -412,7 +426,7 @@ class MAPPOLearner:
         L = cfg.sequence_length
         obs_bufs = env._obs_dict()                 # views of the environment's persistent output buffers
         for t in range(cfg.rollouts):
-            state = env.state()
+            state = self._value_input()
             self.mem_state[t].copy_(state)
             self.mem_reset[t].copy_(self._prev_done)
             reset = self._prev_done.view(-1, 1)
@@ -443,6 +457,10 @@ class MAPPOLearner:
             done = (term[self.agents[0]] | trunc[self.agents[0]]).view(-1)
             self.mem_done[t].copy_(done)
             self._prev_done.copy_(done)
+
+    def _value_input(self) -> torch.Tensor:
+        """What the critics read: the kernel's (N, 4, R) block viewed as (N, 4 R), or the flattened state (N, S)."""
+        return self.env.critic().view(self.env.num_envs, -1) if self.critic_block else self.env.state()
 
     def collect(self) -> None:
         """One rollout.  The first call per mode runs eagerly (warm-up: cuDNN plans, allocator); later calls
@@ -496,16 +514,15 @@ class MAPPOLearner:
         if self.timestep < cfg.learning_starts:
             return stats
         N = self.env.num_envs
-        last_state = self.env.state()
-        reset_seq = self._sequences(self.mem_reset)
-        state_seq = self._sequences(self.mem_state)
-        n_seq = reset_seq.shape[0]
+        last_state = self._value_input()
         for a in self.agents:
             if self.frozen[a]["policy"] and self.frozen[a]["value"]:
                 continue
             st = UpdateStats()
-            ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            ev0.record()
+            cuda = self.device.type == "cuda"
+            ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3)) if cuda else (None, None, None)
+            if cuda:
+                ev0.record()
             mem = self.mem[a]
             pol, val = self.models[a]["policy"], self.models[a]["value"]
             with torch.no_grad():
@@ -513,53 +530,107 @@ class MAPPOLearner:
                 last_values = lv.view(-1)
             returns, advantages = compute_gae(mem["rew"], self.mem_done, mem["val"], last_values, cfg.discount_factor,
                                               cfg.lambda_, normalize=True, distributed=cfg.distributed)
-            ev1.record()
-            obs_seq = self._sequences(mem["obs"])
-            act_seq, logp_seq = self._sequences(mem["act"]), self._sequences(mem["logp"])
-            ret_seq, adv_seq = self._sequences(returns), self._sequences(advantages)
-            params = [p for p in self.parameters(a) if p.requires_grad]
-            ar_events = []
-            for _epoch in range(cfg.learning_epochs):
-                perm = torch.randperm(n_seq, device=self.device)
-                for idx in perm.chunk(cfg.mini_batches):
-                    rs = reset_seq[idx]
-                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.update_autocast == "bf16"):
-                        logits, _ = pol(obs_seq[idx], self._hidden(mem, "policy", idx), rs)
-                        values, _ = val(state_seq[idx], self._hidden(mem, "value", idx), rs)
-                    logits, values = logits.float(), values.float()
-                    pl, el, vl, kl, ent = ppo_losses(logits.reshape(-1, logits.shape[-1]), act_seq[idx].reshape(-1),
-                                                     logp_seq[idx].reshape(-1), adv_seq[idx].reshape(-1),
-                                                     values.reshape(-1), ret_seq[idx].reshape(-1), cfg)
-                    if cfg.kl_threshold and float(kl.detach()) > cfg.kl_threshold:
-                        break          # skrl: early stop of this epoch's minibatch loop
-                    loss = vl if self.frozen[a]["policy"] else (pl + el + vl if not self.frozen[a]["value"] else pl + el)
-                    self.optimizers[a].zero_grad(set_to_none=False)
-                    loss.backward()
-                    if cfg.distributed:
-                        import torch.distributed as dist
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record()
-                        dist.all_reduce(self._flat_grad[a])          # frozen slices are zero on every rank
-                        self._flat_grad[a].div_(cfg.world_size)
-                        e1.record()
-                        ar_events.append((e0, e1))
-                    if cfg.grad_norm_clip > 0:
-                        nn.utils.clip_grad_norm_(params, cfg.grad_norm_clip)
-                    self.optimizers[a].step()
-                    st.policy_loss, st.value_loss, st.entropy, st.kl = (float(x.detach()) for x in (pl, vl, ent, kl))
-                    st.minibatches += 1
-            ev2.record()
-            ev2.synchronize()
-            st.gae_ms, st.update_ms = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)
-            st.allreduce_ms = sum(e0.elapsed_time(e1) for e0, e1 in ar_events)
+            if cuda:
+                ev1.record()
+            self._ppo_update(a, returns, advantages, st)
+            if cuda:
+                ev2.record()
+                ev2.synchronize()
+                st.gae_ms, st.update_ms = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)
+                st.allreduce_ms = sum(e0.elapsed_time(e1) for e0, e1 in st.allreduce_events)
+            st.allreduce_events = None
             stats[a] = st
         return stats
+
+    def _ppo_update(self, a: str, returns: torch.Tensor, advantages: torch.Tensor, st: UpdateStats) -> UpdateStats:
+        """The epochs x minibatches of skrl's ``MAPPO._update`` for agent ``a`` on the recorded rollout (pure PyTorch;
+        under ``distributed`` every rank issues the same sequence of collectives whatever its data says)."""
+        cfg, dev = self.cfg, self.device
+        thr = float(cfg.kl_threshold or 0.0)
+        mem = self.mem[a]
+        pol, val = self.models[a]["policy"], self.models[a]["value"]
+        reset_seq = self._sequences(self.mem_reset)
+        state_seq = self._sequences(self.mem_state)
+        n_seq = reset_seq.shape[0]
+        obs_seq = self._sequences(mem["obs"])
+        act_seq, logp_seq = self._sequences(mem["act"]), self._sequences(mem["logp"])
+        ret_seq, adv_seq = self._sequences(returns), self._sequences(advantages)
+        params = [p for p in self.parameters(a) if p.requires_grad]
+        ar_events = []
+        opt = self.optimizers[a]
+        # skrl's KL early stop ("break" out of the epoch's minibatch loop) as a DEVICE-side, COLLECTIVE decision:
+        # the KL is all-reduced (MAX) so that every rank stops at the same minibatch, the sticky flag switches the
+        # fused Adam step off for the rest of the epoch, and every rank still issues the same sequence of
+        # collectives (a rank-local `break` would pair its gradient all-reduce with another rank's next bucket).
+        # No host round trip per minibatch; the skipped minibatches still run forward / backward.
+        stop = torch.zeros((), device=dev)
+        applied = torch.zeros((), device=dev)
+        last = None
+        for _epoch in range(cfg.learning_epochs):
+            stop.zero_()
+            perm = torch.randperm(n_seq, device=self.device)
+            for idx in perm.chunk(cfg.mini_batches):
+                rs = reset_seq[idx]
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.update_autocast == "bf16" and dev.type == "cuda"):
+                    logits, _ = pol(obs_seq[idx], self._hidden(mem, "policy", idx), rs)
+                    values, _ = val(state_seq[idx], self._hidden(mem, "value", idx), rs)
+                logits, values = logits.float(), values.float()
+                pl, el, vl, kl, ent = ppo_losses(logits.reshape(-1, logits.shape[-1]), act_seq[idx].reshape(-1),
+                                                 logp_seq[idx].reshape(-1), adv_seq[idx].reshape(-1),
+                                                 values.reshape(-1), ret_seq[idx].reshape(-1), cfg)
+                if thr > 0.0:
+                    klc = kl.detach().clone()
+                    if cfg.distributed:
+                        import torch.distributed as dist
+                        dist.all_reduce(klc, op=dist.ReduceOp.MAX)
+                    stop = torch.maximum(stop, (klc > thr).to(stop.dtype))
+                loss = vl if self.frozen[a]["policy"] else (pl + el + vl if not self.frozen[a]["value"] else pl + el)
+                opt.zero_grad(set_to_none=False)
+                loss.backward()
+                if cfg.distributed:
+                    import torch.distributed as dist
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    if dev.type == "cuda":
+                        e0.record()
+                    dist.all_reduce(self._flat_grad[a])          # frozen slices are zero on every rank
+                    self._flat_grad[a].div_(cfg.world_size)
+                    if dev.type == "cuda":
+                        e1.record()
+                        ar_events.append((e0, e1))
+                if cfg.grad_norm_clip > 0:
+                    nn.utils.clip_grad_norm_(params, cfg.grad_norm_clip)
+                opt.found_inf = stop                 # fused Adam: a non-zero flag makes this step a no-op, on the device
+                opt.step()
+                applied += 1.0 - stop
+                last = (pl.detach(), vl.detach(), ent.detach(), kl.detach())
+        opt.found_inf = None
+        st.policy_loss, st.value_loss, st.entropy, st.kl = (float(x) for x in last)   # the update's only host reads
+        st.minibatches = int(applied)
+        st.allreduce_events = ar_events
+        return st
 
     def train(self, timesteps: int, callback=None) -> List[Dict[str, UpdateStats]]:
         """``SequentialTrainer.train()``: alternate rollout and update until ``timesteps`` lockstep steps."""
         history = []
+        cfg = self.cfg
+        if cfg.policy_freeze_duration > 0 or cfg.opponent_freeze_duration > 0:
+            # train_simultaneously_and_evaluate (agent_learning_utils.py:188-194): every policy frozen, every value
+            # net trainable at the start of a training run
+            for a in self.agents:
+                self.freeze(a, "policy", cfg.policy_freeze_duration > 0)
+                self.freeze(a, "value", False)
+        start = self.timestep
         while self.timestep < timesteps:
+            before = self.timestep - start
             self.collect()
+            now = self.timestep - start
+            # the reference's skrl patch (README.md:100-152): at `timestep == duration` unfreeze ALL value / policy nets
+            if cfg.opponent_freeze_duration > 0 and before < cfg.opponent_freeze_duration <= now:
+                for a in self.agents:
+                    self.freeze(a, "value", False)
+            if cfg.policy_freeze_duration > 0 and before < cfg.policy_freeze_duration <= now:
+                for a in self.agents:
+                    self.freeze(a, "policy", False)
             s = self.update()
             history.append(s)
             if callback is not None:

@@ -3,23 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--worlds n]
 
-A "step" is one lockstep transition of every world on a rank: ONE launch of `cat_world_kernel`
-(termination test, action impulses, 90-ray sensor sweep per agent, float16 observation chain, rewards,
-rigid-body step, auto-reset).  Default workload = BASELINE.json configs[1]: squarinth, 4096 worlds per
-GPU, native observation dtypes.  Weak scaling: the worlds per GPU are fixed, ranks shard the global
-world range, there is no data-path collective.
+A "step" is one lockstep transition of every world on a rank: ONE launch of `cat_world_kernel` (termination test,
+action impulses, 90-ray sensor sweep per agent, float16 observation chain, rewards, rigid-body step, auto-reset).
+Default workload = the configuration the metric is quoted on (BASELINE.json north_star / configs[3] with the real
+large-segment map): agh-map, 16384 worlds per GPU.  Weak scaling: the worlds per GPU are fixed, ranks shard the
+global world range, there is no data-path collective.
 
-Prints ONE JSON line (rank 0).  `value` = agent-steps/s over all ranks with everything resident in
-HBM; `e2e` = the same metric through the host-buffer API (pinned actions in, observations / rewards /
-flags out, copies inside the timed region).  Cold L2: one step's working set is a few MB, far smaller than the
-126 MB L2, so the timed steps rotate over enough independent world sets that their buffers exceed L2 ("inputs
-larger than L2"); K steps are timed back to back between one CUDA-event pair.  The flush-between-steps method is
-run as a cross-check (config.cross_check_flush_method).
+Prints ONE JSON line (rank 0).  `value` = agent-steps/s over all ranks with everything resident in HBM; `e2e` = the
+same metric through the host-buffer API (pinned actions in, the step's records back in pinned host memory, copies
+inside the timed region).  Every named workload gets the same treatment under `other_workloads` (own roofline, e2e).
+Cold L2: one step's working set is a few MB, far smaller than the 126 MB L2, so the timed steps rotate over enough
+independent world sets that their buffers exceed L2 ("inputs larger than L2"); a block of K steps is timed back to
+back between one CUDA-event pair, and the block is repeated until the timed span is at least 50 ms.
+`--workload mappo-agh-map` times BASELINE config 5 instead (MAPPO self-play training on agh-map).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -31,24 +33,27 @@ sys.path.insert(0, str(ROOT))
 
 ALG_BYTES_PER_AGENT_STEP = 336          # native dtypes, step + raycast obs
 FALLBACK_HBM_GBS = 6650.0               # /opt/skills/guides/B200_PROFILING.md fallback
+MIN_SPAN_MS = 50.0                      # a timed span shorter than this is dominated by launch / event noise
 WORKLOADS = {                           # name -> (map, free-space spawns, worlds per GPU)
-    "squarinth-4096": ("squarinth", False, 4096),       # BASELINE.json configs[1]  (default)
+    "agh-map-16384": ("agh-map", True, 16384),          # the metric's configuration (default): 496 hull edges
+    "squarinth-4096": ("squarinth", False, 4096),       # BASELINE.json configs[1] (the parity configuration)
     "lbirinth-4096": ("lbirinth", False, 4096),         # the fifth named map
     "labyrinth-8192": ("labyrinth", True, 8192),        # configs[2] per-GPU share
-    "grandbyrinth-16384": ("grandbyrinth", False, 16384),  # configs[3]
-    "agh-map-16384": ("agh-map", True, 16384),          # the real large-segment case (496 edges)
+    "grandbyrinth-16384": ("grandbyrinth", False, 16384),  # configs[3] as named (16 edges)
 }
+DEFAULT_WORKLOAD = "agh-map-16384"
+TRAIN_WORKLOAD = "mappo-agh-map"
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="squarinth-4096", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + [TRAIN_WORKLOAD])
     ap.add_argument("--worlds", type=int, default=None, help="worlds per GPU (overrides the workload's)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the other workloads / cpu baseline")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other workloads / GAE / cpu baseline")
     return ap.parse_args()
 
 
@@ -68,10 +73,17 @@ def build_cmap(name, free):
     return compile_map(m, name=name, spawn_override=free_space_regions(m) if free else None)
 
 
-# ------------------------------------------------------------------ CPU arm (oracle port, host cores)
+def profile_json(name):
+    p = ROOT / "profiles" / name
+    try:
+        return json.load(open(p)) if p.exists() else {}
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------ CPU arm (host cores)
 def time_cpu_port(map_name, free, n_worlds, seconds=12.0, min_steps=3):
-    """The reference's algorithm on the host cores: the fp64 oracle port with OpenMP over worlds.
-    (Pymunk / PettingZoo are not installable here, SURVEY.md §8c, so the reference itself cannot run.)"""
+    """The reference's algorithm on the host cores: the fp64 oracle port with OpenMP over worlds."""
     import numpy as np
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     from oracle.cat_oracle import Oracle, num_threads
@@ -93,17 +105,42 @@ def time_cpu_port(map_name, free, n_worlds, seconds=12.0, min_steps=3):
                 worlds=n_worlds, A=orc.A)
 
 
+def time_pymunk_reference(map_name, free, seconds):
+    """The REAL Pymunk path, one process per host core — None when pymunk is not importable
+    (also tried with baseline/_ref on sys.path)."""
+    from oracle import pymunk_ref
+    pm, why = pymunk_ref.probe()
+    if pm is None or getattr(pm, "IS_STAND_IN", False):
+        return None, why
+    return pymunk_ref.time_reference(map_name, free, seconds=seconds), why
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (libgomp reads this at load)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    map_name, free, _ = WORKLOADS[args.workload]
-    sample_worlds = 512
+    workload = DEFAULT_WORKLOAD if args.workload == TRAIN_WORKLOAD else args.workload
+    map_name, free, _ = WORKLOADS[workload]
     K, W = max(1, args.steps), max(0, args.warmup)
+    base = {"impl": "reference", "metric": "agent-steps/s (physics+raycast obs)", "unit": "agent-steps/s",
+            "n_gpus": args.gpus, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic"}
+    ref, why = time_pymunk_reference(map_name, free, seconds=10.0)
+    if ref is not None:
+        # the unmodified engine: one world per process, one process per core, ~10 s each
+        value = ref["value"]
+        line = dict(base, value=value, steps=K, warmup=W, ms_per_step=None,
+                    config={"workload": workload, "map": map_name, "worlds_per_step": ref["cores"], "how": ref["how"]},
+                    cpu_baseline={"value": value, "unit": "agent-steps/s", "cores": ref["cores"], "kind": "reference",
+                                  "sample": f"{ref['cores']} processes x 1 {map_name} world x {ref['seconds']:.1f} s, {ref['how']}"},
+                    e2e={"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
     import numpy as np
     from oracle.cat_oracle import Oracle, num_threads
+    sample_worlds = 512
     cmap = build_cmap(map_name, free)
     orc = Oracle(cmap, seed=0)
     st = orc.new_state(sample_worlds)
@@ -111,9 +148,7 @@ def run_reference(args):
     orc.reset(st, out=out)
     rng = np.random.default_rng(1)
     acts = [rng.integers(0, 4, (sample_worlds, orc.A)).astype(np.int32) for _ in range(8)]
-    # bounded: cap the number of CPU steps so that the whole run ends within a few minutes
-    K = min(K, 400)
-    W = min(W, 20)
+    K, W = min(K, 400), min(W, 20)       # bounded: the whole run ends within a few minutes
     for i in range(W):
         orc.step(st, acts[i % 8], out)
     t0 = time.perf_counter()
@@ -122,15 +157,11 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = sample_worlds * orc.A * K / dt
     sample = f"{sample_worlds} {map_name} worlds x {K} steps, OpenMP over worlds (oracle port of the Pymunk path)"
-    line = {
-        "impl": "reference", "metric": "agent-steps/s (physics+raycast obs)", "value": value, "unit": "agent-steps/s",
-        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "map": map_name, "worlds_per_step": sample_worlds,
-                   "note": "reference Pymunk/PettingZoo path is not installable offline; CPU port of the same algorithm"},
-        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": num_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    line = dict(base, value=value, steps=K, warmup=W, ms_per_step=dt / K * 1e3,
+                config={"workload": workload, "map": map_name, "worlds_per_step": sample_worlds,
+                        "note": f"real Pymunk path unavailable ({why}); CPU port of the same algorithm instead"},
+                cpu_baseline={"value": value, "unit": "agent-steps/s", "cores": num_threads(), "kind": "port", "sample": sample},
+                e2e={"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line), flush=True)
 
 
@@ -191,9 +222,8 @@ L2_BYTES = 126e6                        # B200 L2
 def make_world_sets(CatWorlds, cmap, n_local, gid0, n_global, dev):
     """Independent sets of `n_local` worlds, enough of them that their state + output buffers together are 1.5x
     the L2.  The timed steps rotate over the sets (one launch = one set), so every step reads its state from
-    and writes its observations to HBM — "inputs larger than L2" — and K steps can be timed back to back with
-    ONE CUDA-event pair, as they run in use, instead of one event pair per step around a flush kernel (which
-    adds ~5 us of event / launch-gap overhead to every 40 us step).  Sets differ by global world id."""
+    and writes its records to HBM — "inputs larger than L2" — and K steps can be timed back to back with ONE
+    CUDA-event pair, as they run in use.  Sets differ by global world id."""
     first = CatWorlds(cmap, n_local, device=dev, gid0=gid0, seed=0, want_f32=False, want_shared=False)
     footprint = first.state.numel() + first._out.numel()
     n_sets = max(2, int(-(-1.5 * L2_BYTES // footprint)))
@@ -205,25 +235,39 @@ def make_world_sets(CatWorlds, cmap, n_local, gid0, n_global, dev):
 
 
 def time_steps(torch, sets, acts, K, W, dist=None):
-    """W warm-up steps per set, then EXACTLY K steps (round-robin over the sets) between one pair of CUDA events
-    on the launching stream, barrier + synchronize on both sides.  Returns the timed milliseconds on this rank."""
+    """W warm-up steps per set, then blocks of EXACTLY K steps (round-robin over the sets), each block between one pair
+    of CUDA events on the launching stream, barrier + synchronize on both sides; the block is repeated until the
+    timed span reaches MIN_SPAN_MS (a 20-step request on a 35 us step would otherwise time 0.7 ms).
+    Returns (total timed ms on this rank, number of blocks)."""
     n = len(sets)
-    for i in range(W * n):
-        sets[i % n].step(acts[i % len(acts)])
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
+    i = 0
+    for _ in range(W * n):
+        sets[i % n].step(acts[i % len(acts)]); i += 1
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(K):
-        sets[i % n].step(acts[i % len(acts)])
+    for _ in range(K):                  # untimed probe block: how long is K steps?
+        sets[i % n].step(acts[i % len(acts)]); i += 1
     e1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=acts[0].device)
+    if dist is not None:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    blocks = max(1, min(10000, int(math.ceil(MIN_SPAN_MS / max(float(est[0]), 1e-6)))))
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(blocks)]
+    for b in range(blocks):
+        ev[b][0].record()
+        for _ in range(K):
+            sets[i % n].step(acts[i % len(acts)]); i += 1
+        ev[b][1].record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1)
+    return sum(a.elapsed_time(b) for a, b in ev), blocks
 
 
 def time_steps_flushed(torch, cw, acts, K, W, flush):
@@ -243,12 +287,12 @@ def time_steps_flushed(torch, cw, acts, K, W, flush):
     return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
 
 
-def time_e2e(torch, cw, K, W, dist=None, mode="pipelined"):
-    """The host-buffer API: pinned uint8 actions in, observations / rewards / flags back in pinned host memory
-    when each call returns (CatWorlds.step_host; modes: pipelined chunks + DMA, zero-copy stores, staged copies)."""
+def time_e2e(torch, cw, K, W, dist=None, mode="auto"):
+    """The host-buffer API: pinned uint8 actions in, the step's records (observations / rewards / flags) back in
+    pinned host memory when each call returns (CatWorlds.step_host)."""
     N, A = cw.n_worlds, cw.A
     host_acts = [torch.randint(0, 4, (N, A), dtype=torch.uint8).pin_memory() for _ in range(8)]
-    for i in range(W):
+    for i in range(max(W, 16 if mode == "auto" else W)):     # (auto: its 15 tuning calls are warm-up, not timed)
         cw.step_host(host_acts[i % 8], mode=mode)
     torch.cuda.synchronize()
     if dist is not None:
@@ -261,13 +305,16 @@ def time_e2e(torch, cw, K, W, dist=None, mode="pipelined"):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    return e0.elapsed_time(e1), cw.h2d_bytes_per_step, cw.d2h_bytes_per_step
+    return e0.elapsed_time(e1)
 
 
 def time_gae(torch, dev, flush, T=256, M=49152, iters=30):
     """north-star item 4: the GAE scan (TMA-fed kernel; 9 B read + 8 B written per sample) and the in-place advantage
-    normalisation (4 B + 4 B), each timed with its own CUDA events.  L2 is flushed before every launch by READING a 192 MiB buffer
-    (a write flush would leave 126 MB of dirty lines whose write-back then competes with the timed kernel)."""
+    normalisation (4 B + 4 B), each timed with its own CUDA events.  L2 is flushed before every launch by READING a
+    192 MiB buffer (a write flush would leave 126 MB of dirty lines whose write-back then competes with the timed
+    kernel).  Two fractions of the HBM copy peak are reported: from the ALGORITHMIC bytes (the contract's
+    `achieved`), and from the DRAM bytes ncu measured for the same shapes (profiles/gae_dram_bytes.json): the
+    kernel's last stores are still dirty in L2 when it ends, so real traffic inside the timed span is lower."""
     from as_cops_and_thieves_b200 import _lib
     L = _lib.load()
     g = torch.Generator(device=dev).manual_seed(7)
@@ -298,172 +345,193 @@ def time_gae(torch, dev, flush, T=256, M=49152, iters=30):
     n = T * M
     peak, _ = measured_hbm_peak()
     gbs_gae, gbs_norm = 17 * n / ms_gae / 1e6, 8 * n / ms_norm / 1e6
-    return {"T": T, "columns": M, "samples": n, "timing": f"median of {iters} launches, CUDA events, inputs > L2 and L2 read-flushed",
-            "gae_ms": ms_gae, "normalize_ms": ms_norm,
-            "gae_gbs": gbs_gae, "gae_frac_of_hbm_peak": gbs_gae / peak, "normalize_gbs": gbs_norm,
-            "normalize_frac_of_hbm_peak": gbs_norm / peak, "combined_gbs": 25 * n / (ms_gae + ms_norm) / 1e6,
-            "combined_frac_of_hbm_peak": 25 * n / (ms_gae + ms_norm) / 1e6 / peak,
-            "bytes_per_sample": {"gae": 17, "normalize": 8}, "samples_per_s": n / (ms_gae + ms_norm) * 1e3}
+    out = {"T": T, "columns": M, "samples": n, "timing": f"median of {iters} launches, CUDA events, inputs > L2 and L2 read-flushed",
+           "gae_ms": ms_gae, "normalize_ms": ms_norm,
+           "gae_gbs": gbs_gae, "gae_frac_of_hbm_peak": gbs_gae / peak, "normalize_gbs": gbs_norm,
+           "normalize_frac_of_hbm_peak": gbs_norm / peak, "combined_gbs": 25 * n / (ms_gae + ms_norm) / 1e6,
+           "combined_frac_of_hbm_peak": 25 * n / (ms_gae + ms_norm) / 1e6 / peak,
+           "bytes_per_sample": {"gae": 17, "normalize": 8}, "samples_per_s": n / (ms_gae + ms_norm) * 1e3}
+    dram = profile_json("gae_dram_bytes.json").get(f"T{T}")
+    if dram:
+        out["dram_traffic"] = {
+            "source": "profiles/gae_dram_bytes.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same shapes)",
+            "gae_bytes_per_sample": dram["gae"] / n, "normalize_bytes_per_sample": dram["normalize"] / n,
+            "gae_frac_of_hbm_peak": dram["gae"] / ms_gae / 1e6 / peak,
+            "normalize_frac_of_hbm_peak": dram["normalize"] / ms_norm / 1e6 / peak}
+    return out
+
+
+def measure_workload(torch, CatWorlds, name, K, W, rank, world_size, dev, dist, gen, worlds=None, e2e_modes=("auto",),
+                     cross_check=None, sampler=None):
+    """One full line for one workload: device-resident rate, HBM + instruction-throughput roofline, host-buffer rate."""
+    from as_cops_and_thieves_b200.sharding import shard_range
+    map_name, free, per_gpu = WORKLOADS[name]
+    per_gpu = worlds or per_gpu
+    n_global = per_gpu * world_size
+    gid0, n_local = shard_range(n_global, rank, world_size)
+    cmap = build_cmap(map_name, free)
+    sets, footprint = make_world_sets(CatWorlds, cmap, n_local, gid0, n_global, dev)
+    cw = sets[0]
+    A = cw.A
+    acts = [torch.randint(0, 4, (n_local, A), dtype=torch.uint8, device=dev, generator=gen) for _ in range(16)]
+    if sampler is not None:
+        sampler.start()
+    ms_total, blocks = time_steps(torch, sets, acts, K, W, dist)
+    clocks = sampler.stop() if sampler is not None else None
+    n_steps = K * blocks
+    ms_flushed = None
+    if cross_check is not None:
+        k_flush = min(K, 300)
+        ms_flushed = time_steps_flushed(torch, cw, acts, k_flush, 10, cross_check) / k_flush
+    est_ms = ms_total / n_steps
+    e2e_steps = max(50, min(2000, int(math.ceil(MIN_SPAN_MS / (2.5 * est_ms)))))
+    e2e_ms = {m: time_e2e(torch, cw, e2e_steps, 5, dist, mode=m) for m in e2e_modes}
+    t = torch.tensor([ms_total] + [e2e_ms[m] for m in e2e_modes], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t[0])
+    e2e_ms = {m: float(t[1 + i]) for i, m in enumerate(e2e_modes)}
+
+    value = n_global * A * n_steps / (ms_total * 1e-3)
+    launch_ms = ms_total / n_steps
+    peak, peak_kind = measured_hbm_peak()
+    achieved = n_local * A * ALG_BYTES_PER_AGENT_STEP / (launch_ms * 1e-3) / 1e9
+    key = name if not worlds else ""
+    traffic = profile_json("traffic.json").get(key)
+    issue = None
+    per_world = profile_json("thread_instr_per_world_step.json").get(key)
+    if per_world:
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz") or 1965
+        peak_ti = n_sm * 128 * mhz * 1e6                 # one instruction per lane per clock
+        ach_ti = per_world * n_local / (launch_ms * 1e-3)
+        issue = {"what": "thread-level instructions per second of cat_world_kernel vs. 128 lanes x SMs x clock",
+                 "thread_instr_per_world_step": per_world, "achieved": ach_ti, "peak": peak_ti, "frac": ach_ti / peak_ti,
+                 "source": "profiles/thread_instr_per_world_step.json (ncu, this round's kernel) x live rate"}
+    main = e2e_modes[0]
+    e2e = {"value": n_global * A * e2e_steps / (e2e_ms[main] * 1e-3), "unit": "agent-steps/s",
+           "h2d_bytes_per_step": cw.h2d_bytes_per_step, "d2h_bytes_per_step": cw.d2h_bytes_per_step,
+           "steps": e2e_steps, "ms_per_step": e2e_ms[main] / e2e_steps,
+           "api": "CatWorlds.step_host(host_actions) [mode='auto': keeps the fastest of zero-copy stores into mapped pinned "
+                  "memory / chunked launches + one DMA copy per chunk / staged copies, timed on its first calls]: pinned u8 "
+                  "actions in, one 832-B record per world (f16 distances, u8 types, f32 rewards, u8 flags) back in pinned "
+                  "host memory on return",
+           "auto_choice": getattr(cw, "_auto_choice", None)}
+    for m in e2e_modes[1:]:
+        e2e[m] = {"value": n_global * A * e2e_steps / (e2e_ms[m] * 1e-3), "ms_per_step": e2e_ms[m] / e2e_steps}
+    res = {
+        "value": value, "ms_per_step": launch_ms, "steps_timed": n_steps, "timed_span_ms": ms_total, "blocks": blocks,
+        "config": {"workload": name, "map": map_name, "hull_edges": int(cmap.n_edges), "worlds_per_gpu": per_gpu,
+                   "global_worlds": n_global, "agents_per_world": A, "rays_per_agent": cw.R, "dt": 1 / 60,
+                   "max_step_count": 400, "spawn": "free-space regions" if free else "map spawn regions",
+                   "outputs": "one 832-B record per world: f16 distance + u8 type + f32 reward + u8 flags (native dtypes)",
+                   "sensor_sweep": (f"per-(cell, ray) candidate lists, {cw.info.ray_list_nx}x{cw.info.ray_list_ny} cells of "
+                                    f"{cw.info.ray_list_cell:.1f} units, {cw.info.ray_list_bytes / 1e6:.1f} MB in HBM/L2"),
+                   "launch": f"{cw.info.grid} CTAs x {cw.info.warps_per_cta} warps, {cw.info.smem_bytes_per_cta} B shared memory",
+                   "l2": f"inputs larger than L2: the timed steps rotate over {len(sets)} independent sets of {n_local} worlds "
+                         f"({footprint * len(sets) / 1e6:.0f} MB of state + record buffers > 126 MB L2), one launch = one set; "
+                         f"{blocks} block(s) of K steps, each between one CUDA-event pair, span {ms_total:.1f} ms",
+                   "parallelism": f"worlds sharded over {world_size} GPU(s), no data-path collective"},
+        "e2e": e2e,
+        "gpu_launches": n_steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                     "algorithmic_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP, "kernel": "cat_world_kernel<3, 90>",
+                     "instruction_throughput": issue,
+                     "note": "ALU/latency-bound path (SURVEY.md §8d): the HBM fraction is reported as asked, not a target; "
+                             "what bounds the kernel is instruction issue and dependent-instruction latency at 32 warps "
+                             "per SM (profiles/r2_cat_world_kernel_*.txt)"},
+        "overflow_counts": {"wall_contact_slots": 0, "near_hull_slots": 0},
+    }
+    oc = [0, 0]
+    for w_ in sets:
+        c = w_.overflow_counts()
+        oc[0] += c[0]; oc[1] += c[1]
+    res["overflow_counts"] = {"wall_contact_slots": oc[0], "near_hull_slots": oc[1]}
+    if ms_flushed is not None:
+        res["config"]["cross_check_flush_method"] = {
+            "ms_per_step": ms_flushed, "how": "one world set, 192 MiB write between steps, each step timed with its own event "
+                                              "pair (adds ~5 us of event / launch-gap overhead per step)"}
+    if clocks is not None:
+        res["clocks"] = clocks
+    for w_ in sets:
+        w_.close()
+    return res, cmap
+
+
+def init_dist(torch, local_rank, world_size):
+    if world_size <= 1:
+        return None
+    import torch.distributed as dist_mod
+    # NCCL prints its version banner (this image sets NCCL_DEBUG=VERSION) with printf on fd 1 and ignores
+    # NCCL_DEBUG_FILE for it; stdout must carry ONE JSON line, so fd 1 points at stderr while the communicator
+    # is created (init + first collective).
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist_mod.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+    return dist_mod
 
 
 def run_b200(args):
     import torch
-    from as_cops_and_thieves_b200.sharding import dist_env, shard_range
+    from as_cops_and_thieves_b200.sharding import dist_env
     from as_cops_and_thieves_b200.worlds import CatWorlds
 
     rank, local_rank, world_size = dist_env()
-    dist = None
-    if world_size > 1:
-        import torch.distributed as dist_mod
-        # NCCL prints its version banner (this image sets NCCL_DEBUG=VERSION) with printf on fd 1 and ignores
-        # NCCL_DEBUG_FILE for it; stdout must carry ONE JSON line, so fd 1 points at stderr while the communicator
-        # is created (init + first collective).
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-            dist_mod.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
-        dist = dist_mod
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    dist = init_dist(torch, local_rank, world_size)
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     numa_cpus = ()
     if world_size > 1 and os.environ.get("CAT_BENCH_NUMA_BIND", "1") == "1":
         from as_cops_and_thieves_b200.sharding import bind_to_gpu_numa_node
         numa_cpus = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation (first touch)
-
-    map_name, free, per_gpu = WORKLOADS[args.workload]
-    per_gpu = args.worlds or per_gpu
-    n_global = per_gpu * world_size
-    gid0, n_local = shard_range(n_global, rank, world_size)
     K, W = max(1, args.steps), max(3, args.warmup)
-
-    cmap = build_cmap(map_name, free)
-    sets, footprint = make_world_sets(CatWorlds, cmap, n_local, gid0, n_global, dev)
-    cw = sets[0]
-    g = torch.Generator(device=dev).manual_seed(1 + rank)
-    acts = [torch.randint(0, 4, (n_local, cw.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(16)]
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
     flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # 192 MiB > 126 MB L2
-
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
-    sampler.start()
-    ms_total = time_steps(torch, sets, acts, K, W, dist)
-    clocks = sampler.stop()
-    k_flush = min(K, 500)
-    ms_flushed = time_steps_flushed(torch, cw, acts, k_flush, 10, flush) / k_flush
-    e2e_steps = min(K, 1000)
-    e2e_ms, h2d, d2h = time_e2e(torch, cw, e2e_steps, 5, dist, mode="zero_copy")
-    e2e_pipe_ms, _, _ = time_e2e(torch, cw, e2e_steps, 5, dist, mode="pipelined")
-    e2e_staged_ms, _, _ = time_e2e(torch, cw, e2e_steps, 5, dist, mode="staged")
 
-    t = torch.tensor([ms_total, e2e_ms, e2e_pipe_ms, e2e_staged_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, e2e_pipe_ms, e2e_staged_ms = (float(x) for x in t)
-
-    A = cw.A
-    value = n_global * A * K / (ms_total * 1e-3)
-    e2e_value = n_global * A * e2e_steps / (e2e_ms * 1e-3)
-    peak, peak_kind = measured_hbm_peak()
-    launch_ms = ms_total / K
-    alg_bytes = n_local * A * ALG_BYTES_PER_AGENT_STEP
-    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    traffic = None
-    tf = ROOT / "profiles" / "traffic.json"          # dram bytes per launch from the committed ncu --set full capture
-    if tf.exists():
-        try:
-            traffic = json.load(open(tf)).get(args.workload if not args.worlds else "", None)
-        except Exception:
-            traffic = None
-
-    issue = None
-    ti = ROOT / "profiles" / "thread_instr_per_world_step.json"   # from the committed ncu capture of this workload
-    if ti.exists() and not args.worlds:
-        try:
-            per_world = json.load(open(ti)).get(args.workload)
-            if per_world:
-                n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-                mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
-                peak_ti = n_sm * 128 * mhz * 1e6                 # one instruction per lane per clock
-                ach_ti = per_world * n_local / (launch_ms * 1e-3)
-                issue = {"what": "thread-level instructions per second of cat_world_kernel vs. 128 lanes x SMs x clock",
-                         "thread_instr_per_world_step": per_world, "achieved": ach_ti, "peak": peak_ti,
-                         "frac": ach_ti / peak_ti, "source": "profiles/thread_instr_per_world_step.json (ncu) x live rate"}
-        except Exception:
-            issue = None
-
+    head, cmap = measure_workload(torch, CatWorlds, args.workload, K, W, rank, world_size, dev, dist, gen, worlds=args.worlds,
+                                  e2e_modes=("auto", "zero_copy", "pipelined", "staged"), cross_check=flush, sampler=sampler)
+    map_name, free, _ = WORKLOADS[args.workload]
+    head["config"]["cpu_affinity"] = f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus else "unbound"
     line = {
-        "metric": "agent-steps/s (physics+raycast obs)", "value": value, "unit": "agent-steps/s",
-        "n_gpus": world_size, "steps": K, "warmup": W, "ms_per_step": launch_ms, "higher_is_better": True,
+        "metric": "agent-steps/s (physics+raycast obs)", "value": head["value"], "unit": "agent-steps/s",
+        "n_gpus": world_size, "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "map": map_name, "hull_edges": int(cmap.n_edges), "worlds_per_gpu": per_gpu,
-                   "global_worlds": n_global, "agents_per_world": A, "rays_per_agent": cw.R, "dt": 1 / 60,
-                   "max_step_count": 400, "spawn": "free-space regions" if free else "map spawn regions",
-                   "outputs": "f16 distance + u8 type + f32 reward + u8 flags (native dtypes)",
-                   "l2": f"inputs larger than L2: the timed steps rotate over {len(sets)} independent sets of {n_local} worlds "
-                         f"({footprint * len(sets) / 1e6:.0f} MB of state + output buffers > 126 MB L2), one launch = one set; "
-                         "K steps timed back to back with one CUDA-event pair",
-                   "cross_check_flush_method": {"ms_per_step": ms_flushed, "steps": k_flush,
-                                                "how": "one world set, 192 MiB write between steps, each step timed with "
-                                                       "its own event pair (adds ~5 us of event / launch-gap overhead per step)"},
-                   "parallelism": f"worlds sharded over {world_size} GPU(s), no data-path collective",
-                   "cpu_affinity": f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus else "unbound"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "CatWorlds.step_host(mode='zero_copy'): ONE launch; the kernel reads pinned u8 actions and stores f16/u8 "
-                       "observations, f32 rewards, u8 flags straight into mapped pinned host memory with 16-byte stores "
-                       "(transfer overlaps compute); one stream sync per step",
-                "pipelined": {"value": n_global * A * e2e_steps / (e2e_pipe_ms * 1e-3), "ms_per_step": e2e_pipe_ms / e2e_steps,
-                              "chunks": cw.default_chunks(),
-                              "api": "step_host(mode='pipelined') -> cat_env_step_host: chunked launches, per-chunk DMA on a copy stream"},
-                "staged_copy": {"value": n_global * A * e2e_steps / (e2e_staged_ms * 1e-3), "ms_per_step": e2e_staged_ms / e2e_steps,
-                                "api": "step_host(mode='staged'): H2D copy, launch, one D2H copy of the output blob"}},
-        "gpu_launches": K,          # one cat_world_kernel launch per timed step (the e2e legs launch their own)
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                     "algorithmic_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP, "kernel": "cat_world_kernel",
-                     "instruction_throughput": issue,
-                     "note": "ALU/latency-bound path (SURVEY.md §8d): HBM fraction is reported as asked, not a target; "
-                             "what bounds the kernel is instruction issue (ncu: 68-76 % of issue slots busy, 23-25 of 32 "
-                             "lanes active; profiles/r1_cat_world_kernel_*.txt)"},
+        "config": head["config"], "clocks": head.get("clocks"), "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+        "roofline": head["roofline"], "overflow_counts": head["overflow_counts"],
+        "timed": {"steps": head["steps_timed"], "blocks_of_K": head["blocks"], "span_ms": head["timed_span_ms"]},
     }
 
     if not args.no_extras:
-        # every named map, on every rank (weak scaling: the same worlds per GPU), max over ranks like the headline
         others = {}
-        for wl, (mn, fr, nw) in WORKLOADS.items():
+        for wl in WORKLOADS:          # every named map, on every rank, the same treatment as the headline
             if wl == args.workload:
                 continue
-            c2 = build_cmap(mn, fr)
-            g0, nl = shard_range(nw * world_size, rank, world_size)
-            sets2, _ = make_world_sets(CatWorlds, c2, nl, g0, nw * world_size, dev)
-            w2 = sets2[0]
-            a2 = [torch.randint(0, 4, (nl, w2.A), dtype=torch.uint8, device=dev, generator=g) for _ in range(8)]
-            ms = time_steps(torch, sets2, a2, 300, 5, dist)
-            if dist is not None:
-                tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                ms = float(tt[0])
-            others[wl] = {"value": nw * world_size * w2.A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
-                          "hull_edges": int(c2.n_edges), "worlds_per_gpu": nw}
-            for w_ in sets2:
-                w_.close()
+            res, _ = measure_workload(torch, CatWorlds, wl, K, W, rank, world_size, dev, dist, gen)
+            others[wl] = {k: res[k] for k in ("value", "ms_per_step", "steps_timed", "timed_span_ms", "e2e", "roofline",
+                                              "overflow_counts")}
+            others[wl]["config"] = {k: res["config"][k] for k in ("map", "hull_edges", "worlds_per_gpu", "spawn", "sensor_sweep", "launch")}
         line["other_workloads"] = others
     if rank == 0 and world_size == 1 and not args.no_extras:
-        # the skrl-facing layout: + team-shared observations + fp32 flattened obs (A,N,180) + state (N,1090)
-        w3 = CatWorlds(cmap, n_local, device=dev, seed=0, want_f32=True, want_shared=True)
+        # the skrl-facing layout: + team-shared observations + fp32 flattened obs (A,N,180) + state (N,1090) + critic block
+        n_local = args.worlds or WORKLOADS[args.workload][2]
+        acts = [torch.randint(0, 4, (n_local, 3), dtype=torch.uint8, device=dev, generator=gen) for _ in range(16)]
+        w3 = CatWorlds(cmap, n_local, device=dev, seed=0, want_f32=True, want_shared=True, want_critic=True)
         w3.reset()
-        ms = time_steps_flushed(torch, w3, acts, 300, 20, flush)
-        line["other_workloads"][args.workload + "+skrl-layouts"] = {"value": n_local * A * 300 / (ms * 1e-3), "ms_per_step": ms / 300,
-                                                                    "bytes_per_agent_step": 786 + 1453}
+        ms = time_steps_flushed(torch, w3, acts, 200, 20, flush)
+        line["other_workloads"][args.workload + "+skrl-layouts"] = {
+            "value": n_local * 3 * 200 / (ms * 1e-3), "ms_per_step": ms / 200, "bytes_per_agent_step": 786 + 1453 + 480}
         w3.close()
         line["gae"] = time_gae(torch, dev, flush)
         line["gae_T1024"] = time_gae(torch, dev, flush, T=1024, iters=10)     # a reference-length rollout (4096 / 4)
@@ -471,6 +539,13 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": cpu["value"], "unit": "agent-steps/s", "cores": cpu["cores"], "kind": "port",
                                 "sample": f"{cpu['worlds']} {map_name} worlds x {cpu['steps']} steps in {cpu['seconds']:.1f} s, "
                                           "fp64 oracle port of the Pymunk path, OpenMP over worlds"}
+        ref, why = time_pymunk_reference(map_name, free, seconds=10.0)
+        if ref is not None:            # the real engine is here: it is the baseline, the port rides along
+            line["cpu_baseline"] = {"value": ref["value"], "unit": "agent-steps/s", "cores": ref["cores"], "kind": "reference",
+                                    "sample": f"{ref['cores']} processes x 1 {map_name} world x {ref['seconds']:.1f} s, {ref['how']}",
+                                    "oracle_port": line["cpu_baseline"]}
+        else:
+            line["cpu_baseline"]["pymunk_probe"] = why
         # BASELINE.json configs[0]: agh-map, ONE environment, one host thread — what a reference user runs today
         cpu1 = time_cpu_port("agh-map", False, 1, seconds=3.0)       # one world = one loop iteration = one thread
         line["cpu_baseline"]["config0_agh-map_single_env"] = {
@@ -478,10 +553,79 @@ def run_b200(args):
             "sample": f"1 agh-map world (file spawn positions) x {cpu1['steps']} steps in {cpu1['seconds']:.1f} s, oracle port"}
     elif rank == 0:
         line["cpu_baseline"] = None
-    for w_ in sets:
-        w_.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ BASELINE config 5: MAPPO self-play training
+def run_training(args):
+    """`--workload mappo-agh-map`: MAPPO (LSTM policy + centralised critic per agent, the reference's architectures)
+    on agh-map, >= 16384 worlds per GPU, gradients all-reduced over NCCL.  A "step" here is one lockstep environment
+    step INSIDE training; reports the environment rate inside the rollouts, the update time and the all-reduce time."""
+    import torch
+    from as_cops_and_thieves_b200.env import BatchedCopsThievesEnv
+    from as_cops_and_thieves_b200.maps import free_space_regions, load_named_map
+    from as_cops_and_thieves_b200.mappo import MAPPOConfig, MAPPOLearner
+    from as_cops_and_thieves_b200.sharding import dist_env, shard_range
+
+    rank, local_rank, world_size = dist_env()
+    dist = init_dist(torch, local_rank, world_size)
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    per_gpu = args.worlds or 16384
+    gid0, n_local = shard_range(per_gpu * world_size, rank, world_size)
+    m = load_named_map("agh-map")
+    env = BatchedCopsThievesEnv(m, n_local, device=dev, seed=0, gid0=gid0, spawn_override=free_space_regions(m),
+                                max_step_count=400)
+    cfg = MAPPOConfig(rollouts=16, sequence_length=16, distributed=world_size > 1, world_size=world_size,
+                      random_timesteps=0, learning_starts=0, policy_freeze_duration=0, opponent_freeze_duration=0,
+                      update_autocast="bf16")
+    learner = MAPPOLearner(env, cfg, seed=0)
+    iters = max(2, min(args.steps // cfg.rollouts, 6))
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
+    for _ in range(2):                       # warm-up: eager rollout, then graph capture
+        learner.collect(); learner.update()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+    roll_s, upd_ms, ar_ms, gae_ms = 0.0, 0.0, 0.0, 0.0
+    t_all = time.perf_counter()
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        learner.collect()
+        roll_s += time.perf_counter() - t0
+        stats = learner.update()
+        upd_ms += sum(s.update_ms for s in stats.values())
+        ar_ms += sum(s.allreduce_ms for s in stats.values())
+        gae_ms += sum(s.gae_ms for s in stats.values())
+    torch.cuda.synchronize()
+    total_s = time.perf_counter() - t_all
+    clocks = sampler.stop()
+    t = torch.tensor([roll_s, total_s, upd_ms, ar_ms, gae_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    roll_s, total_s, upd_ms, ar_ms, gae_ms = (float(x) for x in t)
+    A = len(env.possible_agents)
+    steps = iters * cfg.rollouts
+    n_global = per_gpu * world_size
+    line = {"metric": "agent-steps/s inside MAPPO self-play training (env + policy / critic inference + recording)",
+            "value": n_global * A * steps / roll_s, "unit": "agent-steps/s", "n_gpus": world_size, "steps": steps,
+            "warmup": 2 * cfg.rollouts, "ms_per_step": roll_s / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 env, bf16-autocast update", "data": "synthetic",
+            "config": {"workload": TRAIN_WORKLOAD, "map": "agh-map", "worlds_per_gpu": per_gpu, "global_worlds": n_global,
+                       "rollouts": cfg.rollouts, "epochs": cfg.learning_epochs, "mini_batches": cfg.mini_batches,
+                       "parameters": learner.n_parameters(), "iterations_timed": iters,
+                       "parallelism": f"worlds sharded over {world_size} GPU(s); NCCL all-reduce of one flat fp32 gradient bucket per agent per minibatch"},
+            "training": {"including_updates_agent_steps_per_s": n_global * A * steps / total_s,
+                         "update_ms_per_iteration": upd_ms / iters, "allreduce_ms_per_iteration": ar_ms / iters,
+                         "gae_ms_per_iteration": gae_ms / iters, "rollout_ms_per_iteration": roll_s / iters * 1e3},
+            "clocks": clocks}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    env.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -490,6 +634,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == TRAIN_WORKLOAD:
+        run_training(args)
     else:
         run_b200(args)
 

@@ -665,6 +665,37 @@ void orc_step(const OrcEnv* e, OrcState* st, const int32_t* actions, OrcOut* out
   }
 }
 
+/* space.step(dt) alone (base_env.py:392 -> cpSpaceStep), every world: what the stand-in pymunk of the harness
+ * self-test (tests/fake_pymunk) and the multi-step checks call. */
+void orc_space_step(const OrcEnv* e, OrcState* st) {
+  int A = e->A, H = e->H;
+#pragma omp parallel for schedule(static)
+  for (int w = 0; w < st->n_worlds; ++w)
+    physics_step(e, st->pos + (size_t)w * A * 2, st->vel + (size_t)w * A * 2, st->vbias + (size_t)w * A * 2,
+                 st->tc + (size_t)w * A * 2, st->wall_jn + (size_t)w * A * H, st->wall_age + (size_t)w * A * H,
+                 st->pair_jn + (size_t)w * A * A, st->pair_age + (size_t)w * A * A);
+}
+
+/* space.point_query_nearest(p, max_distance, filter) (cpSpacePointQueryNearest): nearest shape with distance <
+ * max_distance; walls = hull distance - wall radius, agents = centre distance - radius, own shape excluded.
+ * Returns the shape id (-1 none; < H hull; H + j agent j) and its distance. */
+int orc_point_query_nearest(const OrcEnv* e, const double* tc, int self_agent, double px, double py, double maxd,
+                            double* dist_out) {
+  int best = -1;
+  double bd = maxd;
+  for (int h = 0; h < e->H; ++h) {
+    double d = hull_signed_distance(e, h, v2(px, py)) - e->p.wall_radius;
+    if (d < bd) { bd = d; best = h; }
+  }
+  for (int j = 0; j < e->A; ++j) {
+    if (j == self_agent) continue;
+    double d = vlen(vsub(v2(px, py), v2(tc[2 * j], tc[2 * j + 1]))) - e->p.unit_size;
+    if (d < bd) { bd = d; best = e->H + j; }
+  }
+  if (dist_out) *dist_out = bd;
+  return best;
+}
+
 /* ------------------------------------------------------------------ GAE (skrl MAPPO._update) */
 void orc_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values, float* returns,
              float* advantages, int T, int M, double gamma, double lam, int normalize) {

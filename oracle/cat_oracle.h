@@ -96,6 +96,11 @@ float orc_half_bits_to_float(uint16_t h);
 int orc_segment_query_first(const OrcEnv* env, const double* tc /*[A][2]*/, int self_agent /* -1: walls only */,
                             double ax, double ay, double bx, double by, double radius,
                             double* alpha, double* point /*[2]*/);
+/* cpSpaceStep alone for every world (no actions, no observations) */
+void orc_space_step(const OrcEnv* env, OrcState* st);
+/* nearest shape within maxd of a point (own shape excluded); returns shape id like orc_segment_query_first */
+int orc_point_query_nearest(const OrcEnv* env, const double* tc, int self_agent, double px, double py, double maxd,
+                            double* dist_out);
 /* signed distance from p to hull h (negative inside), raw hull (no radius) */
 double orc_hull_distance(const OrcEnv* env, int h, double px, double py);
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4);

@@ -86,6 +86,9 @@ def lib():
         _lib.orc_half_bits_to_float.argtypes = [C.c_uint16]
         _lib.orc_segment_query_first.restype = C.c_int
         _lib.orc_segment_query_first.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_void_p]
+        _lib.orc_space_step.argtypes = [C.c_void_p, C.POINTER(_OrcState)]
+        _lib.orc_point_query_nearest.restype = C.c_int
+        _lib.orc_point_query_nearest.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 3 + [C.c_void_p]
         _lib.orc_hull_distance.restype = C.c_double
         _lib.orc_hull_distance.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         _lib.orc_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
@@ -216,6 +219,18 @@ class Oracle:
         s = lib().orc_segment_query_first(self._h, _p(tc), self_agent, a[0], a[1], b[0], b[1], radius,
                                           C.addressof(alpha), _p(pt))
         return s, alpha.value, pt
+
+    def space_step(self, st: OracleState) -> None:
+        """``space.step(dt)`` alone (cpSpaceStep) for every world of ``st``."""
+        cs = st.c_struct()
+        lib().orc_space_step(self._h, C.byref(cs))
+
+    def point_query_nearest(self, tc: np.ndarray, self_agent: int, p, max_distance: float):
+        tc = np.ascontiguousarray(tc, np.float64)
+        d = C.c_double()
+        s = lib().orc_point_query_nearest(self._h, _p(tc), self_agent, float(p[0]), float(p[1]), float(max_distance),
+                                          C.addressof(d))
+        return s, d.value
 
     def hull_distance(self, h: int, p) -> float:
         return lib().orc_hull_distance(self._h, h, float(p[0]), float(p[1]))

@@ -19,6 +19,27 @@ pytestmark = pytest.mark.gpu
 
 VBIAS_ATOL = 2e-3   # v_bias = 6/s * penetration; penetration is resolved at fp32 position granularity (~6e-5 at x~1e3)
 
+# Exclusion budgets: what may be set aside as ε class, per comparison.  The observed rates of every
+# case are committed in profiles/parity_stats.json (written by this module when CAT_PARITY_STATS is set); the bounds
+# below are about twice the largest observed value.
+MAX_EPS_RAYS = 0.01          # rays whose oracle answer changes under a +-1e-3 nudge (observed <= 0.75 %)
+MAX_EPS_RAYS_DEGENERATE = 0.025   # agh-map's FILE spawns: two of three agents sit inside wall hulls, the third touches one
+                                  # (SURVEY.md §7 hard part 2) — rays start at / graze hull surfaces: observed 1.3 %
+MAX_PHYS_BAD = 0.02          # worlds whose oracle transition is discontinuous under the nudge (observed <= 0.9 %)
+MIN_RESPAWN_SAME = 0.995     # re-spawned worlds landing on the oracle's spawn point (fp32 vs fp64 rejection test)
+MAX_F16_FLIPS = 1e-3         # stable rays whose float16 distance differs from the oracle's by one quantisation step
+_STATS = {}
+
+
+def _record(label, stats):
+    import json
+    import os
+    path = os.environ.get("CAT_PARITY_STATS")
+    _STATS[label] = stats
+    if path:
+        with open(path, "w") as f:
+            json.dump(_STATS, f, indent=1, sort_keys=True)
+
 
 def _acts(rng, N, A, dev):
     a = rng.integers(0, 4, (N, A))
@@ -39,7 +60,7 @@ def _physics_unstable(orc, base_state, actions, ref_state, n_pert=3, eps=1e-3, t
     return bad
 
 
-def _compare_transition(cw, orc, rng, label):
+def _compare_transition(cw, orc, rng, label, max_eps=None):
     N, A = cw.n_worlds, cw.A
     st = cw.get_state()
     torch.cuda.synchronize()
@@ -59,7 +80,7 @@ def _compare_transition(cw, orc, rng, label):
     otype, odist = cw.obs_type.cpu().numpy(), cw.obs_dist.cpu().numpy()
     hp = cw.hit_point.cpu().numpy()
     unstable = pu.ray_unstable_mask(orc, base, pre.hit_alpha, pre.obs_type)
-    assert unstable.mean() < 0.03, f"{label}: ε-class unexpectedly large ({unstable.mean():.3%})"
+    assert unstable.mean() <= (max_eps or MAX_EPS_RAYS), f"{label}: ε-class unexpectedly large ({unstable.mean():.3%})"
     ok = ~unstable & ndr
     # --- object types and hit points (pre-quantisation)
     assert not ((otype != oout.obs_type) & ok).any(), f"{label}: object type mismatch on stable rays"
@@ -74,9 +95,10 @@ def _compare_transition(cw, orc, rng, label):
     # ... and within one f16 step of the oracle's (quantisation can flip on a 1e-4 fp32/fp64 difference)
     dq = np.abs(odist.astype(np.float32) - oout.obs_dist.astype(np.float32))
     assert dq[ok].max(initial=0.0) <= 1.5, f"{label}: f16 distance far from oracle"
-    assert (dq[ok] > 0).mean() < 2e-3
+    assert (dq[ok] > 0).mean() <= MAX_F16_FLIPS
     # --- flags, winner, counters
     phys_bad = _physics_unstable(orc, base, acts_np, ost)
+    assert phys_bad.mean() <= MAX_PHYS_BAD, f"{label}: {phys_bad.sum()} of {N} worlds in the physics ε class"
     good = ~phys_bad
     for k in ("terminated", "truncated", "winner"):
         assert np.array_equal(getattr(cw, k).cpu().numpy()[good], getattr(oout, k)[good]), f"{label}: {k}"
@@ -94,25 +116,34 @@ def _compare_transition(cw, orc, rng, label):
     np.testing.assert_allclose(rw[stable_worlds], oout.reward[stable_worlds], atol=pu.REWARD_ATOL)
     # --- physics
     sel = good & nd
-    assert sel.mean() > 0.9
+    max_rel = {}
     for k in ("pos", "vel"):
         c = st2[k].cpu().numpy().astype(np.float64)[sel]
         o = getattr(ost, k)[sel]
         rel = np.abs(c - o) / np.maximum(1.0, np.abs(o))
+        max_rel[k] = rel.max(initial=0.0)
         assert rel.max(initial=0.0) <= pu.POS_RTOL, f"{label}: {k} rel err {rel.max():.3e}"
     np.testing.assert_allclose(st2["vbias"].cpu().numpy()[sel], ost.vbias[sel], atol=VBIAS_ATOL)
     np.testing.assert_allclose(st2["tc"].cpu().numpy()[sel], ost.tc[sel], rtol=pu.POS_RTOL)
     # --- worlds that re-spawned: same sampled positions (fp32 fma sampling is bit-reproducible)
     rs = good & ~nd
+    respawn_same = 1.0
     if rs.any():
         same = np.abs(st2["pos"].cpu().numpy()[rs] - ost.pos[rs]).max(axis=(1, 2)) <= 1e-4
-        assert same.mean() >= 0.98, f"{label}: re-spawn positions differ in {(~same).sum()} of {same.size} worlds"
+        respawn_same = float(same.mean())
+        assert respawn_same >= MIN_RESPAWN_SAME or (~same).sum() <= 1, \
+            f"{label}: re-spawn positions differ in {(~same).sum()} of {same.size} worlds"
         assert np.all(st2["vel"].cpu().numpy()[rs] == 0)
     # --- arbiter cache bookkeeping (same contacts cached, same ages)
     wh = st2["wall_hull"].cpu().numpy()
     assert (wh[sel] >= 0).sum() == (ost.wall_age[sel] >= 0).sum(), f"{label}: cached wall arbiters differ"
-    return dict(unstable=float(unstable.mean()), phys_bad=int(phys_bad.sum()), done=int((~nd).sum()),
-                max_hit_err=float(err[hit].max(initial=0.0)))
+    oc = cw.overflow_counts()
+    stats = dict(worlds=int(N), eps_rays=float(unstable.mean()), phys_bad=float(phys_bad.mean()), done=int((~nd).sum()),
+                 respawn_same=respawn_same, f16_flips=float((dq[ok] > 0).mean()), max_hit_err=float(err[hit].max(initial=0.0)),
+                 max_pos_rel=float(max_rel["pos"]), max_vel_rel=float(max_rel["vel"]),
+                 overflow_wall_slots=oc[0], overflow_near_slots=oc[1])
+    _record(label, stats)
+    return stats
 
 
 CASES = [("squarinth", False, 4096, (0, 49, 150)),      # BASELINE config 2: all 4096 worlds at steps 1, 50, 200
@@ -133,8 +164,12 @@ def test_single_step_transition_parity(cuda_device, name, free, N, gaps):
     for gap in gaps:
         for _ in range(gap):
             cw.step(_acts(rng, N, cw.A, cw.device)[1])
-        stats = _compare_transition(cw, orc, rng, f"{name}@+{gap}")
+        stats = _compare_transition(cw, orc, rng, f"{name}{'-free' if free else ''}@+{gap}",
+                                    max_eps=MAX_EPS_RAYS_DEGENERATE if (name, free) == ("agh-map", False) else None)
         print(name, gap, stats)
+    # the fixed per-agent capacities (CAT_WALL_SLOTS contacts, CAT_NEAR_SLOTS near hulls) were never exceeded — also
+    # not on agh-map's file spawns, where agents start inside overlapping convexified hulls
+    assert cw.overflow_counts() == (0, 0), f"{name}: capacity overflows {cw.overflow_counts()}"
     cw.close()
 
 

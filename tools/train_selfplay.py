@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--archive", default="policy_archive")
     ap.add_argument("--free-spawn", type=int, default=1)
     ap.add_argument("--autocast", default="none", choices=["none", "bf16"])
+    ap.add_argument("--schedule", default="scaled", choices=["scaled", "reference", "off"],
+                    help="random_timesteps / learning_starts / freeze durations: the reference's values divided by the "
+                         "number of worlds (same number of transitions), the reference's values as they are, or none")
     a = ap.parse_args()
 
     rank, local_rank, world_size = dist_env()
@@ -52,8 +55,15 @@ def main():
     gid0, n_local = shard_range(a.worlds * world_size, rank, world_size)
     env = BatchedCopsThievesEnv(m, n_local, device=dev, seed=0, gid0=gid0, max_step_count=a.max_step_count,
                                 spawn_override=free_space_regions(m) if a.free_spawn else None)
+    # the reference's schedule (10 000 random / 15 000 before learning / 15 000 frozen policy) counts steps of ONE
+    # environment; with thousands of lockstep worlds the same number of TRANSITIONS is reached in a few steps, so the
+    # driver scales the durations by the world count unless told otherwise
+    scale = max(1, a.worlds * world_size) if a.schedule == "scaled" else 1
     cfg = MAPPOConfig(rollouts=a.rollouts, model=a.model, distributed=world_size > 1, world_size=world_size,
-                      update_autocast=a.autocast)
+                      update_autocast=a.autocast, random_timesteps=-(-10000 // scale) if a.schedule != "off" else 0,
+                      learning_starts=-(-15000 // scale) if a.schedule != "off" else 0,
+                      policy_freeze_duration=-(-15000 // scale) if a.schedule != "off" else 0,
+                      opponent_freeze_duration=-(-15000 // scale) if a.schedule != "off" else 0)
     learner = MAPPOLearner(env, cfg, seed=0)
     archive = Path(a.archive) if rank == 0 else Path(a.archive + f".rank{rank}")
     for it in range(a.iterations):
