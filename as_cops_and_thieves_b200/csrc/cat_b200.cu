@@ -301,6 +301,7 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
     CREATE_TRY(cudaMemcpy(env->ray_slots_dev, rl.slots.data(), rl.slots.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(ray lists)");
     CREATE_TRY(cudaMemcpy(env->ray_ovf_dev, rl.ovf.data(), rl.ovf.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(ray lists)");
     k.ray_slots = env->ray_slots_dev; k.ray_ovf = env->ray_ovf_dev;
+    k.ray_slot_count = (unsigned)(rl.slots.size() / 4); k.ray_ovf_words = (unsigned)rl.ovf.size();
     k.rg_x0 = rl.g.x0; k.rg_y0 = rl.g.y0; k.rg_inv_cell = rl.g.inv_cell; k.rg_nx = rl.g.nx; k.rg_ny = rl.g.ny;
     inf.ray_list_cells = rl.g.nx * rl.g.ny; inf.ray_list_nx = rl.g.nx; inf.ray_list_ny = rl.g.ny; inf.ray_list_cell = rl.g.cell;
     inf.ray_list_bytes = (int64_t)(rl.slots.size() + rl.ovf.size()) * 4;

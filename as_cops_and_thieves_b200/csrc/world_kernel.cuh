@@ -22,8 +22,12 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2, MODE_INIT = 3 };
 #ifdef CAT_STATS   // developer build only (tools/raster_stats.py): rasteriser work counters
 __device__ unsigned long long g_stats[8];
 #define CAT_COUNT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+// index / capacity assertions of the checked build (tools/bounds_check.py): a violation is COUNTED (g_stats[6], with the
+// source line of the last one in g_stats[7]) instead of trapping, so one run reports all of them and the context survives
+#define CAT_CHECK(cond) do { if (!(cond)) { atomicAdd(&g_stats[6], 1ull); g_stats[7] = __LINE__; } } while (0)
 #else
 #define CAT_COUNT(i, v)
+#define CAT_CHECK(cond)
 #endif
 
 // ------------------------------------------------------------------ shared-memory map blob
@@ -54,6 +58,7 @@ struct MapView {
   const float2* init_pos;
   int H, nx, ny;
   float gx0, gy0, cell, inv_cell;
+  int n_edges_dbg;
 };
 
 struct KParams {
@@ -66,6 +71,7 @@ struct KParams {
   const uint32_t* ray_ovf;
   float rg_x0, rg_y0, rg_inv_cell;
   int rg_nx, rg_ny;
+  unsigned int ray_slot_count, ray_ovf_words;   // sizes of the two arrays (checked build only)
   unsigned long long* overflow;  // [2] wall-contact / near-hull slots exceeded (cat_env_overflow_counts)
   float* state;
   int rec_words;
@@ -131,7 +137,7 @@ __device__ __forceinline__ MapView make_view(const unsigned char* blob) {
   m.reg_off = reinterpret_cast<const int32_t*>(blob + h->off_regoff);
   m.regions = reinterpret_cast<const float4*>(blob + h->off_regions);
   m.init_pos = reinterpret_cast<const float2*>(blob + h->off_initpos);
-  m.H = h->n_hulls; m.nx = h->nx; m.ny = h->ny;
+  m.H = h->n_hulls; m.nx = h->nx; m.ny = h->ny; m.n_edges_dbg = h->n_edges;
   m.gx0 = h->gx0; m.gy0 = h->gy0; m.cell = h->cell; m.inv_cell = h->inv_cell;
   return m;
 }
@@ -421,6 +427,7 @@ __device__ __noinline__ void raster_batch(const unsigned char* blob, unsigned lo
     if (p < total) {
       int i = i0l + (p - exl);
       if (i >= R) i -= R;
+      CAT_CHECK(i >= 0 && i < R && el >= 0 && el < m.n_edges_dbg);
       const float4 dv = m.dir[i];
       Ray r;
       r.ox = ox; r.oy = oy; r.ux = dv.x; r.uy = dv.y; r.L = L;
@@ -516,6 +523,7 @@ __device__ __noinline__ void rasterise_agent(const KParams& k, const unsigned ch
       is_cand = (pd > 0.f || pdn > 0.f) && (fmaf(pd, pd, dq * dq) < range2);
     }
     const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
+    CAT_CHECK(ncand + __popc(cmask) <= 64);
     if (is_cand) w.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)e;
     ncand += __popc(cmask);
     __syncwarp();
@@ -579,6 +587,7 @@ __device__ __forceinline__ void stage_ray_slots(const KParams& k, const Warp& w,
     const int ba = __shfl_sync(0xFFFFFFFFu, base, a);
     uint4* dst = reinterpret_cast<uint4*>(w.best) + a * R;
     if (ba >= 0) {
+      CAT_CHECK((unsigned)(ba + R) <= k.ray_slot_count && (a + 1) * R * 16 <= k.nrays_pad * 16);
       if (lane == 0)
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                      "l"(k.ray_slots + ba), "r"(R * 16), "r"(bar)
@@ -645,6 +654,7 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
     if (cur >= 0) {
       uint32_t ent = e0;
       if (__builtin_expect((int)ent < 0, 0)) {   // link: the list continues in a chunk of the overflow array
+        CAT_CHECK((ent & 0x7FFFFFFFu) + 4u <= k.ray_ovf_words && ((ent & 3u) == 0u));
         const uint4 c = __ldg(reinterpret_cast<const uint4*>(k.ray_ovf + (ent & 0x7FFFFFFFu)));
         ent = c.x; e1 = c.y; e2 = c.z; e3 = c.w;
       }
@@ -652,6 +662,7 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
       if (__uint_as_float(bs) < __uint_as_float(ent & 0xFFFF0000u)) fin = true;   // (an empty list: its first entry is the end mark)
       else {
         const uint32_t el = ent & 0xFFFFu;
+        CAT_CHECK((int)el < k.n_edges && cur < nrays);
         Ray r;
         r.ox = ox; r.oy = oy; r.ux = ux; r.uy = uy; r.L = L;
         int kind;
@@ -853,6 +864,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
           // rewards need the nearest opponent seen by this agent (cop.py:66-70, thief.py:60-63)
           if (type == want) atomicMin(&w.minbits[a], (uint32_t)dbits);
         }
+        CAT_CHECK(r < k.nrays && (feat == kNoFeature || feat >= kAgentTag || (int)(feat >> 1) < k.n_edges));
         w.rdist[r] = dbits;
         w.rtype[r] = type;
         if (k.hit_point) {
@@ -1108,6 +1120,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
       if (hit) {
         const uint32_t rank = w.ccount[a] + __popc(hits & same & ((1u << lane) - 1u));
         if (rank < (uint32_t)kSlots) {
+          CAT_CHECK(a >= 0 && a < A && (a * kSlots + (int)rank) < k.maxc && h >= 0 && h < m.H);
           float* c = w.con + (a * kSlots + rank) * 8;
           c[0] = nx; c[1] = ny; c[2] = d;
           reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)h;

@@ -28,6 +28,16 @@ from .worlds import CatWorlds
 
 OBJECT_TYPE_MAX = 4  # ObjectType.EMPTY (utils/object_types.py:4-9)
 
+# The reference's BaseEnv IS a pettingzoo.ParallelEnv (base_env.py:30), and skrl's wrap_env(env, wrapper="pettingzoo")
+# (self_play_driver.py:35) checks for it.  Subclass the real class wherever pettingzoo is importable; this image has
+# none, so the surface is duck-typed here and the base class is a plain object.
+try:  # pragma: no cover - exercised only where pettingzoo exists
+    from pettingzoo import ParallelEnv as _ParallelEnvBase  # type: ignore
+    HAVE_PETTINGZOO = True
+except Exception:
+    _ParallelEnvBase = object
+    HAVE_PETTINGZOO = False
+
 
 def _agent_observation_space(n_rays: int, ray_length: float) -> "spaces.Dict":
     # entity.py:92-107
@@ -105,8 +115,9 @@ def _make_params(max_step_count: int, time_step: float, physical: Optional[dict]
     return p
 
 
-class BaseEnv(_EnvCommon):
-    """Single-world PettingZoo ``ParallelEnv`` face (``base_env.py:30``).  Needs a CUDA device."""
+class BaseEnv(_EnvCommon, _ParallelEnvBase):
+    """Single-world PettingZoo ``ParallelEnv`` face (``base_env.py:30``): a real ``pettingzoo.ParallelEnv`` subclass
+    when pettingzoo is importable (``HAVE_PETTINGZOO``), the same surface duck-typed otherwise.  Needs a CUDA device."""
 
     def __init__(self, map: Map, map_image=None, render_mode=None, max_step_count: int = 400,
                  time_step: float = 1 / 15.0, *, device: Union[str, torch.device] = "cuda:0",
@@ -232,7 +243,7 @@ class SimpleEnv(BaseEnv):
         return info
 
 
-class BatchedCopsThievesEnv(_EnvCommon):
+class BatchedCopsThievesEnv(_EnvCommon, _ParallelEnvBase):
     """N worlds behind the surface skrl's multi-agent trainers use.
 
     ``agents`` never empties: finished worlds are re-spawned inside the step kernel and report the

@@ -8,9 +8,10 @@ import parity_utils as pu
 from as_cops_and_thieves_b200 import spaces
 from as_cops_and_thieves_b200.env import BatchedCopsThievesEnv, SimpleEnv, BaseEnv
 from as_cops_and_thieves_b200.gae import compute_gae
-from as_cops_and_thieves_b200.maps import load_named_map, free_space_regions, Map
+from as_cops_and_thieves_b200.maps import compile_map, load_named_map, free_space_regions, Map
 from as_cops_and_thieves_b200.worlds import CatWorlds
 from oracle import cat_oracle as co
+from oracle.cat_oracle import Oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -316,3 +317,90 @@ def test_full_size_properties(cuda_device, name, free, N, T):
     print(name, "episodes", done_total, "captures", cops_won)
     w.close()
     w2.close()
+
+
+def test_two_environments_on_different_maps_stay_usable(cuda_device):
+    """the kernel's dynamic shared-memory cap is a per-function attribute; creating an environment for a
+    SMALLER map must not lower it under one that is still alive (agh-map needs ~20 KB more per CTA than squarinth)."""
+    big = CatWorlds(pu.named_cmap("agh-map", free_spawn=True), 256, device=cuda_device, seed=1)
+    big.reset()
+    small = CatWorlds(pu.named_cmap("squarinth"), 256, device=cuda_device, seed=1)
+    small.reset()
+    a = torch.ones((256, 3), dtype=torch.uint8, device=cuda_device)
+    for _ in range(3):
+        big.step(a)
+        small.step(a)
+    torch.cuda.synchronize()
+    # (a world that ended meanwhile restarted its count: look at the maximum)
+    assert int(big.get_state()["step_count"].max()) == 3 and int(small.get_state()["step_count"].max()) == 3
+    big.close()
+    small.step(a)           # destroying one environment leaves the other alone
+    torch.cuda.synchronize()
+    small.close()
+
+
+def test_reset_with_a_seed_reproduces_the_spawn(cuda_device):
+    """base_env.py:307-311 re-creates np_random from the seed: reset(seed=s) restarts the spawn stream.  (The reference
+    itself is NOT reproducible — it draws the point from the unseeded global `random`; here the Philox
+    stream is keyed by (seed, world, episode), and reset(seed) restarts the episode counter.)  With the shape cache kept
+    fresh the spawn depends on nothing else, so two resets agree exactly; with pymunk's stale cache (default) the
+    rejection test also looks at where the OTHER agents were before the reset, so a few worlds may differ."""
+    env = BatchedCopsThievesEnv(load_named_map("squarinth"), 128, device=cuda_device, seed=0, stale_shape_cache=False)
+    o1, _ = env.reset(seed=42)
+    first = {k: v.clone() for k, v in o1.items()}
+    p1 = env.worlds.get_state()["pos"].clone()
+    for _ in range(5):
+        env.step(torch.ones((128, 3), dtype=torch.uint8, device=cuda_device))
+    o2, _ = env.reset(seed=42)
+    assert torch.equal(env.worlds.get_state()["pos"], p1)
+    assert all(torch.equal(first[k], o2[k]) for k in first)
+    env.reset(seed=43)
+    assert not torch.equal(env.worlds.get_state()["pos"], p1)
+    env.close()
+    stale = BatchedCopsThievesEnv(load_named_map("squarinth"), 512, device=cuda_device, seed=0)
+    stale.reset(seed=42)
+    p1 = stale.worlds.get_state()["pos"].clone()
+    for _ in range(5):
+        stale.step(torch.ones((512, 3), dtype=torch.uint8, device=cuda_device))
+    stale.reset(seed=42)
+    same = (stale.worlds.get_state()["pos"] == p1).all(dim=2).all(dim=1)
+    assert float(same.float().mean()) > 0.9
+    stale.close()
+    single = SimpleEnv(load_named_map("squarinth"), device=cuda_device, stale_shape_cache=False)
+    a, _ = single.reset(seed=7)
+    single.step({k: 1 for k in single.possible_agents})
+    b, _ = single.reset(seed=7)
+    assert all(np.array_equal(a[k]["distance"], b[k]["distance"]) for k in a)
+    single.close()
+
+
+def test_fresh_shape_cache_spawns_one_agent_after_the_other(cuda_device):
+    """with stale_shape_cache = 0 agent j's spawn test must see the NEW positions of agents i < j (the
+    reference resets them in order); the oracle does, and the kernel must land on the same points bit for bit — and
+    never on top of each other."""
+    import json
+    m = json.loads(json.dumps(pu.random_map_json(3, n_blocks=4)))
+    for a in m["agents"]:                       # one small shared region: collisions between spawns are the norm
+        a["spawn_region"] = {"x": 60.0, "y": 60.0, "w": 40.0, "h": 40.0}
+    import tempfile
+    from as_cops_and_thieves_b200.maps import Map
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(m, f)
+    cmap = compile_map(Map(f.name), name="crowded")
+    N = 512
+    cw = CatWorlds(cmap, N, device=cuda_device, seed=12, stale_shape_cache=0)
+    orc = Oracle(cmap, seed=12, stale_shape_cache=0)
+    ost = orc.new_state(N)
+    for _ in range(3):
+        cw.reset()
+        orc.reset(ost)
+        pos = cw.get_state()["pos"].cpu().numpy().astype(np.float64)
+        assert np.array_equal(pos, ost.pos)
+    d01 = np.linalg.norm(pos[:, 0] - pos[:, 1], axis=-1)
+    d02 = np.linalg.norm(pos[:, 0] - pos[:, 2], axis=-1)
+    d12 = np.linalg.norm(pos[:, 1] - pos[:, 2], axis=-1)
+    # an accepted sample keeps >= 10 between centres; only the 20-tries-failed fallback (region centre) may overlap
+    centre = np.array([80.0, 80.0])
+    fell_back = (np.abs(pos - centre).max(axis=-1) < 1e-6).any(axis=1)
+    assert (np.minimum(np.minimum(d01, d02), d12)[~fell_back] >= 10.0 - 1e-4).all()
+    cw.close()
