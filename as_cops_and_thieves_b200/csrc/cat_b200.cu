@@ -570,8 +570,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 static bool gae_tma_usable(const void* r, const void* d, const void* v, int M) {
-  const char* env = getenv("CAT_GAE_TMA");
-  if (env && env[0] == '0') return false;                                  // opt-out (A/B against the register-pipelined kernel)
+  const char* env = getenv("CAT_GAE_TMA");   // opt-out (A/B against the register-pipelined kernel); a libc table look-up, ~50 ns
+  if (env && env[0] == '0') return false;
   if (M % 16 != 0) return false;                                           // u8 row stride must be a multiple of 16 bytes
   if ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(v)) & 15) return false;
   return tensor_map_encoder() != nullptr;
@@ -602,13 +602,19 @@ int cat_gae(const float* rewards, const uint8_t* dones, const float* values, con
     if (encode_2d(&tm_r, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rewards, M, T, 4) && encode_2d(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, values, M, T, 4) &&
         encode_2d(&tm_d, CU_TENSOR_MAP_DATA_TYPE_UINT8, dones, M, T, 1)) {
       const int smem = kTmaStages * kTmaStageBytes, tblocks = (M + kTmaCols - 1) / kTmaCols;
-      if (idx32) {
+      // the shared-memory opt-in is a per-function, per-device attribute: set once per device, not per call
+      static bool attr_set[64] = {false};
+      int devid = 0;
+      CUDA_TRY(cudaGetDevice(&devid));
+      if (devid < 0 || devid >= 64 || !attr_set[devid]) {
         CUDA_TRY(cudaFuncSetAttribute(cat_gae_tma_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        cat_gae_tma_kernel<uint32_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
-      } else {
         CUDA_TRY(cudaFuncSetAttribute(cat_gae_tma_kernel<size_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        cat_gae_tma_kernel<size_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+        if (devid >= 0 && devid < 64) attr_set[devid] = true;
       }
+      if (idx32)
+        cat_gae_tma_kernel<uint32_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+      else
+        cat_gae_tma_kernel<size_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
       CUDA_TRY(cudaGetLastError());
       return CAT_OK;
     }
