@@ -119,7 +119,7 @@ static bool pick_launch_shape(CatEnv* env, int n_worlds, LaunchShape* out) {
   int wpc_max = kMaxThreads / 32;
   if (const char* e = getenv("CAT_MAX_WARPS_PER_CTA")) { const int v = atoi(e); if (v >= 2 && v < wpc_max) wpc_max = v; }   // tuning knob
   for (int wpc = wpc_max; wpc >= 2; --wpc) {   // any warp count: 4096 worlds = 586 CTAs of 7 warps = 28 warps per SM
-    const int smem = align_up(env->blob_bytes, 128) + wpc * env->kp.scratch_bytes;
+    const int smem = align_up(env->blob_bytes, 128) + wpc * env->kp.lay.scratch_bytes;
     if (smem > env->max_optin) continue;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env->kernel, wpc * 32, smem) != cudaSuccess || occ < 1) continue;
@@ -307,37 +307,13 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
     inf.ray_list_bytes = (int64_t)(rl.slots.size() + rl.ovf.size()) * 4;
   }
   k.n_worlds = n_worlds; k.gid0 = gid0;
-  k.A = A; k.nc = map->n_cops; k.R = R; k.P = P; k.nrays = A * R; k.nrays_pad = align_up(A * R, 32);
-  k.maxc = A * kSlots + P;
+  k.A = A; k.nc = map->n_cops; k.R = R;
   k.n_edges = E;
-  // record layout (4-byte words)
-  k.o_vel = 2 * A; k.o_vb = 4 * A; k.o_tc = 6 * A; k.o_wkey = 8 * A; k.o_wjn = 8 * A + A * kSlots;
-  k.o_page = 8 * A + 2 * A * kSlots; k.o_pjn = k.o_page + P; k.o_sc = k.o_pjn + P; k.o_ep = k.o_sc + 1; k.o_flags = k.o_ep + 1;
-  k.o_near = k.o_flags + 1;                                   // u16 [A][kNear]: hulls within ray_r of each body (0xFFFF = none)
-  k.rec_words = align_up(k.o_near + (A * kNear + 1) / 2, 32);
-  // scratch layout (bytes)
-  int so = k.rec_words * 4;
-  auto stake = [&](int bytes) { int o = so; so = align_up(so + bytes, 16); return o; };
-  // the world's output record is staged contiguously (CatRecordLayout): f16 distances | u8 types | f32 rewards | flags
+  k.lay = make_layout(A, R);          // record / scratch / output-record offsets (world_kernel.cuh)
   CatRecordLayout& rc = env->rec;
-  rc.off_dist = 0;
-  rc.off_type = align_up(k.nrays * 2, 16);
-  rc.off_reward = align_up(rc.off_type + k.nrays, 4);
-  rc.off_terminated = rc.off_reward + 4 * A; rc.off_truncated = rc.off_terminated + 1; rc.off_winner = rc.off_terminated + 2;
-  rc.bytes = align_up(rc.off_terminated + 3, 16);
-  k.r_bytes = rc.bytes; k.r_off_reward = rc.off_reward; k.r_off_flags = rc.off_terminated;
-  k.s_rdist = stake(rc.bytes);
-  k.s_rtype = k.s_rdist + rc.off_type;
-  k.s_min = stake(CAT_MAX_AGENTS * 4);
-  k.s_rcell = stake(CAT_MAX_AGENTS * 4);
-  k.s_nearcnt = stake(CAT_MAX_AGENTS * 4);
-  k.s_con = stake(k.maxc * 32);
-  k.s_ccount = stake(CAT_MAX_AGENTS * 4);
-  k.s_order = stake(k.maxc);
-  // per-ray hit keys (8 B each); with ray lists the same area first holds the rays' 16-byte candidate slots
-  k.s_best = stake(k.ray_slots ? k.nrays_pad * 16 : k.nrays_pad * 8);
-  k.s_cand = stake(64 * 2);
-  k.scratch_bytes = align_up(so, 128);
+  rc.off_dist = 0; rc.off_type = k.lay.r_off_type; rc.off_reward = k.lay.r_off_reward;
+  rc.off_terminated = k.lay.r_off_flags; rc.off_truncated = k.lay.r_off_flags + 1; rc.off_winner = k.lay.r_off_flags + 2;
+  rc.bytes = k.lay.r_bytes;
   k.state_dim = 0;
   for (int a = 0; a < A; ++a) k.state_dim += 4 * R + 2 * (a < map->n_cops ? map->n_cops : map->n_thieves);
   k.dt = (float)pr->dt; k.inv_dt = (float)(1.0 / pr->dt);
@@ -355,8 +331,8 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   int max_optin = 0, n_sm = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-  const int smem_max = align_up(blob_bytes, 128) + 2 * k.scratch_bytes;
-  if (align_up(blob_bytes, 128) + 2 * k.scratch_bytes > max_optin) {
+  const int smem_max = align_up(blob_bytes, 128) + 2 * k.lay.scratch_bytes;
+  if (align_up(blob_bytes, 128) + 2 * k.lay.scratch_bytes > max_optin) {
     cat_env_destroy(env);
     return fail(CAT_ERR_LIMIT, "map does not fit in shared memory (" + std::to_string(smem_max) + " B)");
   }
@@ -374,7 +350,7 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   k.world_begin = 0; k.world_end = n_worlds;
 
   inf.n_worlds = n_worlds; inf.n_agents = A; inf.n_cops = map->n_cops; inf.n_thieves = map->n_thieves;
-  inf.n_rays = R; inf.n_hulls = H; inf.n_edges = E; inf.state_dim = k.state_dim; inf.record_words = k.rec_words;
+  inf.n_rays = R; inf.n_hulls = H; inf.n_edges = E; inf.state_dim = k.state_dim; inf.record_words = k.lay.rec_words;
   inf.map_blob_bytes = blob_bytes; inf.smem_bytes_per_cta = env->smem_bytes; inf.warps_per_cta = env->threads / 32;
   inf.grid = env->grid; inf.n_pairs = P;
 #undef CREATE_TRY
@@ -428,7 +404,7 @@ int cat_env_set_seed(CatEnv* env, uint64_t seed) {
 }
 
 size_t cat_env_state_bytes(const CatEnv* env) {
-  return env ? (size_t)env->n_worlds * env->kp.rec_words * 4 : 0;
+  return env ? (size_t)env->n_worlds * env->kp.lay.rec_words * 4 : 0;
 }
 
 static int prepare(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, KParams* out) {
@@ -446,21 +422,21 @@ static int prepare(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, 
     }
     k.reset_mask = io->reset_mask;
     k.obs_dist = io->obs_dist; k.obs_type = io->obs_type; k.reward = io->reward;
-    k.dist_stride = io->obs_dist_world_stride ? io->obs_dist_world_stride : k.nrays * 2;
-    k.type_stride = io->obs_type_world_stride ? io->obs_type_world_stride : k.nrays;
-    if (k.dist_stride < k.nrays * 2 || (k.dist_stride & 1) || k.type_stride < k.nrays)
+    k.dist_stride = io->obs_dist_world_stride ? io->obs_dist_world_stride : k.lay.nrays * 2;
+    k.type_stride = io->obs_type_world_stride ? io->obs_type_world_stride : k.lay.nrays;
+    if (k.dist_stride < k.lay.nrays * 2 || (k.dist_stride & 1) || k.type_stride < k.lay.nrays)
       return fail(CAT_ERR_INVALID, "observation world strides are smaller than one world's block");
     k.obs_vec = ((k.dist_stride | k.type_stride) & 15) == 0 &&
                 ((reinterpret_cast<uintptr_t>(io->obs_dist) | reinterpret_cast<uintptr_t>(io->obs_type)) & 15) == 0 &&
-                k.dist_stride >= (k.nrays * 2 + 15) / 16 * 16 && k.type_stride >= (k.nrays + 15) / 16 * 16;
+                k.dist_stride >= (k.lay.nrays * 2 + 15) / 16 * 16 && k.type_stride >= (k.lay.nrays + 15) / 16 * 16;
     k.terminated = io->terminated;
     k.truncated = io->truncated; k.winner = io->winner; k.shared_dist = io->shared_dist; k.shared_type = io->shared_type;
     k.team_pos = io->team_pos; k.obs_f32 = io->obs_f32; k.state_f32 = io->state_f32; k.hit_point = io->hit_point;
     k.critic_f32 = io->critic_f32; k.obs_bf16 = io->obs_bf16; k.critic_bf16 = io->critic_bf16;
     if (io->record) {
       k.record = reinterpret_cast<unsigned char*>(io->record);
-      k.record_stride = io->record_world_stride ? io->record_world_stride : k.r_bytes;
-      if ((reinterpret_cast<uintptr_t>(io->record) & 15) || (k.record_stride & 15) || k.record_stride < k.r_bytes)
+      k.record_stride = io->record_world_stride ? io->record_world_stride : k.lay.r_bytes;
+      if ((reinterpret_cast<uintptr_t>(io->record) & 15) || (k.record_stride & 15) || k.record_stride < k.lay.r_bytes)
         return fail(CAT_ERR_INVALID, "record output must be 16-byte aligned with a world stride that is a multiple of 16 and >= CatRecordLayout.bytes");
       k.obs_dist = nullptr; k.obs_type = nullptr; k.reward = nullptr; k.terminated = nullptr; k.truncated = nullptr; k.winner = nullptr;
     }
@@ -537,9 +513,9 @@ static int state_view(CatEnv* env, void* state_dev, const CatStateView* view, in
   const KParams& k = env->kp;
   ViewParams p{};
   p.state = reinterpret_cast<float*>(state_dev);
-  p.rec_words = k.rec_words; p.n_worlds = k.n_worlds; p.A = k.A; p.P = k.P;
-  p.o_vel = k.o_vel; p.o_vb = k.o_vb; p.o_tc = k.o_tc; p.o_wkey = k.o_wkey; p.o_wjn = k.o_wjn;
-  p.o_page = k.o_page; p.o_pjn = k.o_pjn; p.o_sc = k.o_sc; p.o_ep = k.o_ep; p.o_flags = k.o_flags;
+  p.rec_words = k.lay.rec_words; p.n_worlds = k.n_worlds; p.A = k.A; p.P = k.lay.P;
+  p.o_vel = k.lay.o_vel; p.o_vb = k.lay.o_vb; p.o_tc = k.lay.o_tc; p.o_wkey = k.lay.o_wkey; p.o_wjn = k.lay.o_wjn;
+  p.o_page = k.lay.o_page; p.o_pjn = k.lay.o_pjn; p.o_sc = k.lay.o_sc; p.o_ep = k.lay.o_ep; p.o_flags = k.lay.o_flags;
   p.v = *view; p.set = set;
   DEVICE_SCOPE(env);
   const int threads = 128, blocks = (k.n_worlds + threads - 1) / threads;

@@ -61,6 +61,48 @@ struct MapView {
   int n_edges_dbg;
 };
 
+// Word offsets inside a world's packed state record and byte offsets inside a warp's scratch area — ONE definition,
+// evaluated by the host for every environment (into KParams) and at COMPILE TIME by the kernel instantiation for the
+// shipped shape, where every offset then is an immediate instead of a constant-bank load + add.
+struct Layout {
+  int P, nrays, nrays_pad, maxc;
+  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags, o_near, rec_words;
+  int r_bytes, r_off_type, r_off_reward, r_off_flags;
+  int s_rdist, s_rtype, s_min, s_rcell, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, scratch_bytes;
+};
+__host__ __device__ constexpr int layout_align(int v, int a) { return (v + a - 1) / a * a; }
+__host__ __device__ constexpr Layout make_layout(int A, int R) {
+  Layout l{};
+  l.P = A * (A - 1) / 2; l.nrays = A * R; l.nrays_pad = layout_align(A * R, 32); l.maxc = A * kSlots + l.P;
+  l.o_vel = 2 * A; l.o_vb = 4 * A; l.o_tc = 6 * A; l.o_wkey = 8 * A; l.o_wjn = 8 * A + A * kSlots;
+  l.o_page = 8 * A + 2 * A * kSlots; l.o_pjn = l.o_page + l.P; l.o_sc = l.o_pjn + l.P; l.o_ep = l.o_sc + 1; l.o_flags = l.o_ep + 1;
+  l.o_near = l.o_flags + 1;                                   // u16 [A][kNear]: hulls within ray_r of each body (0xFFFF = none)
+  l.rec_words = layout_align(l.o_near + (A * kNear + 1) / 2, 32);
+  // the world's output record, staged contiguously (CatRecordLayout): f16 distances | u8 types | f32 rewards | flags
+  l.r_off_type = layout_align(l.nrays * 2, 16);
+  l.r_off_reward = layout_align(l.r_off_type + l.nrays, 4);
+  l.r_off_flags = l.r_off_reward + 4 * A;
+  l.r_bytes = layout_align(l.r_off_flags + 3, 16);
+  int so = l.rec_words * 4;
+  l.s_rdist = so; so = layout_align(so + l.r_bytes, 16);
+  l.s_rtype = l.s_rdist + l.r_off_type;
+  l.s_min = so; so = layout_align(so + CAT_MAX_AGENTS * 4, 16);
+  l.s_rcell = so; so = layout_align(so + CAT_MAX_AGENTS * 4, 16);      // (holds the warp's mbarrier)
+  l.s_nearcnt = so; so = layout_align(so + CAT_MAX_AGENTS * 4, 16);
+  l.s_con = so; so = layout_align(so + l.maxc * 32, 16);
+  l.s_ccount = so; so = layout_align(so + CAT_MAX_AGENTS * 4, 16);
+  l.s_order = so; so = layout_align(so + l.maxc, 16);
+  // per-ray hit keys; with ray lists the same area first holds the rays' 16-byte candidate slots
+  l.s_best = so; so = layout_align(so + l.nrays_pad * 16, 16);
+  l.s_cand = so; so = layout_align(so + 64 * 2, 16);
+  l.scratch_bytes = layout_align(so, 128);
+  return l;
+}
+
+template <int TA, int TR> struct FixedLayout { static constexpr Layout v = make_layout(TA ? TA : 1, TR ? TR : 1); };
+// inside a function templated on <TA, TR>: the layout value as an immediate (shipped shape) or from the parameters
+#define LAY(f) (TA ? FixedLayout<TA, TR>::v.f : k.lay.f)
+
 struct KParams {
   const unsigned char* blob;
   int blob_bytes;
@@ -74,18 +116,12 @@ struct KParams {
   unsigned int ray_slot_count, ray_ovf_words;   // sizes of the two arrays (checked build only)
   unsigned long long* overflow;  // [2] wall-contact / near-hull slots exceeded (cat_env_overflow_counts)
   float* state;
-  int rec_words;
   int n_worlds;
   int world_begin, world_end;   // the slice of worlds this launch steps (chunked host path); default [0, n_worlds)
   long long gid0;
-  int A, nc, R, P, nrays, nrays_pad, maxc, n_edges;
+  int A, nc, R, n_edges;
   int mode;
-  // record offsets (words)
-  int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags, o_near;
-  // per-warp scratch offsets (bytes) and size
-  int s_rdist, s_rtype, s_min, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, s_rcell, scratch_bytes;
-  // output record of one world, staged contiguously in shared memory at s_rdist (CatRecordLayout)
-  int r_bytes, r_off_reward, r_off_flags;
+  Layout lay;      // record offsets (words), per-warp scratch offsets (bytes), output-record offsets: make_layout(A, R)
   int state_dim;
   // constants
   float dt, inv_dt, impulse, inv_mass, agent_r, max_speed, term_r, ray_len, ray_r, wall_r;
@@ -456,8 +492,8 @@ __device__ __noinline__ void rasterise_agent(const KParams& k, const unsigned ch
   // (scalars, not the Warp struct: a struct passed by reference to an out-of-line function would live in local memory)
   const MapView m = make_view(blob);
   struct { unsigned long long* best; uint16_t* cand; const unsigned char* blob; int lane; } w;
-  w.best = reinterpret_cast<unsigned long long*>(scratch + k.s_best);
-  w.cand = reinterpret_cast<uint16_t*>(scratch + k.s_cand);
+  w.best = reinterpret_cast<unsigned long long*>(scratch + k.lay.s_best);
+  w.cand = reinterpret_cast<uint16_t*>(scratch + k.lay.s_cand);
   w.blob = blob; w.lane = threadIdx.x & 31;
   const int R = k.R, lane = w.lane, E = k.n_edges;
   const float L = k.ray_len, rsum = k.wall_r + k.ray_r;
@@ -587,7 +623,7 @@ __device__ __forceinline__ void stage_ray_slots(const KParams& k, const Warp& w,
     const int ba = __shfl_sync(0xFFFFFFFFu, base, a);
     uint4* dst = reinterpret_cast<uint4*>(w.best) + a * R;
     if (ba >= 0) {
-      CAT_CHECK((unsigned)(ba + R) <= k.ray_slot_count && (a + 1) * R * 16 <= k.nrays_pad * 16);
+      CAT_CHECK((unsigned)(ba + R) <= k.ray_slot_count && (a + 1) * R * 16 <= LAY(nrays_pad) * 16);
       if (lane == 0)
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                      "l"(k.ray_slots + ba), "r"(R * 16), "r"(bar)
@@ -732,8 +768,8 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
   const bool lists = k.ray_slots != nullptr;
   if (lists && !staged) stage_ray_slots<TA, TR>(k, w, st);
   const float* pos = w.rec;
-  const float* tc = w.rec + k.o_tc;
-  const uint32_t flags = reinterpret_cast<const uint32_t*>(w.rec)[k.o_flags];
+  const float* tc = w.rec + LAY(o_tc);
+  const uint32_t flags = reinterpret_cast<const uint32_t*>(w.rec)[LAY(o_flags)];
   const float L = k.ray_len, rsum = k.wall_r + k.ray_r, inv_L = 1.f / k.ray_len;
   const float reach = k.agent_r + k.ray_r, reach2 = reach * reach, inv_reach = 1.f / reach;
   // per agent: hulls whose rounded surface is within ray_r of the origin -> alpha = 0 candidates.  The list is
@@ -767,7 +803,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
     w.minbits[lane] = kEmpty;
   }
   __syncwarp();
-  if (lane == 0 && flags) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0u;   // lists are now valid for these positions
+  if (lane == 0 && flags) reinterpret_cast<uint32_t*>(w.rec)[LAY(o_flags)] = 0u;   // lists are now valid for these positions
 
   if (lists) sweep_lists<TA, TR>(k, m, w, st);
   const int kstride = lists ? 2 : 1;   // the list walk leaves ray r's key in the first half of its 16-byte slot
@@ -864,11 +900,11 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
           // rewards need the nearest opponent seen by this agent (cop.py:66-70, thief.py:60-63)
           if (type == want) atomicMin(&w.minbits[a], (uint32_t)dbits);
         }
-        CAT_CHECK(r < k.nrays && (feat == kNoFeature || feat >= kAgentTag || (int)(feat >> 1) < k.n_edges));
+        CAT_CHECK(r < LAY(nrays) && (feat == kNoFeature || feat >= kAgentTag || (int)(feat >> 1) < k.n_edges));
         w.rdist[r] = dbits;
         w.rtype[r] = type;
         if (k.hit_point) {
-          float2* hp = reinterpret_cast<float2*>(k.hit_point) + (size_t)world * k.nrays + r;
+          float2* hp = reinterpret_cast<float2*>(k.hit_point) + (size_t)world * LAY(nrays) + r;
           *hp = make_float2(hx, hy);
         }
       }
@@ -965,7 +1001,7 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
     uint4* dst = reinterpret_cast<uint4*>(k.record + (size_t)world * k.record_stride);
     const uint4* src = reinterpret_cast<const uint4*>(w.rdist);
 #pragma unroll 1
-    for (int i = lane; i < (k.r_bytes >> 4); i += 32) dst[i] = src[i];
+    for (int i = lane; i < (LAY(r_bytes) >> 4); i += 32) dst[i] = src[i];
   } else if (k.obs_vec) {
     // 16-byte aligned world blocks (mapped pinned host memory): one or two 512-byte warp stores per array
     if (k.obs_dist) {
@@ -1052,17 +1088,17 @@ __device__ __forceinline__ float agent_reward(const KParams& k, int a, uint32_t 
 }
 
 // cpSpaceStep(dt) for one world, state in shared memory.
-template <int TA>
+template <int TA, int TR>
 __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m, const Warp& w) {
-  const int A = TA ? TA : k.A, P = TA ? TA * (TA - 1) / 2 : k.P, lane = w.lane;
+  const int A = TA ? TA : k.A, P = LAY(P), lane = w.lane;
   float* pos = w.rec;
-  float* vel = w.rec + k.o_vel;
-  float* vb = w.rec + k.o_vb;
-  float* tc = w.rec + k.o_tc;
-  uint32_t* wkey = reinterpret_cast<uint32_t*>(w.rec + k.o_wkey);
-  float* wjn = w.rec + k.o_wjn;
-  uint32_t* page = reinterpret_cast<uint32_t*>(w.rec + k.o_page);
-  float* pjn = w.rec + k.o_pjn;
+  float* vel = w.rec + LAY(o_vel);
+  float* vb = w.rec + LAY(o_vb);
+  float* tc = w.rec + LAY(o_tc);
+  uint32_t* wkey = reinterpret_cast<uint32_t*>(w.rec + LAY(o_wkey));
+  float* wjn = w.rec + LAY(o_wjn);
+  uint32_t* page = reinterpret_cast<uint32_t*>(w.rec + LAY(o_page));
+  float* pjn = w.rec + LAY(o_pjn);
   const float rsum_w = k.agent_r + k.wall_r;
 
   // (1) cpBodyUpdatePosition, (2) shape caches
@@ -1120,7 +1156,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
       if (hit) {
         const uint32_t rank = w.ccount[a] + __popc(hits & same & ((1u << lane) - 1u));
         if (rank < (uint32_t)kSlots) {
-          CAT_CHECK(a >= 0 && a < A && (a * kSlots + (int)rank) < k.maxc && h >= 0 && h < m.H);
+          CAT_CHECK(a >= 0 && a < A && (a * kSlots + (int)rank) < LAY(maxc) && h >= 0 && h < m.H);
           float* c = w.con + (a * kSlots + rank) * 8;
           c[0] = nx; c[1] = ny; c[2] = d;
           reinterpret_cast<uint32_t*>(c)[7] = (uint32_t)h;
@@ -1186,7 +1222,7 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
     }
     w.ccount[lane] = cnt;
   }
-  if (lane == 0) reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0u;   // the stored near lists are valid for the new positions
+  if (lane == 0) reinterpret_cast<uint32_t*>(w.rec)[LAY(o_flags)] = 0u;   // the stored near lists are valid for the new positions
   uint32_t pair_hit = 0;
   if (lane < P) {
     // pair index -> (i, j), i-major
@@ -1327,9 +1363,9 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
 __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, const Warp& w, long long world) {
   const int A = k.A, lane = w.lane;
   float* pos = w.rec;
-  float* vel = w.rec + k.o_vel;
-  float* tc = w.rec + k.o_tc;
-  uint32_t* ep = reinterpret_cast<uint32_t*>(w.rec + k.o_ep);
+  float* vel = w.rec + k.lay.o_vel;
+  float* tc = w.rec + k.lay.o_tc;
+  uint32_t* ep = reinterpret_cast<uint32_t*>(w.rec + k.lay.o_ep);
   const uint32_t episode = *ep + 1u;
   // With pymunk's stale shape cache (A.10) every candidate is tested against the centres the OTHER agents had
   // before this reset, so the A spawns are independent and run on A lanes at once.  With the cache kept fresh
@@ -1386,8 +1422,8 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
   }
   if (lane == 0) {
     *ep = episode;
-    reinterpret_cast<int32_t*>(w.rec)[k.o_sc] = 0;  // base_env.py:350
-    reinterpret_cast<uint32_t*>(w.rec)[k.o_flags] = 0xFFu;  // re-spawned bodies may sit next to a wall
+    reinterpret_cast<int32_t*>(w.rec)[k.lay.o_sc] = 0;  // base_env.py:350
+    reinterpret_cast<uint32_t*>(w.rec)[k.lay.o_flags] = 0xFFu;  // re-spawned bodies may sit next to a wall
   }
   __syncwarp();
 }
@@ -1410,12 +1446,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   // Prefetch this warp's first record while the map copy is in flight (with one world per warp, the usual case
   // at a few thousand worlds, both latencies would otherwise add up on the critical path).
   const long long first_world = k.world_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const bool prefetched = k.rec_words <= 64 && k.mode != MODE_INIT && first_world < k.world_end;
+  const bool prefetched = LAY(rec_words) <= 64 && k.mode != MODE_INIT && first_world < k.world_end;
   float pf0 = 0.f, pf1 = 0.f;
   if (prefetched) {
-    const float* g = k.state + (size_t)first_world * k.rec_words;
-    if (lane < k.rec_words) pf0 = g[lane];
-    if (lane + 32 < k.rec_words) pf1 = g[lane + 32];
+    const float* g = k.state + (size_t)first_world * LAY(rec_words);
+    if (lane < LAY(rec_words)) pf0 = g[lane];
+    if (lane + 32 < LAY(rec_words)) pf1 = g[lane + 32];
   }
   if (tid == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(k.blob_bytes)
@@ -1440,22 +1476,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   }
   const MapView m = make_view(smem);
 
-  unsigned char* scratch = smem + ((k.blob_bytes + 127) & ~127) + (size_t)warp * k.scratch_bytes;
+  unsigned char* scratch = smem + ((k.blob_bytes + 127) & ~127) + (size_t)warp * LAY(scratch_bytes);
   Warp w;
   w.rec = reinterpret_cast<float*>(scratch);
-  w.rdist = reinterpret_cast<uint16_t*>(scratch + k.s_rdist);
-  w.rtype = reinterpret_cast<uint8_t*>(scratch + k.s_rtype);
-  w.minbits = reinterpret_cast<uint32_t*>(scratch + k.s_min);
-  w.near = reinterpret_cast<uint16_t*>(w.rec + k.o_near);   // lives in the state record
-  w.nearcnt = reinterpret_cast<uint32_t*>(scratch + k.s_nearcnt);
-  w.con = reinterpret_cast<float*>(scratch + k.s_con);
-  w.ccount = reinterpret_cast<uint32_t*>(scratch + k.s_ccount);
-  w.order = reinterpret_cast<uint8_t*>(scratch + k.s_order);
-  w.best = reinterpret_cast<unsigned long long*>(scratch + k.s_best);
-  w.cand = reinterpret_cast<uint16_t*>(scratch + k.s_cand);
-  w.rew = reinterpret_cast<float*>(scratch + k.s_rdist + k.r_off_reward);
-  w.flg = reinterpret_cast<uint8_t*>(scratch + k.s_rdist + k.r_off_flags);
-  w.mbar = reinterpret_cast<unsigned long long*>(scratch + k.s_rcell);
+  w.rdist = reinterpret_cast<uint16_t*>(scratch + LAY(s_rdist));
+  w.rtype = reinterpret_cast<uint8_t*>(scratch + LAY(s_rtype));
+  w.minbits = reinterpret_cast<uint32_t*>(scratch + LAY(s_min));
+  w.near = reinterpret_cast<uint16_t*>(w.rec + LAY(o_near));   // lives in the state record
+  w.nearcnt = reinterpret_cast<uint32_t*>(scratch + LAY(s_nearcnt));
+  w.con = reinterpret_cast<float*>(scratch + LAY(s_con));
+  w.ccount = reinterpret_cast<uint32_t*>(scratch + LAY(s_ccount));
+  w.order = reinterpret_cast<uint8_t*>(scratch + LAY(s_order));
+  w.best = reinterpret_cast<unsigned long long*>(scratch + LAY(s_best));
+  w.cand = reinterpret_cast<uint16_t*>(scratch + LAY(s_cand));
+  w.rew = reinterpret_cast<float*>(scratch + LAY(s_rdist) + LAY(r_off_reward));
+  w.flg = reinterpret_cast<uint8_t*>(scratch + LAY(s_rdist) + LAY(r_off_flags));
+  w.mbar = reinterpret_cast<unsigned long long*>(scratch + LAY(s_rcell));
   w.blob = smem;
   w.lane = lane;
   SlotStage slot_stage{0u, false};
@@ -1466,7 +1502,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   __syncwarp();
 
   // the padding of the staged output record is shipped by the 16-byte store paths: keep it zero
-  for (int i = lane; i < (k.r_bytes >> 2); i += 32) reinterpret_cast<uint32_t*>(w.rdist)[i] = 0u;
+  for (int i = lane; i < (LAY(r_bytes) >> 2); i += 32) reinterpret_cast<uint32_t*>(w.rdist)[i] = 0u;
   __syncwarp();
   const int A = TA ? TA : k.A;
   const int wpc = blockDim.x >> 5;   // warps per CTA: chosen per environment by the host (pick_launch_shape)
@@ -1481,17 +1517,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
 #endif
     const long long world = wbase + warp;
     if (world >= k.world_end) continue;
-    float* grec = k.state + (size_t)world * k.rec_words;
+    float* grec = k.state + (size_t)world * LAY(rec_words);
     int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
 
     if (k.mode == MODE_INIT) {  // fresh environment (entity.py:115,124): agents at map positions
 #pragma unroll 1
-      for (int i = lane; i < k.rec_words; i += 32) {
+      for (int i = lane; i < LAY(rec_words); i += 32) {
         float v = 0.f;
         if (i < 2 * A) v = (i & 1) ? m.init_pos[i >> 1].y : m.init_pos[i >> 1].x;
-        else if (i >= k.o_tc && i < k.o_tc + 2 * A) { const int q = i - k.o_tc; v = (q & 1) ? m.init_pos[q >> 1].y : m.init_pos[q >> 1].x; }
-        else if ((i >= k.o_wkey && i < k.o_wkey + A * kSlots) || (i >= k.o_page && i < k.o_page + k.P)) v = __uint_as_float(kEmpty);
-        else if (i == k.o_flags) v = __uint_as_float(0xFFu);
+        else if (i >= LAY(o_tc) && i < LAY(o_tc) + 2 * A) { const int q = i - LAY(o_tc); v = (q & 1) ? m.init_pos[q >> 1].y : m.init_pos[q >> 1].x; }
+        else if ((i >= LAY(o_wkey) && i < LAY(o_wkey) + A * kSlots) || (i >= LAY(o_page) && i < LAY(o_page) + LAY(P))) v = __uint_as_float(kEmpty);
+        else if (i == LAY(o_flags)) v = __uint_as_float(0xFFu);
         grec[i] = v;
       }
       continue;
@@ -1499,11 +1535,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     if (k.mode == MODE_RESET && k.reset_mask && !k.reset_mask[world]) continue;
 
     if (prefetched && world == first_world) {
-      if (lane < k.rec_words) w.rec[lane] = pf0;
-      if (lane + 32 < k.rec_words) w.rec[lane + 32] = pf1;
+      if (lane < LAY(rec_words)) w.rec[lane] = pf0;
+      if (lane + 32 < LAY(rec_words)) w.rec[lane + 32] = pf1;
     } else {
 #pragma unroll 1
-      for (int i = lane; i < k.rec_words; i += 32) w.rec[i] = grec[i];
+      for (int i = lane; i < LAY(rec_words); i += 32) w.rec[i] = grec[i];
     }
     __syncwarp();
 
@@ -1514,10 +1550,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     if (do_step && k.ray_slots) { stage_ray_slots<TA, TR>(k, w, slot_stage); staged = true; }
     if (do_step) {  // ---------------- base_env.py:354-383 ----------------
       const float* pos = w.rec;
-      float* vel = w.rec + k.o_vel;
-      const int step_count = reci[k.o_sc] + 1;  // :372
+      float* vel = w.rec + LAY(o_vel);
+      const int step_count = reci[LAY(o_sc)] + 1;  // :372
       __syncwarp();
-      if (lane == 0) reci[k.o_sc] = step_count;
+      if (lane == 0) reci[LAY(o_sc)] = step_count;
       // _termination_criterion (:521-554): thief-major; LOS blocked by walls only; dist < radius (strict)
 #pragma unroll 1
       for (int t = k.nc; t < A && !captured; ++t)
@@ -1580,7 +1616,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
       if (!again) write_observation<TA, TR>(k, w, world, k.mode == MODE_STEP);
       __syncwarp();
       if (do_step) {
-        physics_world<TA>(k, m, w);  // base_env.py:392
+        physics_world<TA, TR>(k, m, w);  // base_env.py:392
         do_step = false;
         if (again) { do_reset = true; continue; }
       }
@@ -1588,7 +1624,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     }
     if (k.mode != MODE_OBSERVE) {
 #pragma unroll 1
-      for (int i = lane; i < k.rec_words; i += 32) grec[i] = w.rec[i];
+      for (int i = lane; i < LAY(rec_words); i += 32) grec[i] = w.rec[i];
     }
     __syncwarp();
   }
