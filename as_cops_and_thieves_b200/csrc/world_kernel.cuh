@@ -584,10 +584,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns): sleep, do not spin
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(4000)
         : "memory");
   }
 }
@@ -1125,6 +1125,26 @@ __device__ __forceinline__ void physics_world(const KParams& k, const MapView& m
     for (int d = 1; d < CAT_MAX_AGENTS; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
     const int total = __shfl_sync(0xFFFFFFFFu, incl, A - 1);
     __syncwarp();
+    if (total == 0) {
+      // Free flight, the common case away from walls: no hull within contact reach of any agent's cell.  If, besides,
+      // no agent pair touches and no arbiter is cached from earlier steps, the rest of cpSpaceStep (arbiter look-up and
+      // ageing, warm start, the impulse iterations) has nothing to do: leave with the flags it would have set.
+      bool busy = false;
+      if (lane < A * kSlots) busy = wkey[lane] != kEmpty;
+      if (lane < P) {
+        int i = 0, rem = lane;
+#pragma unroll 1
+        while (rem >= A - 1 - i) { rem -= A - 1 - i; ++i; }
+        const int j = i + 1 + rem;
+        const float dx = pos[2 * j] - pos[2 * i], dy = pos[2 * j + 1] - pos[2 * i + 1], mind = 2.f * k.agent_r;
+        busy = busy || page[lane] != kEmpty || dx * dx + dy * dy < mind * mind;
+      }
+      if (!__any_sync(0xFFFFFFFFu, busy)) {
+        if (lane == 0) reinterpret_cast<uint32_t*>(w.rec)[LAY(o_flags)] = 0u;
+        __syncwarp();
+        return;
+      }
+    }
 #pragma unroll 1
     for (int p0 = 0; p0 < total; p0 += 32) {
       const int p = p0 + lane;

@@ -20,7 +20,7 @@ from as_cops_and_thieves_b200 import _lib  # noqa: E402
 from as_cops_and_thieves_b200.worlds import CatWorlds  # noqa: E402
 import parity_utils as pu  # noqa: E402
 L = _lib.load()
-for mp, free, N in (("squarinth", False, 4096), ("labyrinth", True, 4096), ("agh-map", True, 4096)):
+for mp, free, N in (("squarinth", False, 4096), ("lbirinth", False, 4096), ("grandbyrinth", False, 4096), ("labyrinth", True, 4096), ("agh-map", True, 4096)):
     cw = CatWorlds(pu.named_cmap(mp, free_spawn=free), N, want_f32=False, want_shared=False)
     cw.reset()
     acts = [torch.randint(0, 4, (N, 3), dtype=torch.uint8, device="cuda") for _ in range(8)]
