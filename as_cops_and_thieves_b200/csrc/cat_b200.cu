@@ -380,6 +380,22 @@ int cat_env_info(const CatEnv* env, CatEnvInfo* info) {
   return CAT_OK;
 }
 
+int cat_ray_lists_host(const CatMapDesc* map, int32_t n_rays, double ray_length, double rsum, double cell, double grid_out[5],
+                       uint32_t* slots, int64_t* n_slot_words, uint32_t* ovf, int64_t* n_ovf_words) {
+  if (!map || !grid_out || !n_slot_words || !n_ovf_words) return fail(CAT_ERR_INVALID, "null argument");
+  if (n_rays < 2 || n_rays > CAT_MAX_RAYS || map->n_hulls < 1 || map->n_edges > 65535) return fail(CAT_ERR_LIMIT, "ray / hull / edge count out of range");
+  RayLists rl;
+  build_ray_lists(map, n_rays, ray_length, rsum, cell, &rl);
+  grid_out[0] = rl.g.x0; grid_out[1] = rl.g.y0; grid_out[2] = rl.g.cell; grid_out[3] = rl.g.nx; grid_out[4] = rl.g.ny;
+  if (slots && ovf) {
+    if (*n_slot_words < (int64_t)rl.slots.size() || *n_ovf_words < (int64_t)rl.ovf.size()) return fail(CAT_ERR_INVALID, "buffers too small");
+    memcpy(slots, rl.slots.data(), rl.slots.size() * 4);
+    memcpy(ovf, rl.ovf.data(), rl.ovf.size() * 4);
+  }
+  *n_slot_words = (int64_t)rl.slots.size(); *n_ovf_words = (int64_t)rl.ovf.size();
+  return CAT_OK;
+}
+
 int cat_env_record_layout(const CatEnv* env, CatRecordLayout* layout) {
   if (!env || !layout) return fail(CAT_ERR_INVALID, "null argument");
   *layout = env->rec;

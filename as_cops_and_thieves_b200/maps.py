@@ -356,8 +356,8 @@ def _clip_interval(p0: np.ndarray, dp: np.ndarray, lo: np.ndarray, hi: np.ndarra
 RAY_LIST_LB_SCALE = 64.0     # the lower bounds stored with the list entries are in 1/64 units, rounded down
 
 
-def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, eps: float = 1e-2
-              ) -> Tuple[np.ndarray, np.ndarray]:
+def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, eps: float = 1e-2,
+              grid: Optional[Tuple[float, float, float, int, int]] = None, return_bounds: bool = False):
     """Per (grid cell, ray index): the edges ray ``i`` cast from ANY origin inside the cell can touch, nearest first.
 
     The sensor's rays have fixed directions (``entity.py:182``), so for one direction the fat rays of every origin in
@@ -370,7 +370,12 @@ def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, 
     holds is closer than the next bound.  The list is a conservative superset and every listed edge still gets the
     exact ``cpPolyShapeSegmentQuery`` arithmetic, so results do not depend on it.
 
-    Returns ``(off int32 [ncell * R + 1], ent uint32)`` with ``ent = (lb_q << 16) | edge``.
+    This is the numpy statement of what the library builds in C++ at ``cat_env_create`` (``csrc/ray_lists.h``;
+    ``tests/test_maps.py`` compares the two on the library's own grid, passed as ``grid = (x0, y0, cell, nx, ny)``;
+    default: the compiled map's contact grid).
+
+    Returns ``(off int32 [ncell * R + 1], ent uint32)`` with ``ent = (lb_q << 16) | edge`` (``lb_q`` in 1/64 units), plus
+    the un-quantised bounds (float64, same order) when ``return_bounds``.
     """
     E, R, L = cmap.n_edges, int(n_rays), float(ray_length)
     assert E < 65536
@@ -384,11 +389,12 @@ def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, 
         prev[o:e] = np.roll(idx, 1)
         nxt[o:e] = np.roll(idx, -1)
     A, B, n, nn = vert[prev], vert, normal, normal[nxt]
-    nx, ny, cell = cmap.nx, cmap.ny, cmap.cell
+    gx0, gy0, cell, nx, ny = (cmap.grid_x0, cmap.grid_y0, cmap.cell, cmap.nx, cmap.ny) if grid is None else grid
+    nx, ny = int(nx), int(ny)
     ncell = nx * ny
     cxs, cys = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
-    cl = (cmap.grid_x0 + cxs.ravel() * cell - 0.05)[:, None]      # the kernel bins the origin in fp32: grow a little
-    cb = (cmap.grid_y0 + cys.ravel() * cell - 0.05)[:, None]
+    cl = (gx0 + cxs.ravel() * cell - 0.05)[:, None]      # the kernel bins the origin in fp32: grow a little
+    cb = (gy0 + cys.ravel() * cell - 0.05)[:, None]
     cr, ct = cl + cell + 0.1, cb + cell + 0.1
     corners = [(cl, cb), (cr, cb), (cr, ct), (cl, ct)]
     # ---- per (cell, edge), direction independent
@@ -416,7 +422,7 @@ def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, 
     dist = np.where(crosses, 0.0, dist)
     lb_euclid = dist - rs
 
-    cells_all, rays_all, lbs_all, edges_all = [], [], [], []
+    cells_all, rays_all, lbs_all, edges_all, raw_all = [], [], [], [], []
     for i in range(R):
         th = i * (2.0 * math.pi / R)
         ux, uy = math.cos(th), math.sin(th)
@@ -430,7 +436,8 @@ def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, 
         b0, b1 = _clip_interval(wA[None, :], (wB - wA)[None, :], w0 - rs, w1 + rs)
         l0, l1 = np.maximum(np.maximum(a0, b0), 0.0), np.minimum(np.minimum(a1, b1), 1.0)
         hit = (l0 <= l1) & in_front & runs_against[None, :]
-        tmin = np.minimum(tA[None, :] + l0 * (tB - tA)[None, :], tA[None, :] + l1 * (tB - tA)[None, :])
+        with np.errstate(invalid="ignore"):
+            tmin = np.minimum(tA[None, :] + l0 * (tB - tA)[None, :], tA[None, :] + l1 * (tB - tA)[None, :])
         lb = np.maximum(np.maximum(tmin - rs - t1, lb_euclid), 0.0)
         hit &= lb < L
         c_idx, e_idx = np.nonzero(hit)
@@ -438,13 +445,16 @@ def ray_lists(cmap: "CompiledMap", n_rays: int, ray_length: float, rsum: float, 
         rays_all.append(np.full(len(c_idx), i, np.int64))
         lbs_all.append(np.clip(np.floor(lb[c_idx, e_idx] * RAY_LIST_LB_SCALE) - 1.0, 0, 65535).astype(np.int64))
         edges_all.append(e_idx.astype(np.int64))
+        raw_all.append(lb[c_idx, e_idx])
     cells_all, rays_all = np.concatenate(cells_all), np.concatenate(rays_all)
-    lbs_all, edges_all = np.concatenate(lbs_all), np.concatenate(edges_all)
+    lbs_all, edges_all, raw_all = np.concatenate(lbs_all), np.concatenate(edges_all), np.concatenate(raw_all)
     key = cells_all * R + rays_all
     order = np.lexsort((edges_all, lbs_all, key))
     ent = ((lbs_all[order] << 16) | edges_all[order]).astype(np.uint32)
     off = np.zeros(ncell * R + 1, np.int64)
     np.cumsum(np.bincount(key, minlength=ncell * R), out=off[1:])
+    if return_bounds:
+        return off.astype(np.int32), ent, raw_all[order]
     return off.astype(np.int32), ent
 
 

@@ -224,6 +224,14 @@ int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* str
 int cat_env_get_state(CatEnv* env, const void* state_dev, const CatStateView* view, void* stream);
 int cat_env_set_state(CatEnv* env, void* state_dev, const CatStateView* view, void* stream);
 
+/* Inspection / test entry point (host only, needs no GPU): the per-(cell, ray) candidate lists cat_env_create builds for
+ * this map and these sensor parameters (csrc/ray_lists.h).  grid_out = {x0, y0, cell, nx, ny}.  Call with slots = ovf =
+ * NULL to get the sizes (in 32-bit words) in n_slot_words / n_ovf_words, then again with buffers of those sizes.
+ * slot[(cell * n_rays + ray) * 4 .. +4]: entries (bf16 bits of the lower bound of the hit distance << 16 | edge id),
+ * 0x7F80FFFF = end, bit 31 = link to a 4-word chunk of ovf (word offset in the low 31 bits). */
+int cat_ray_lists_host(const CatMapDesc* map, int32_t n_rays, double ray_length, double rsum, double cell,
+                       double grid_out[5], uint32_t* slots, int64_t* n_slot_words, uint32_t* ovf, int64_t* n_ovf_words);
+
 /* skrl MAPPO._update GAE (call site agent_learning_utils.py:198-199).
  * rewards/values [T][M] f32, dones [T][M] u8, last_values [M]; returns/advantages [T][M].
  * stats_dev: 2 doubles {sum(adv), sum(adv^2)} accumulated by this call (zeroed first).

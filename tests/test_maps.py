@@ -222,3 +222,85 @@ def test_random_maps_compile_to_valid_hulls_and_conservative_lists(seed, tmp_pat
         d = np.hypot(*(p - (A + AB * t[:, None])).T)
         cand = np.nonzero(((((p - B) * nrm).sum(1) > 0) | (((p - B) * nn).sum(1) > 0)) & (d < 402.0))[0]
         assert set(cand.tolist()) <= view
+
+
+def _library_ray_lists(cmap, n_rays, ray_length, rsum, cell):
+    """The lists the C++ builder (csrc/ray_lists.h) makes at cat_env_create, unpacked to {(cell, ray): [(bound, edge)]}."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from test_abi import _desc
+    from as_cops_and_thieves_b200 import _lib
+    L = _lib.load()
+    md, keep = _desc(cmap)
+    grid = (C.c_double * 5)()
+    ns, no = C.c_int64(0), C.c_int64(0)
+    assert L.cat_ray_lists_host(C.byref(md), n_rays, ray_length, rsum, cell, C.byref(grid), None, C.byref(ns), None, C.byref(no)) == 0
+    slots = np.zeros(ns.value, np.uint32)
+    ovf = np.zeros(no.value, np.uint32)
+    assert L.cat_ray_lists_host(C.byref(md), n_rays, ray_length, rsum, cell, C.byref(grid), slots.ctypes.data_as(C.c_void_p),
+                                C.byref(ns), ovf.ctypes.data_as(C.c_void_p), C.byref(no)) == 0
+    END, LINK = 0x7F80FFFF, 0x80000000
+    lists = {}
+    for s in range(len(slots) // 4):
+        out, words, guard = [], list(slots[4 * s:4 * s + 4]), 0
+        while words:
+            w = int(words.pop(0))
+            if w == END:
+                break
+            if w & LINK:
+                o = w & 0x7FFFFFFF
+                assert o % 4 == 0 and o + 4 <= len(ovf)
+                words = list(ovf[o:o + 4])
+                guard += 1
+                assert guard < 1000
+                continue
+            bound = np.array([w & 0xFFFF0000], np.uint32).view(np.float32)[0]
+            out.append((float(bound), w & 0xFFFF))
+        lists[s] = out
+    return tuple(grid), lists
+
+
+@pytest.mark.parametrize("name,free,cell", [("squarinth", False, 60.0), ("agh-map", True, 75.0), ("lbirinth", False, 0.0)])
+def test_ray_list_builder_matches_its_numpy_statement(name, free, cell):
+    """csrc/ray_lists.h (C++, what the kernel walks) against maps.ray_lists (numpy) on the same grid: the same edges per
+    (cell, ray) up to the eps band of the inclusion tests, sorted by a lower bound that never exceeds the numpy one, which
+    in turn never exceeds the true hit distance of any ray cast from inside the cell."""
+    from as_cops_and_thieves_b200.maps import ray_lists
+    m = load_named_map(name)
+    cmap = compile_map(m, name=name, spawn_override=free_space_regions(m) if free else None)
+    R, L, rsum = 90, 400.0, 2.0
+    grid, lib = _library_ray_lists(cmap, R, L, rsum, cell)
+    x0, y0, c, nx, ny = grid
+    assert nx * ny * R == len(lib) and (cell == 0.0 or abs(c - cell) < 1e-6)
+    if cell == 0.0:
+        assert 8000 <= nx * ny <= 20000 and c >= 12.0           # automatic: about 16k cells, not below 12 units
+        return
+    tight = ray_lists(cmap, R, L, rsum, eps=0.5e-2, grid=grid, return_bounds=True)
+    loose = ray_lists(cmap, R, L, rsum, eps=2e-2, grid=grid, return_bounds=True)
+
+    def as_dict(res):
+        off, ent, lb = res
+        return off, ent & 0xFFFF, lb
+    to, te, tl = as_dict(tight)
+    lo, le, ll = as_dict(loose)
+    n_entries = 0
+    for s in range(len(lib)):
+        got = lib[s]
+        edges = [e for _, e in got]
+        assert len(set(edges)) == len(edges)
+        bounds = [b for b, _ in got]
+        assert bounds == sorted(bounds)                          # nearest lower bound first
+        must = set(te[to[s]:to[s + 1]].tolist())
+        may = set(le[lo[s]:lo[s + 1]].tolist())
+        assert must <= set(edges) <= may, (s, must - set(edges), set(edges) - may)
+        # the bound shrinks as eps grows (the clip region of an edge that runs almost along the ray moves a lot), so
+        # the library's (eps 1e-2) lies between the numpy ones for 2e-2 and 0.5e-2, up to its bf16 truncation (downwards)
+        hi = dict(zip(te[to[s]:to[s + 1]].tolist(), tl[to[s]:to[s + 1]].tolist()))
+        lw = dict(zip(le[lo[s]:lo[s + 1]].tolist(), ll[lo[s]:lo[s + 1]].tolist()))
+        for b, e in got:
+            if e in hi:
+                assert b <= hi[e] + 0.02, (s, e, b, hi[e])
+            assert b >= lw[e] * (1 - 1 / 128) - 0.05, (s, e, b, lw[e])
+        n_entries += len(got)
+    assert n_entries > 0
