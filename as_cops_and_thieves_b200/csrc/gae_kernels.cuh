@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
 #ifndef CAT_GAE_TMA_STAGES
 #define CAT_GAE_TMA_STAGES 3
 #endif
-constexpr int kTmaCols = 64, kTmaSegs = 4, kTmaRows = kTmaSegs * kGaeS, kTmaStages = CAT_GAE_TMA_STAGES;
+#ifndef CAT_GAE_TMA_COLS
+#define CAT_GAE_TMA_COLS 64
+#endif
+constexpr int kTmaCols = CAT_GAE_TMA_COLS, kTmaSegs = 4, kTmaRows = kTmaSegs * kGaeS, kTmaStages = CAT_GAE_TMA_STAGES;
 constexpr int kTmaStageBytes = kTmaRows * kTmaCols * (4 + 4 + 1);   // 18432, a multiple of 128
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* mbar) {
@@ -184,7 +187,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
 }
 
 template <typename Index>
-__global__ void __launch_bounds__(kTmaCols* kTmaSegs, 4)
+__global__ void __launch_bounds__(kTmaCols* kTmaSegs, kTmaCols >= 64 ? 4 : 8)
     cat_gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_v,
                        const __grid_constant__ CUtensorMap tm_d, const float* __restrict__ last_values,
                        float* __restrict__ returns, float* __restrict__ advantages, double* __restrict__ stats, int T, int M,
