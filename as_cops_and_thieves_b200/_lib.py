@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-CAT_ABI_VERSION = 4
+CAT_ABI_VERSION = 5
 CAT_MAX_AGENTS = 8
 CAT_MAX_RAYS = 128
 CAT_WALL_SLOTS = 4

@@ -137,6 +137,24 @@ static bool pick_launch_shape(CatEnv* env, int n_worlds, LaunchShape* out) {
   return best_score >= 0;
 }
 
+// Launch with programmatic stream serialisation: the kernel's CTAs may be scheduled while the previous kernel in the
+// stream drains; the kernels call griddepcontrol.wait before they touch global memory (gae_kernels.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int allowed = [] { const char* e = getenv("CAT_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  attr[0].val.programmaticStreamSerializationAllowed = allowed;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 extern "C" {
 
 #ifdef CAT_STATS
@@ -585,7 +603,6 @@ int cat_gae(const float* rewards, const uint8_t* dones, const float* values, con
     return fail(CAT_ERR_INVALID, "null argument");
   if (T < 1 || M < 1) return fail(CAT_ERR_INVALID, "T and M must be >= 1");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(double), s));
   const int threads = kGaeCols * kGaeSegs, blocks = (M + kGaeCols - 1) / kGaeCols;
   const bool idx32 = (long long)(T + kTmaRows) * M < (1ll << 31);
   if (gae_tma_usable(rewards, dones, values, M)) {
@@ -604,17 +621,17 @@ int cat_gae(const float* rewards, const uint8_t* dones, const float* values, con
         if (devid >= 0 && devid < 64) attr_set[devid] = true;
       }
       if (idx32)
-        cat_gae_tma_kernel<uint32_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+        CUDA_TRY(launch_pdl(cat_gae_tma_kernel<uint32_t>, tblocks, kTmaCols * kTmaSegs, smem, s, tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam));
       else
-        cat_gae_tma_kernel<size_t><<<tblocks, kTmaCols * kTmaSegs, smem, s>>>(tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+        CUDA_TRY(launch_pdl(cat_gae_tma_kernel<size_t>, tblocks, kTmaCols * kTmaSegs, smem, s, tm_r, tm_v, tm_d, last_values, returns, advantages, stats_dev, T, M, gamma, lam));
       CUDA_TRY(cudaGetLastError());
       return CAT_OK;
     }
   }
   if (idx32)
-    cat_gae_kernel<uint32_t><<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+    CUDA_TRY(launch_pdl(cat_gae_kernel<uint32_t>, blocks, threads, 0, s, rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam));
   else
-    cat_gae_kernel<size_t><<<blocks, threads, 0, s>>>(rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam);
+    CUDA_TRY(launch_pdl(cat_gae_kernel<size_t>, blocks, threads, 0, s, rewards, dones, values, last_values, returns, advantages, stats_dev, T, M, gamma, lam));
   CUDA_TRY(cudaGetLastError());
   return CAT_OK;
 }
@@ -627,7 +644,7 @@ int cat_adv_normalize(float* advantages, int64_t n, const double* stats_dev, int
   long long blocks = (n / 4 + threads - 1) / threads;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  cat_adv_normalize_kernel<<<(int)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(advantages, n, stats_dev, count);
+  CUDA_TRY(launch_pdl(cat_adv_normalize_kernel, (int)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream), advantages, (long long)n, stats_dev, (long long)count));
   CUDA_TRY(cudaGetLastError());
   return CAT_OK;
 }

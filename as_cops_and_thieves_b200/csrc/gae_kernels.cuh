@@ -84,6 +84,38 @@ __device__ __forceinline__ void gae_store(const GaeChunk& ck, float adv, int bas
   }
 }
 
+// Programmatic dependent launch (cat_b200.cu launches these kernels with programmatic stream serialisation): a CTA may
+// become resident while the previous kernel in the stream is still draining; nothing that kernel wrote may be touched
+// before pdl_wait() returns (it returns when the previous grid has completed and its writes are visible).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// The call's {sum(adv), sum(adv^2)} without a memset in front of the kernel and without a round trip at the end of a CTA.
+// stats (include/cat_b200.h, CAT_GAE_STATS_DOUBLES doubles zeroed once by their owner) holds two sum slots, a 64-bit
+// count of the calls made on this buffer and a 64-bit ticket:  { slot0[2], slot1[2], calls, ticket }.
+//   call number c accumulates (fire-and-forget reductions) into slot (c + 1) & 1, which the call before left zero;
+//   at its START every CTA reads c and then draws a ticket — the CTA that draws the last one knows every CTA of this
+//   launch has read c, so it zeroes the other slot (the previous call's sums, whose consumers are earlier in the stream)
+//   for the next call, resets the ticket and publishes calls = c + 1;
+//   afterwards the sums of the latest call are in slot (calls & 1) — what cat_adv_normalize_kernel reads.
+// Both round trips happen while the CTA's first tiles are in flight.
+__device__ __forceinline__ int stats_begin(double* stats) {
+  unsigned long long* u = reinterpret_cast<unsigned long long*>(stats);
+  const unsigned long long c = *reinterpret_cast<volatile unsigned long long*>(u + 4);
+  // (c >> 63 is zero: it makes the ticket depend on the value read, so the read is complete before the ticket is drawn)
+  if (atomicAdd(u + 5, 1ull + (c >> 63)) == (unsigned long long)gridDim.x - 1ull) {
+    const int z = (int)(c & 1ull);
+    stats[2 * z] = 0.0; stats[2 * z + 1] = 0.0;
+    u[5] = 0ull;
+    u[4] = c + 1ull;
+  }
+  return (int)((c + 1ull) & 1ull);
+}
+__device__ __forceinline__ void stats_add(double* stats, int slot, double a, double b) {
+  atomicAdd(&stats[2 * slot], a);
+  atomicAdd(&stats[2 * slot + 1], b);
+}
+
 template <typename Index>
 __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
     cat_gae_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, const float* __restrict__ values,
@@ -95,6 +127,10 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
   const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
   const int col = blockIdx.x * kGaeCols + lane;
   const bool valid = col < M;
+  pdl_wait();
+  pdl_launch_dependents();
+  int stats_slot = 0;
+  if (threadIdx.x == 0) stats_slot = stats_begin(stats);
   const bool cols_full = blockIdx.x * kGaeCols + kGaeCols <= M;   // CTA-uniform
   const float gl = gamma * lam;
   constexpr int kChunk = kGaeSegs * kGaeS;
@@ -157,8 +193,7 @@ __global__ void __launch_bounds__(kGaeCols* kGaeSegs, CAT_GAE_MIN_CTAS)
   if (threadIdx.x == 0) {
     double a = 0, b = 0;
     for (int i = 0; i < kGaeSegs; ++i) { a += sh1[i]; b += sh2[i]; }
-    atomicAdd(&stats[0], a);
-    atomicAdd(&stats[1], b);
+    stats_add(stats, stats_slot, a, b);
   }
 }
 
@@ -218,8 +253,13 @@ __global__ void __launch_bounds__(kTmaCols* kTmaSegs, kTmaCols >= 64 ? 4 : 8)
     tma_load_2d(base + kTmaRows * kTmaCols * 4, &tm_v, c0, t_lo, &full[s]);
     tma_load_2d(base + kTmaRows * kTmaCols * 8, &tm_d, c0, t_lo, &full[s]);
   };
-  if (tid == 0)
+  pdl_wait();                // everything above overlaps the tail of the previous kernel in the stream
+  pdl_launch_dependents();   // ... and the next one may take this CTA's place the moment it exits
+  int stats_slot = 0;
+  if (tid == 0) {
     for (int k = 0; k < kTmaStages - 1 && k < nch; ++k) issue(k);
+    stats_slot = stats_begin(stats);   // its two round trips overlap the tiles' flight
+  }
   float carry_adv = 0.f, carry_v = valid ? last_values[gcol] : 0.f;
   double s1 = 0.0, s2 = 0.0;
   const int rb = kTmaRows - (seg + 1) * kGaeS;   // this thread's 8 rows of the tile (segment 0 = the latest steps)
@@ -306,8 +346,7 @@ __global__ void __launch_bounds__(kTmaCols* kTmaSegs, kTmaCols >= 64 ? 4 : 8)
   if (tid == 0) {
     double a = 0, b = 0;
     for (int i = 0; i < (kTmaCols * kTmaSegs) / 32; ++i) { a += sh1[i]; b += sh2[i]; }
-    atomicAdd(&stats[0], a);
-    atomicAdd(&stats[1], b);
+    stats_add(stats, stats_slot, a, b);
   }
 }
 
@@ -317,9 +356,13 @@ __global__ void __launch_bounds__(256) cat_adv_normalize_kernel(float* __restric
                                                                 const double* __restrict__ stats, long long count) {
   // mean / 1/(std + eps) once per CTA (fp64 divide + sqrt), broadcast through shared memory
   __shared__ float s_fm, s_inv;
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    const double mean = stats[0] / (double)count;
-    double var = count > 1 ? (stats[1] - (double)count * mean * mean) / (double)(count - 1) : 0.0;
+    const int slot = (int)(reinterpret_cast<const unsigned long long*>(stats)[4] & 1ull);   // the latest call's sums
+    const double sum = stats[2 * slot], sumsq = stats[2 * slot + 1];
+    const double mean = sum / (double)count;
+    double var = count > 1 ? (sumsq - (double)count * mean * mean) / (double)(count - 1) : 0.0;
     if (var < 0.0) var = 0.0;
     s_fm = (float)mean;
     s_inv = (float)(1.0 / (sqrt(var) + 1e-8));

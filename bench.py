@@ -330,7 +330,7 @@ def time_gae(torch, dev, flush, T=256, M=49152, iters=30):
         v = torch.randn((T, M), device=dev, generator=g)
         d = (torch.rand((T, M), device=dev, generator=g) < 0.01).to(torch.uint8)
         sets.append((r, v, d, torch.randn((M,), device=dev, generator=g), torch.empty_like(r), torch.empty_like(r),
-                     torch.zeros(2, dtype=torch.float64, device=dev)))
+                     torch.zeros(6, dtype=torch.float64, device=dev)))
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def gae(s_):

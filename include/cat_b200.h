@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CAT_ABI_VERSION 4
+#define CAT_ABI_VERSION 5
 #define CAT_MAX_AGENTS 8
 #define CAT_MAX_RAYS 128
 #define CAT_WALL_SLOTS 4 /* cached wall arbiters / simultaneous wall contacts kept per agent; a 5th is counted by
@@ -234,14 +234,21 @@ int cat_ray_lists_host(const CatMapDesc* map, int32_t n_rays, double ray_length,
 
 /* skrl MAPPO._update GAE (call site agent_learning_utils.py:198-199).
  * rewards/values [T][M] f32, dones [T][M] u8, last_values [M]; returns/advantages [T][M].
- * stats_dev: 2 doubles {sum(adv), sum(adv^2)} accumulated by this call (zeroed first).
+ * stats_dev: CAT_GAE_STATS_DOUBLES (6) doubles = { slot0[2], slot1[2], u64 calls, u64 ticket }, ZEROED BY THE CALLER
+ * ONCE when it allocates them and then owned by cat_gae.  After a call, {sum(adv), sum(adv^2)} of that call are in slot
+ * (calls & 1), i.e. stats_dev[2 * (calls & 1) .. + 2]; the other slot is zero and takes the next call's sums (so no memset
+ * runs in front of the kernel and no CTA waits on a counter at its end: csrc/gae_kernels.cuh).  Calls that share a
+ * stats buffer must be ordered (same stream).  Both kernels are launched with programmatic stream serialisation — their
+ * prologues overlap the previous kernel's tail (environment CAT_PDL=0 turns that off).
  * Runs the TMA-fed kernel when M % 16 == 0 and the three input arrays are 16-byte aligned, the register-pipelined
  * kernel otherwise (environment CAT_GAE_TMA=0 forces the latter); both give the same results to fp32 rounding. */
+#define CAT_GAE_STATS_DOUBLES 6
 int cat_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values,
             float* returns, float* advantages, double* stats_dev, int32_t T, int32_t M, float gamma,
             float lam, void* stream);
-/* advantages = (advantages - mean) / (std + 1e-8) with mean/std (unbiased) from stats over `count`
- * samples; all-reduce stats and count across ranks first for a global normalisation. */
+/* advantages = (advantages - mean) / (std + 1e-8) with mean/std (unbiased) from stats over `count` samples.  stats_dev
+ * has cat_gae's layout (pass the buffer cat_gae filled).  For a global normalisation across ranks, all-reduce the sums and
+ * the count and pass a zeroed CAT_GAE_STATS_DOUBLES buffer with the reduced sums in [0..1] (calls = 0 selects slot 0). */
 int cat_adv_normalize(float* advantages, int64_t n, const double* stats_dev, int64_t count, void* stream);
 
 #ifdef __cplusplus

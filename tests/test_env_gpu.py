@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import parity_utils as pu
-from as_cops_and_thieves_b200 import spaces
+from as_cops_and_thieves_b200 import spaces, _lib
 from as_cops_and_thieves_b200.env import BatchedCopsThievesEnv, SimpleEnv, BaseEnv
 from as_cops_and_thieves_b200.gae import compute_gae
 from as_cops_and_thieves_b200.maps import compile_map, load_named_map, free_space_regions, Map
@@ -222,6 +222,35 @@ def test_gae_kernels_match_oracle_and_torch(cuda_device, monkeypatch, tma):
         np.testing.assert_allclose(adv.cpu().numpy(), ((advs - advs.mean()) / (advs.std() + 1e-8)).numpy(), rtol=1e-3, atol=1e-4)
         ret2, adv2 = compute_gae(r.to(cuda_device), d.to(cuda_device), v.to(cuda_device), lv.to(cuda_device), normalize=False)
         np.testing.assert_allclose(adv2.cpu().numpy(), advs.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_gae_statistics_buffer_protocol(cuda_device):
+    """include/cat_b200.h: the stats buffer is zeroed once by its owner; every call leaves its sums in slot (calls & 1),
+    the other slot and the ticket zero — no memset in front of the kernel."""
+    L = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    stats = torch.zeros(6, dtype=torch.float64, device=cuda_device)
+    stream = torch.cuda.current_stream(cuda_device).cuda_stream
+    for call, (T, M) in enumerate(((40, 4096), (7, 33), (300, 64), (64, 1600)), start=1):
+        r = torch.randn((T, M), generator=g).to(cuda_device)
+        v = torch.randn((T, M), generator=g).to(cuda_device)
+        d = (torch.rand((T, M), generator=g) < 0.05).to(torch.uint8).to(cuda_device)
+        lv = torch.randn((M,), generator=g).to(cuda_device)
+        ret, adv = torch.empty_like(r), torch.empty_like(r)
+        _lib.check(L.cat_gae(r.data_ptr(), d.data_ptr(), v.data_ptr(), lv.data_ptr(), ret.data_ptr(), adv.data_ptr(),
+                             stats.data_ptr(), T, M, 0.99, 0.95, stream), "cat_gae")
+        torch.cuda.synchronize()
+        words = stats.view(torch.int64).cpu()
+        assert int(words[4]) == call and int(words[5]) == 0
+        s = stats.cpu().numpy()
+        slot = call & 1
+        a64 = adv.double()
+        np.testing.assert_allclose(s[2 * slot], float(a64.sum()), rtol=1e-6, atol=1e-3)   # fp32 partials per thread
+        np.testing.assert_allclose(s[2 * slot + 1], float((a64 * a64).sum()), rtol=1e-6)
+        assert s[2 * (1 - slot)] == 0.0 and s[2 * (1 - slot) + 1] == 0.0
+        _lib.check(L.cat_adv_normalize(adv.data_ptr(), adv.numel(), stats.data_ptr(), adv.numel(), stream), "norm")
+        want = (a64 - a64.mean()) / (a64.std() + 1e-8)
+        np.testing.assert_allclose(adv.cpu().numpy(), want.float().cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
 def test_step_is_cuda_graph_capturable(cuda_device):

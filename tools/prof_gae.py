@@ -23,7 +23,7 @@ v = torch.randn((T, M), device=dev, generator=g)
 d = (torch.rand((T, M), device=dev, generator=g) < 0.01).to(torch.uint8)
 lv = torch.randn((M,), device=dev, generator=g)
 ret, adv = torch.empty_like(r), torch.empty_like(r)
-stats = torch.zeros(2, dtype=torch.float64, device=dev)
+stats = torch.zeros(6, dtype=torch.float64, device=dev)
 flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
 stream = torch.cuda.current_stream(dev).cuda_stream
 n = T * M

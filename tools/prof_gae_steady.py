@@ -28,7 +28,7 @@ for _ in range(S):
     r = torch.randn((T, M), device=dev, generator=g); v = torch.randn((T, M), device=dev, generator=g)
     d = (torch.rand((T, M), device=dev, generator=g) < 0.01).to(torch.uint8)
     sets.append((r, v, d, torch.randn((M,), device=dev, generator=g), torch.empty_like(r), torch.empty_like(r),
-                 torch.zeros(2, dtype=torch.float64, device=dev)))
+                 torch.zeros(6, dtype=torch.float64, device=dev)))
 stream = torch.cuda.current_stream(dev).cuda_stream
 
 
