@@ -133,6 +133,7 @@ static bool pick_launch_shape(CatEnv* env, int n_worlds, LaunchShape* out) {
       out->threads = wpc * 32; out->smem = smem; out->grid = one_wave ? need : env->n_sm * occ;
     }
   }
+  if (const char* e = getenv("CAT_MAX_GRID")) { const int v = atoi(e); if (v >= 1 && v < out->grid) out->grid = v; }   // tuning knob
   if (best_score >= 0 && env->shape_cache.size() < 64) env->shape_cache.emplace_back(n_worlds, *out);
   return best_score >= 0;
 }
