@@ -253,6 +253,34 @@ def test_gae_statistics_buffer_protocol(cuda_device):
         np.testing.assert_allclose(adv.cpu().numpy(), want.float().cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
+def test_gae_distributed_statistics_path(cuda_device):
+    """compute_gae(distributed=True): the sums of the latest call are picked out of the two-slot statistics buffer on the
+    device, all-reduced with the count and handed to cat_adv_normalize — a one-rank group must reproduce the local result
+    on every call (odd and even: both slots)."""
+    import os
+    import torch.distributed as dist
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda_device)
+    try:
+        g = torch.Generator().manual_seed(5)
+        for T, M in ((32, 4096), (9, 160), (64, 48)):
+            r = torch.randn((T, M), generator=g).to(cuda_device)
+            v = torch.randn((T, M), generator=g).to(cuda_device)
+            d = (torch.rand((T, M), generator=g) < 0.05).to(cuda_device)
+            lv = torch.randn((M,), generator=g).to(cuda_device)
+            ret0, adv0 = compute_gae(r, d, v, lv)
+            ret1, adv1 = compute_gae(r, d, v, lv, distributed=True)
+            torch.testing.assert_close(ret1, ret0, rtol=0, atol=0)
+            torch.testing.assert_close(adv1, adv0, rtol=1e-5, atol=1e-6)
+            a = adv1.double()
+            assert abs(float(a.mean())) < 1e-4 and abs(float(a.std()) - 1.0) < 1e-3
+    finally:
+        dist.destroy_process_group()
+
+
 def test_step_is_cuda_graph_capturable(cuda_device):
     cmap = pu.named_cmap("squarinth")
     N = 1024
