@@ -60,13 +60,13 @@ class CatStepIO(C.Structure):
         ("obs_f32", C.c_void_p), ("state_f32", C.c_void_p), ("hit_point", C.c_void_p),
         ("obs_dist_world_stride", C.c_int32), ("obs_type_world_stride", C.c_int32),
         ("record", C.c_void_p), ("record_world_stride", C.c_int32),
-        ("critic_f32", C.c_void_p), ("obs_bf16", C.c_void_p), ("critic_bf16", C.c_void_p),
+        ("critic_f32", C.c_void_p), ("obs_bf16", C.c_void_p), ("critic_bf16", C.c_void_p), ("record_packed_types", C.c_int32),
     ]
 
 
 class CatRecordLayout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("bytes", "off_dist", "off_type", "off_reward", "off_terminated",
-                                         "off_truncated", "off_winner")]
+                                         "off_truncated", "off_winner", "type_bits")]
 
 
 class CatEnvInfo(C.Structure):
@@ -85,7 +85,7 @@ class CatStateView(C.Structure):
 #: every symbol ``include/cat_b200.h`` declares
 EXPORTS = (
     "cat_abi_version", "cat_last_error", "cat_env_create", "cat_env_destroy", "cat_env_info",
-    "cat_env_record_layout", "cat_env_overflow_counts", "cat_ray_lists_host",
+    "cat_env_record_layout", "cat_env_packed_record_layout", "cat_env_overflow_counts", "cat_ray_lists_host",
     "cat_env_set_seed", "cat_env_state_bytes", "cat_env_init_state", "cat_env_reset", "cat_env_step", "cat_env_step_host", "cat_env_observe",
     "cat_env_get_state", "cat_env_set_state", "cat_gae", "cat_adv_normalize",
 )
@@ -123,10 +123,11 @@ def load():
     L.cat_env_init_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     for fn in (L.cat_env_reset, L.cat_env_step, L.cat_env_observe):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStepIO), C.c_void_p]
-    L.cat_env_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.cat_env_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.cat_ray_lists_host.argtypes = [C.POINTER(CatMapDesc), C.c_int32, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double * 5),
                                      C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64)]
     L.cat_env_record_layout.argtypes = [C.c_void_p, C.POINTER(CatRecordLayout)]
+    L.cat_env_packed_record_layout.argtypes = [C.c_void_p, C.POINTER(CatRecordLayout)]
     L.cat_env_overflow_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 2), C.c_int32]
     for fn in (L.cat_env_get_state, L.cat_env_set_state):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CatStateView), C.c_void_p]

@@ -91,7 +91,7 @@ struct CatEnv {
   uint4* ray_slots_dev = nullptr;
   uint32_t* ray_ovf_dev = nullptr;
   unsigned long long* overflow_dev = nullptr;
-  CatRecordLayout rec{};
+  CatRecordLayout rec{}, rec_packed{};
   KParams kp{};
   CatEnvInfo info{};
   int smem_bytes = 0;
@@ -332,7 +332,11 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   CatRecordLayout& rc = env->rec;
   rc.off_dist = 0; rc.off_type = k.lay.r_off_type; rc.off_reward = k.lay.r_off_reward;
   rc.off_terminated = k.lay.r_off_flags; rc.off_truncated = k.lay.r_off_flags + 1; rc.off_winner = k.lay.r_off_flags + 2;
-  rc.bytes = k.lay.r_bytes;
+  rc.bytes = k.lay.r_bytes; rc.type_bits = 8;
+  CatRecordLayout& rp = env->rec_packed;   // the host-facing form: types packed 4 to a byte
+  rp.off_dist = 0; rp.off_type = k.lay.r_off_type; rp.off_reward = k.lay.rp_off_reward;
+  rp.off_terminated = k.lay.rp_off_flags; rp.off_truncated = k.lay.rp_off_flags + 1; rp.off_winner = k.lay.rp_off_flags + 2;
+  rp.bytes = k.lay.rp_bytes; rp.type_bits = 2;
   k.state_dim = 0;
   for (int a = 0; a < A; ++a) k.state_dim += 4 * R + 2 * (a < map->n_cops ? map->n_cops : map->n_thieves);
   k.dt = (float)pr->dt; k.inv_dt = (float)(1.0 / pr->dt);
@@ -421,6 +425,12 @@ int cat_env_record_layout(const CatEnv* env, CatRecordLayout* layout) {
   return CAT_OK;
 }
 
+int cat_env_packed_record_layout(const CatEnv* env, CatRecordLayout* layout) {
+  if (!env || !layout) return fail(CAT_ERR_INVALID, "null argument");
+  *layout = env->rec_packed;
+  return CAT_OK;
+}
+
 int cat_env_overflow_counts(CatEnv* env, uint64_t out[2], int32_t reset) {
   if (!env || !out) return fail(CAT_ERR_INVALID, "null argument");
   DEVICE_SCOPE(env);
@@ -470,8 +480,10 @@ static int prepare(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, 
     k.critic_f32 = io->critic_f32; k.obs_bf16 = io->obs_bf16; k.critic_bf16 = io->critic_bf16;
     if (io->record) {
       k.record = reinterpret_cast<unsigned char*>(io->record);
-      k.record_stride = io->record_world_stride ? io->record_world_stride : k.lay.r_bytes;
-      if ((reinterpret_cast<uintptr_t>(io->record) & 15) || (k.record_stride & 15) || k.record_stride < k.lay.r_bytes)
+      k.record_packed = io->record_packed_types ? 1 : 0;
+      const int rec_bytes = k.record_packed ? k.lay.rp_bytes : k.lay.r_bytes;
+      k.record_stride = io->record_world_stride ? io->record_world_stride : rec_bytes;
+      if ((reinterpret_cast<uintptr_t>(io->record) & 15) || (k.record_stride & 15) || k.record_stride < rec_bytes)
         return fail(CAT_ERR_INVALID, "record output must be 16-byte aligned with a world stride that is a multiple of 16 and >= CatRecordLayout.bytes");
       k.obs_dist = nullptr; k.obs_type = nullptr; k.reward = nullptr; k.terminated = nullptr; k.truncated = nullptr; k.winner = nullptr;
     }
@@ -503,7 +515,7 @@ int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* str
 // an internal copy stream (DMA engine, full PCIe rate) while the next chunk computes.  `stream` finally waits for
 // the copies, so one cudaStreamSynchronize(stream) by the caller makes every result visible.
 int cat_env_step_host(CatEnv* env, void* state_dev, const uint8_t* host_actions, void* records_dev, void* records_host,
-                      int32_t record_world_stride, int32_t n_chunks, void* stream_) {
+                      int32_t record_world_stride, int32_t packed_types, int32_t n_chunks, void* stream_) {
   if (!env || !host_actions || !records_dev || !records_host) return fail(CAT_ERR_INVALID, "null argument");
   const int N = env->n_worlds;
   if (n_chunks < 1) n_chunks = 1;
@@ -519,7 +531,7 @@ int cat_env_step_host(CatEnv* env, void* state_dev, const uint8_t* host_actions,
   }
   CatStepIO io{};
   io.actions = host_actions; io.actions_kind = 0;
-  io.record = records_dev; io.record_world_stride = record_world_stride;
+  io.record = records_dev; io.record_world_stride = record_world_stride; io.record_packed_types = packed_types;
   KParams k;
   const int rc = prepare(env, state_dev, &io, MODE_STEP, &k);
   if (rc != CAT_OK) return rc;

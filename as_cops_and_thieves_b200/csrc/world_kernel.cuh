@@ -68,6 +68,7 @@ struct Layout {
   int P, nrays, nrays_pad, maxc;
   int o_vel, o_vb, o_tc, o_wkey, o_wjn, o_page, o_pjn, o_sc, o_ep, o_flags, o_near, rec_words;
   int r_bytes, r_off_type, r_off_reward, r_off_flags;
+  int rp_bytes, rp_off_reward, rp_off_flags;   // the same record with the types packed 4 to a byte (host-facing path)
   int s_rdist, s_rtype, s_min, s_rcell, s_nearcnt, s_con, s_ccount, s_order, s_best, s_cand, scratch_bytes;
 };
 __host__ __device__ constexpr int layout_align(int v, int a) { return (v + a - 1) / a * a; }
@@ -83,6 +84,10 @@ __host__ __device__ constexpr Layout make_layout(int A, int R) {
   l.r_off_reward = layout_align(l.r_off_type + l.nrays, 4);
   l.r_off_flags = l.r_off_reward + 4 * A;
   l.r_bytes = layout_align(l.r_off_flags + 3, 16);
+  // ... and its host-facing form: the u8 types packed to 2 bits each, in place at the same offset; rewards and flags follow
+  l.rp_off_reward = layout_align(l.r_off_type + (l.nrays + 3) / 4, 4);
+  l.rp_off_flags = l.rp_off_reward + 4 * A;
+  l.rp_bytes = layout_align(l.rp_off_flags + 3, 16);
   int so = l.rec_words * 4;
   l.s_rdist = so; so = layout_align(so + l.r_bytes, 16);
   l.s_rtype = l.s_rdist + l.r_off_type;
@@ -148,6 +153,7 @@ struct KParams {
   float* hit_point;
   unsigned char* record;          // record output: one r_bytes block per world, record_stride apart
   int record_stride;
+  int record_packed;              // types packed 4 to a byte (rp_bytes per world): what crosses PCIe on the host path
   float* critic_f32;
   uint16_t* obs_bf16;
   uint16_t* critic_bf16;
@@ -997,11 +1003,7 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
   const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane, nrays = A * R;
   const float* pos = w.rec;
   if (k.record) {
-    // one record per world, staged contiguously: [f16 distance | u8 type | f32 reward | flags], 16-byte stores
-    uint4* dst = reinterpret_cast<uint4*>(k.record + (size_t)world * k.record_stride);
-    const uint4* src = reinterpret_cast<const uint4*>(w.rdist);
-#pragma unroll 1
-    for (int i = lane; i < (LAY(r_bytes) >> 4); i += 32) dst[i] = src[i];
+    // (shipped last, below: the packed form rewrites the staged types in place)
   } else if (k.obs_vec) {
     // 16-byte aligned world blocks (mapped pinned host memory): one or two 512-byte warp stores per array
     if (k.obs_dist) {
@@ -1074,6 +1076,57 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
     }
   }
   if (k.obs_f32 || k.state_f32 || k.critic_f32 || k.obs_bf16 || k.critic_bf16) write_flat_layouts(k, w.rdist, w.rtype, pos, world);
+  if (k.record) {
+    // one record per world, staged contiguously: [f16 distance | u8 type | f32 reward | flags], 16-byte stores
+    unsigned char* stage = reinterpret_cast<unsigned char*>(w.rdist);
+    int n16 = LAY(r_bytes) >> 4;
+    if (k.record_packed) {
+      // host-facing form (CatRecordLayout.type_bits == 2): 16 staged u8 types -> one 32-bit word, written back over the
+      // start of the type area (each round reads its 512 source bytes before any lane writes: the 128 bytes a round
+      // writes lie inside source bytes an earlier or the same round has read); rewards and flags move up behind them.
+      // Codes: wall 0, cop 1, thief 2, empty (TYPE_EMPTY = 4) 3.
+      const float rw = lane < A ? w.rew[lane] : 0.f;
+      const uint32_t fl = (uint32_t)w.flg[0] | ((uint32_t)w.flg[1] << 8) | ((uint32_t)w.flg[2] << 16);
+      const int nw = (nrays + 15) >> 4;
+#pragma unroll 1
+      for (int i0 = 0; i0 < nw; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t pk = 0u;
+        if (i < nw) {
+          const uint4 t = reinterpret_cast<const uint4*>(w.rtype)[i];
+          const uint32_t v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c = (v[j] & 0x03030303u) | (((v[j] >> 2) & 0x01010101u) * 3u);
+            pk |= ((c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu) << (8 * j);
+          }
+        }
+        __syncwarp();
+        if (i < nw) reinterpret_cast<uint32_t*>(w.rtype)[i] = pk;
+      }
+      __syncwarp();
+      // behind the packed types: zero up to the end of the packed record, then rewards and flags
+#pragma unroll 1
+      for (int i = (LAY(r_off_type) >> 2) + nw + lane; i < (LAY(rp_bytes) >> 2); i += 32) reinterpret_cast<uint32_t*>(stage)[i] = 0u;
+      __syncwarp();
+      if (lane < A) reinterpret_cast<float*>(stage + LAY(rp_off_reward))[lane] = rw;
+      if (lane == 0) *reinterpret_cast<uint32_t*>(stage + LAY(rp_off_flags)) = fl;
+      __syncwarp();
+      n16 = LAY(rp_bytes) >> 4;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(k.record + (size_t)world * k.record_stride);
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll 1
+    for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+    if (k.record_packed) {
+      // the staged record's own tail (rewards / flags / padding behind the u8 types) held packed-form bytes: restore
+      // what the next world expects there — zero padding (its rewards, flags and types are rewritten every step)
+      __syncwarp();
+#pragma unroll 1
+      for (int i = (LAY(r_off_type) >> 2) + lane; i < (LAY(r_bytes) >> 2); i += 32) reinterpret_cast<uint32_t*>(stage)[i] = 0u;
+      __syncwarp();
+    }
+  }
 }
 
 // cop.py:49-75 / thief.py:48-69 in fp32 from the f16 distance.

@@ -28,6 +28,18 @@ def _require_cuda(device: torch.device) -> None:
             f"(requested device={device}, torch.cuda.is_available()={torch.cuda.is_available()})")
 
 
+class HostRecords(dict):
+    """What ``CatWorlds.step_host`` returns: views of the pinned host record buffer.  With packed records ``obs_type`` is
+    not a view — it is decoded from ``obs_type_packed`` when asked for (and not cached: the buffer is rewritten by the
+    next call)."""
+    shape = (0, 0)
+
+    def __missing__(self, key):
+        if key == "obs_type" and "obs_type_packed" in self:
+            return CatWorlds.unpack_types(self["obs_type_packed"], *self.shape)
+        raise KeyError(key)
+
+
 class CatWorlds:
     def __init__(self, cmap: CompiledMap, n_worlds: int, *, device: Union[str, torch.device] = "cuda:0",
                  gid0: int = 0, params: Optional[EnvParams] = None, want_f32: bool = True,
@@ -94,6 +106,11 @@ class CatWorlds:
         _lib.check(self.L.cat_env_record_layout(self._h, C.byref(rl)), "cat_env_record_layout")
         self.record_layout = rl
         self.record_bytes = int(rl.bytes)
+        # the host-facing form of the same record: types packed to 2 bits each (what step_host moves over PCIe by default)
+        rp = CatRecordLayout()
+        _lib.check(self.L.cat_env_packed_record_layout(self._h, C.byref(rp)), "cat_env_packed_record_layout")
+        self.packed_record_layout = rp
+        self.packed_record_bytes = int(rp.bytes)
         self.pinned_outputs = bool(pinned_outputs)
 
         def alloc(shape, dtype):
@@ -123,25 +140,41 @@ class CatWorlds:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _record_views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Strided tensor views of a record buffer (``N * record_bytes`` uint8, device or pinned host)."""
-        N, A, R, rl, rb = self.n_worlds, self.A, self.R, self.record_layout, self.record_bytes
+    def _record_views(self, buf: torch.Tensor, packed: bool = False) -> Dict[str, torch.Tensor]:
+        """Strided tensor views of a record buffer (``N * record_bytes`` uint8, device or pinned host).  ``packed``: the
+        buffer holds the packed form — ``obs_type_packed`` (N, ceil(A R / 4)) uint8 instead of ``obs_type``."""
+        N, A, R = self.n_worlds, self.A, self.R
+        rl = self.packed_record_layout if packed else self.record_layout
+        rb = int(rl.bytes)
         f16, f32 = buf.view(torch.float16), buf.view(torch.float32)
-        return dict(
+        views = dict(
             obs_dist=f16.as_strided((N, A, R), (rb // 2, R, 1), rl.off_dist // 2),
-            obs_type=buf.as_strided((N, A, R), (rb, R, 1), rl.off_type),
             reward=f32.as_strided((N, A), (rb // 4, 1), rl.off_reward // 4),
             terminated=buf.as_strided((N,), (rb,), rl.off_terminated),
             truncated=buf.as_strided((N,), (rb,), rl.off_truncated),
             winner=buf.view(torch.int8).as_strided((N,), (rb,), rl.off_winner))
+        if packed:
+            views["obs_type_packed"] = buf.as_strided((N, (A * R + 3) // 4), (rb, 1), rl.off_type)
+        else:
+            views["obs_type"] = buf.as_strided((N, A, R), (rb, R, 1), rl.off_type)
+        return views
 
-    def _make_io(self, record: Optional[torch.Tensor] = None, extras: bool = True) -> CatStepIO:
+    @staticmethod
+    def unpack_types(packed: torch.Tensor, A: int, R: int) -> torch.Tensor:
+        """(N, ceil(A R / 4)) uint8 of a packed record -> (N, A, R) uint8 ObjectType values (CatRecordLayout: ray r is
+        bits 2 (r % 4) .. + 1 of byte r // 4; code 3 = EMPTY = 4)."""
+        shifts = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device=packed.device)
+        codes = ((packed.unsqueeze(-1) >> shifts) & 3).reshape(packed.shape[0], -1)[:, :A * R]
+        return (codes + (codes == 3).to(torch.uint8)).reshape(packed.shape[0], A, R)
+
+    def _make_io(self, record: Optional[torch.Tensor] = None, extras: bool = True, packed: bool = False) -> CatStepIO:
         def dp(t):
             return None if t is None or not extras else t.data_ptr()
         rec = self._out if record is None else record
         return CatStepIO(None, 0, None, None, None, None, None, None, None, dp(self.shared_dist), dp(self.shared_type),
                          dp(self.team_pos), dp(self.obs_f32), dp(self.state_f32), dp(self.hit_point), 0, 0,
-                         rec.data_ptr(), self.record_bytes, dp(self.critic_f32), dp(self.obs_bf16), dp(self.critic_bf16))
+                         rec.data_ptr(), self.packed_record_bytes if packed else self.record_bytes,
+                         dp(self.critic_f32), dp(self.obs_bf16), dp(self.critic_bf16), 1 if packed else 0)
 
     def overflow_counts(self, reset: bool = False):
         """(wall contacts beyond CAT_WALL_SLOTS, near hulls beyond CAT_NEAR_SLOTS) since creation / the last reset
@@ -210,37 +243,55 @@ class CatWorlds:
 
     @property
     def d2h_bytes_per_step(self) -> int:
-        """Bytes that cross to the host per ``step_host``: one output record per world (observations, rewards,
-        flags and the record's alignment padding — 832 B of which 825 are payload for 3 agents x 90 rays)."""
-        return self.n_worlds * self.record_bytes
+        """Bytes that cross to the host per ``step_host`` in its default (packed) form."""
+        return self.d2h_bytes(True)
 
-    def _host_buffers(self) -> Dict[str, torch.Tensor]:
-        """Pinned host record buffer (same layout as the device one), its strided views, and the I/O table that
-        points the kernel straight at it (pinned memory is mapped into the device's address space)."""
+    def d2h_bytes(self, packed: bool = True) -> int:
+        """One output record per world (observations, rewards, flags and the record's alignment padding): 640 B packed
+        (types at 2 bits), 832 B with u8 types, for 3 agents x 90 rays."""
+        return self.n_worlds * (self.packed_record_bytes if packed else self.record_bytes)
+
+    def _host_buffers(self, packed: bool = True) -> "HostRecords":
+        """Pinned host record buffer, its strided views, and the I/O table that points the kernel straight at it (pinned
+        memory is mapped into the device's address space); for the packed form also a device staging buffer of that
+        layout for the DMA strategies (the device-resident ``self._out`` keeps u8 types for device consumers)."""
         if self._host is None:
-            N, A = self.n_worlds, self.A
-            hb = torch.zeros(N * self.record_bytes, dtype=torch.uint8).pin_memory()
-            h = dict(blob=hb, actions_dev=torch.zeros((N, A), dtype=torch.uint8, device=self.device),
-                     actions_pinned=torch.zeros((N, A), dtype=torch.uint8).pin_memory(), **self._record_views(hb))
-            h["io"] = self._make_io(record=hb, extras=False)
+            self._host = {}
+        if packed not in self._host:
             if self.pinned_outputs:
                 raise _lib.CatError("step_host needs device-resident outputs (pinned_outputs=False)")
-            self._host = h
-        return self._host
+            N, A = self.n_worlds, self.A
+            rb = self.packed_record_bytes if packed else self.record_bytes
+            hb = torch.zeros(N * rb, dtype=torch.uint8).pin_memory()
+            h = HostRecords(blob=hb, actions_dev=torch.zeros((N, A), dtype=torch.uint8, device=self.device),
+                            actions_pinned=torch.zeros((N, A), dtype=torch.uint8).pin_memory(), **self._record_views(hb, packed))
+            h.shape = (A, self.R)
+            h["record_bytes"] = rb
+            h["io"] = self._make_io(record=hb, extras=False, packed=packed)
+            h["dev"] = torch.zeros(N * rb, dtype=torch.uint8, device=self.device) if packed else self._out
+            h["io_dev"] = self._make_io(record=h["dev"], extras=False, packed=packed)
+            self._host[packed] = h
+        return self._host[packed]
 
     def default_chunks(self) -> int:
         """Chunks for the pipelined host path: each chunk is one launch + one DMA copy of its records, the copy of
         chunk i overlapping the launch of chunk i + 1 (measured on B200, profiles/r2_notes.md)."""
         return 4 if self.n_worlds >= 2048 else 1
 
-    def step_host(self, host_actions: torch.Tensor, mode: str = "auto", chunks: Optional[int] = None
-                  ) -> Dict[str, torch.Tensor]:
+    def step_host(self, host_actions: torch.Tensor, mode: str = "auto", chunks: Optional[int] = None,
+                  packed: bool = True) -> "HostRecords":
         """``step`` for a caller whose buffers live in host memory (the reference's own calling convention):
         uint8 actions ``(N, A)`` in, and the step's observations, rewards and flags in pinned host memory
-        when the call returns (strided views of one record buffer).  Three ways to move the results, same bytes,
-        same values:
+        when the call returns (strided views of one record buffer: ``obs_dist`` f16, ``reward``, ``terminated``,
+        ``truncated``, ``winner``, and the types).
 
-        * ``"pipelined"`` (default) — ``cat_env_step_host``: the worlds are stepped in ``chunks`` launches; each
+        ``packed`` (default): the records cross PCIe in their packed form — ray types at 2 bits each, 640 B instead of
+        832 B per world; the result holds ``obs_type_packed`` (a view) and decodes ``obs_type`` (N, A, R) uint8 on first
+        access (``unpack_types``, a host-side bit unpack).  ``packed=False`` moves u8 types (``obs_type`` is a view).
+
+        Three ways to move the results, same bytes, same values:
+
+        * ``"pipelined"`` — ``cat_env_step_host``: the worlds are stepped in ``chunks`` launches; each
           chunk's block of records is DMA-copied with ONE ``cudaMemcpyAsync`` on a second stream while the next
           chunk computes; the kernel reads the actions straight from the pinned buffer.
         * ``"zero_copy"`` — one launch whose 16-byte stores go straight into mapped pinned host memory, so the
@@ -248,17 +299,17 @@ class CatWorlds:
         * ``"staged"`` — H2D copy, one launch, one D2H copy of the record buffer, strictly in sequence.
 
         ``"auto"`` (default) times the three on this environment's first calls (each trial is a real step) and keeps
-        the fastest: which one wins depends on the step's length and on how many GPUs share the host's PCIe root —
-        B200, one GPU: zero-copy (109 us for 4096 squarinth worlds, 351 us for 16384 agh-map worlds, against 136 / 365
-        pipelined and 141 / 470 staged; profiles/r2_notes.md).
+        the fastest: which one wins depends on the step's length and on how many GPUs share the host's PCIe root
+        (profiles/r2_notes.md: the SM-issued stores of zero-copy sustain 32-39 GB/s, a DMA copy 52 GB/s but a chunk's
+        launch lasts a whole single-wave step).
         """
         if mode == "auto":
-            mode = self._auto_mode()
+            mode = self._auto_mode(packed)
             if mode is None:
-                return self._auto_trial(host_actions)
+                return self._auto_trial(host_actions, packed)
         if mode not in ("pipelined", "zero_copy", "staged"):
             raise ValueError(f"unknown step_host mode {mode!r}")
-        h = self._host_buffers()
+        h = self._host_buffers(packed)
         if mode != "staged":
             if not host_actions.is_pinned():
                 h["actions_pinned"].copy_(host_actions)
@@ -271,35 +322,42 @@ class CatWorlds:
                 _lib.check(self.L.cat_env_step(self._h, self.state.data_ptr(), C.byref(io), self._stream()), "cat_env_step")
             else:
                 _lib.check(self.L.cat_env_step_host(self._h, self.state.data_ptr(), host_actions.data_ptr(),
-                                                    self._out.data_ptr(), h["blob"].data_ptr(), self.record_bytes,
-                                                    int(chunks or self.default_chunks()), self._stream()), "cat_env_step_host")
+                                                    h["dev"].data_ptr(), h["blob"].data_ptr(), h["record_bytes"],
+                                                    1 if packed else 0, int(chunks or self.default_chunks()),
+                                                    self._stream()), "cat_env_step_host")
         else:
             h["actions_dev"].copy_(host_actions, non_blocking=True)
-            io = self._io_bare()
+            io = h["io_dev"]
             io.actions, io.actions_kind = h["actions_dev"].data_ptr(), 0
             _lib.check(self.L.cat_env_step(self._h, self.state.data_ptr(), C.byref(io), self._stream()), "cat_env_step")
-            h["blob"].copy_(self._out, non_blocking=True)
+            h["blob"].copy_(h["dev"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return h
 
     _AUTO_ORDER = ("zero_copy", "pipelined", "staged")
     _AUTO_TRIALS = 4           # timed calls per mode (after one untimed call each)
 
-    def _auto_mode(self) -> Optional[str]:
-        return getattr(self, "_auto_choice", None)
+    def _auto_mode(self, packed: bool = True) -> Optional[str]:
+        return getattr(self, "_auto_choices", {}).get(packed)
 
-    def _auto_trial(self, host_actions: torch.Tensor) -> Dict[str, torch.Tensor]:
+    @property
+    def _auto_choice(self) -> Optional[str]:
+        return self._auto_mode(True)
+
+    def _auto_trial(self, host_actions: torch.Tensor, packed: bool = True) -> "HostRecords":
         import time
-        st = self.__dict__.setdefault("_auto_state", {"i": 0, "t": {m: [] for m in self._AUTO_ORDER}})
+        states = self.__dict__.setdefault("_auto_state", {})
+        st = states.setdefault(packed, {"i": 0, "t": {m: [] for m in self._AUTO_ORDER}})
         per = self._AUTO_TRIALS + 1
         mode = self._AUTO_ORDER[st["i"] // per]
         t0 = time.perf_counter()
-        h = self.step_host(host_actions, mode=mode)
+        h = self.step_host(host_actions, mode=mode, packed=packed)
         if st["i"] % per:                       # the first call of each mode allocates / warms up: not timed
             st["t"][mode].append(time.perf_counter() - t0)
         st["i"] += 1
         if st["i"] == per * len(self._AUTO_ORDER):
-            self._auto_choice = min(self._AUTO_ORDER, key=lambda m: sorted(st["t"][m])[len(st["t"][m]) // 2])
+            self.__dict__.setdefault("_auto_choices", {})[packed] = min(
+                self._AUTO_ORDER, key=lambda m: sorted(st["t"][m])[len(st["t"][m]) // 2])
             self.auto_mode_times = {m: sorted(v)[len(v) // 2] for m, v in st["t"].items()}
         return h
 

@@ -287,20 +287,20 @@ def time_steps_flushed(torch, cw, acts, K, W, flush):
     return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
 
 
-def time_e2e(torch, cw, K, W, dist=None, mode="auto"):
+def time_e2e(torch, cw, K, W, dist=None, mode="auto", packed=True):
     """The host-buffer API: pinned uint8 actions in, the step's records (observations / rewards / flags) back in
     pinned host memory when each call returns (CatWorlds.step_host)."""
     N, A = cw.n_worlds, cw.A
     host_acts = [torch.randint(0, 4, (N, A), dtype=torch.uint8).pin_memory() for _ in range(8)]
     for i in range(max(W, 16 if mode == "auto" else W)):     # (auto: its 15 tuning calls are warm-up, not timed)
-        cw.step_host(host_acts[i % 8], mode=mode)
+        cw.step_host(host_acts[i % 8], mode=mode, packed=packed)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        cw.step_host(host_acts[i % 8], mode=mode)   # synchronises: results are in host memory on return
+        cw.step_host(host_acts[i % 8], mode=mode, packed=packed)   # synchronises: results are in host memory on return
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -417,7 +417,8 @@ def measure_workload(torch, CatWorlds, name, K, W, rank, world_size, dev, dist, 
         ms_flushed = time_steps_flushed(torch, cw, acts, k_flush, 10, cross_check) / k_flush
     est_ms = ms_total / n_steps
     e2e_steps = max(50, min(2000, int(math.ceil(MIN_SPAN_MS / (2.5 * est_ms)))))
-    e2e_ms = {m: time_e2e(torch, cw, e2e_steps, 5, dist, mode=m) for m in e2e_modes}
+    # modes: "auto" / "zero_copy" / ... move the packed record (types at 2 bits); a "+u8" suffix moves u8 types
+    e2e_ms = {m: time_e2e(torch, cw, e2e_steps, 5, dist, mode=m.split("+")[0], packed=not m.endswith("+u8")) for m in e2e_modes}
     t = torch.tensor([ms_total] + [e2e_ms[m] for m in e2e_modes], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -446,11 +447,13 @@ def measure_workload(torch, CatWorlds, name, K, W, rank, world_size, dev, dist, 
            "steps": e2e_steps, "ms_per_step": e2e_ms[main] / e2e_steps,
            "api": "CatWorlds.step_host(host_actions) [mode='auto': keeps the fastest of zero-copy stores into mapped pinned "
                   "memory / chunked launches + one DMA copy per chunk / staged copies, timed on its first calls]: pinned u8 "
-                  "actions in, one 832-B record per world (f16 distances, u8 types, f32 rewards, u8 flags) back in pinned "
-                  "host memory on return",
+                  f"actions in, one {cw.packed_record_bytes}-B record per world (f16 distances, ray types packed at 2 bits, "
+                  "f32 rewards, u8 flags) back in pinned host memory on return; the '+u8' entries move the "
+                  f"{cw.record_bytes}-B record with u8 types instead",
            "auto_choice": getattr(cw, "_auto_choice", None)}
     for m in e2e_modes[1:]:
-        e2e[m] = {"value": n_global * A * e2e_steps / (e2e_ms[m] * 1e-3), "ms_per_step": e2e_ms[m] / e2e_steps}
+        e2e[m] = {"value": n_global * A * e2e_steps / (e2e_ms[m] * 1e-3), "ms_per_step": e2e_ms[m] / e2e_steps,
+                  "d2h_bytes_per_step": cw.d2h_bytes(not m.endswith("+u8"))}
     res = {
         "value": value, "ms_per_step": launch_ms, "steps_timed": n_steps, "timed_span_ms": ms_total, "blocks": blocks,
         "config": {"workload": name, "map": map_name, "hull_edges": int(cmap.n_edges), "worlds_per_gpu": per_gpu,
@@ -533,7 +536,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
 
     head, cmap = measure_workload(torch, CatWorlds, args.workload, K, W, rank, world_size, dev, dist, gen, worlds=args.worlds,
-                                  e2e_modes=("auto", "zero_copy", "pipelined", "staged"), cross_check=flush, sampler=sampler)
+                                  e2e_modes=("auto", "zero_copy", "pipelined", "staged", "auto+u8"), cross_check=flush, sampler=sampler)
     map_name, free, _ = WORKLOADS[args.workload]
     head["config"]["cpu_affinity"] = f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus else "unbound"
     line = {

@@ -140,15 +140,21 @@ typedef struct {
   /* bf16 copies of obs_f32 ([A][N][2R]) and critic_f32 ([N][4][R]) for mixed-precision learners (optional) */
   uint16_t* obs_bf16;
   uint16_t* critic_bf16;
+  /* != 0: `record` takes the PACKED form of the record (cat_env_packed_record_layout; types at 2 bits each, 640 B
+   * instead of 832 B per world for 3 agents x 90 rays) — the form meant to cross PCIe on the host-facing path. */
+  int32_t record_packed_types;
 } CatStepIO;
 
-/* byte offsets inside one world's output record (cat_env_record_layout) */
+/* byte offsets inside one world's output record (cat_env_record_layout / cat_env_packed_record_layout) */
 typedef struct {
   int32_t bytes;        /* record size = default world stride (multiple of 16) */
   int32_t off_dist;     /* f16 [A][R] */
-  int32_t off_type;     /* u8  [A][R] */
+  int32_t off_type;     /* type_bits == 8: u8 [A][R], ObjectType values (0 wall, 1 cop, 2 thief, 4 empty);
+                         * type_bits == 2: ray r = a * R + i of the world is bits 2 (r % 4) .. + 1 of byte r / 4,
+                         *   codes 0 wall, 1 cop, 2 thief, 3 empty */
   int32_t off_reward;   /* f32 [A] */
   int32_t off_terminated, off_truncated, off_winner; /* u8, u8, i8 */
+  int32_t type_bits;    /* 8 or 2 */
 } CatRecordLayout;
 
 typedef struct {
@@ -193,6 +199,8 @@ int cat_env_create(const CatMapDesc* map, const CatParams* params, int32_t n_wor
 int cat_env_destroy(CatEnv* env);
 int cat_env_info(const CatEnv* env, CatEnvInfo* info);
 int cat_env_record_layout(const CatEnv* env, CatRecordLayout* layout);
+/* the record with CatStepIO.record_packed_types != 0 (what cat_env_step_host moves when packed_types != 0) */
+int cat_env_packed_record_layout(const CatEnv* env, CatRecordLayout* layout);
 /* Fixed-capacity bookkeeping that the reference (Chipmunk) does not have: out[0] = wall contacts beyond
  * CAT_WALL_SLOTS per agent, out[1] = near hulls beyond CAT_NEAR_SLOTS per agent, summed over every launch since
  * creation (or since the last call with reset != 0).  Synchronises the device.  Zero means no world ever diverged
@@ -214,9 +222,11 @@ int cat_env_step(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream
  * record output (CatRecordLayout, stride record_world_stride) into `records_dev`; as soon as a chunk's launch has
  * finished its block of records is moved to `records_host` (pinned) with ONE cudaMemcpyAsync on an internal copy
  * stream while the next chunk computes.  host_actions: u8 [N][A] in pinned host memory, read by the kernel
- * directly.  `stream` waits for the copies: one cudaStreamSynchronize(stream) makes every result visible. */
+ * directly.  `stream` waits for the copies: one cudaStreamSynchronize(stream) makes every result visible.
+ * packed_types != 0: the records have the packed form (cat_env_packed_record_layout) — 23 % fewer bytes over PCIe. */
 int cat_env_step_host(CatEnv* env, void* state_dev, const uint8_t* host_actions, void* records_dev,
-                      void* records_host, int32_t record_world_stride, int32_t n_chunks, void* stream);
+                      void* records_host, int32_t record_world_stride, int32_t packed_types, int32_t n_chunks,
+                      void* stream);
 /* Entity.get_observation + get_shared_observations of the current state (entity.py:159-220,
  * observation_spaces.py:67-131) without stepping */
 int cat_env_observe(CatEnv* env, void* state_dev, const CatStepIO* io, void* stream);

@@ -101,7 +101,8 @@ def test_argument_validation_returns_error_codes_not_crashes():
     assert L.cat_env_state_bytes(None) == 0
     assert L.cat_env_record_layout(None, None) == -1
     assert L.cat_env_overflow_counts(None, None, 0) == -1
-    assert L.cat_env_step_host(None, None, None, None, None, 0, 1, None) == -1
+    assert L.cat_env_step_host(None, None, None, None, None, 0, 1, 1, None) == -1
+    assert L.cat_env_packed_record_layout(None, None) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -139,34 +139,61 @@ def test_action_input_forms_are_equivalent(cuda_device):
         e.close()
 
 
-def test_host_buffer_step_modes_are_equivalent(cuda_device):
+@pytest.mark.parametrize("packed", [True, False])
+def test_host_buffer_step_modes_are_equivalent(cuda_device, packed):
     """CatWorlds.step_host: the pipelined path (chunked launches + DMA on a second stream, cat_env_step_host), the
     zero-copy path (kernel stores into mapped pinned host memory) and the staged path (H2D copy -> launch -> D2H
-    copy) must deliver exactly the same bytes, equal to what the device-resident outputs hold."""
+    copy) must deliver exactly the same values, equal to what a device-resident step() holds — with the records in
+    their packed form (types at 2 bits, the default) and with u8 types."""
     cmap = pu.named_cmap("squarinth")
     N = 777
     envs = {m: CatWorlds(cmap, N, device=cuda_device, seed=5, want_f32=False, want_shared=False)
-            for m in ("pipelined", "pipelined5", "zero_copy", "staged")}
+            for m in ("pipelined", "pipelined5", "zero_copy", "staged", "device")}
     for w in envs.values():
         w.reset()
+    ref = envs["device"]
+    assert ref.d2h_bytes(True) == N * 640 and ref.d2h_bytes(False) == N * 832
     g = torch.Generator().manual_seed(3)
     for i in range(60):
         a = torch.randint(0, 4, (N, 3), dtype=torch.uint8, generator=g)
-        out = {"pipelined": envs["pipelined"].step_host(a.pin_memory(), mode="pipelined", chunks=2),
-               "pipelined5": envs["pipelined5"].step_host(a, mode="pipelined", chunks=5),
-               "zero_copy": envs["zero_copy"].step_host(a.pin_memory() if i % 2 else a, mode="zero_copy"),
-               "staged": envs["staged"].step_host(a.pin_memory(), mode="staged")}
-        ref = envs["staged"]
+        ref.step(a.to(cuda_device))
+        out = {"pipelined": envs["pipelined"].step_host(a.pin_memory(), mode="pipelined", chunks=2, packed=packed),
+               "pipelined5": envs["pipelined5"].step_host(a, mode="pipelined", chunks=5, packed=packed),
+               "zero_copy": envs["zero_copy"].step_host(a.pin_memory() if i % 2 else a, mode="zero_copy", packed=packed),
+               "staged": envs["staged"].step_host(a.pin_memory(), mode="staged", packed=packed)}
         for k in ("obs_dist", "obs_type", "reward", "terminated", "truncated", "winner"):
             want = getattr(ref, k).cpu().contiguous().view(torch.uint8)
             for m, h in out.items():
+                assert ("obs_type_packed" in h) == packed
                 assert h[k].shape == getattr(ref, k).shape
                 assert torch.equal(h[k].contiguous().view(torch.uint8), want), (i, k, m)
+        if packed:      # the padding of the packed record is zero: the whole buffer is deterministic
+            blobs = [h["blob"] for h in out.values()]
+            assert all(torch.equal(b, blobs[0]) for b in blobs[1:])
     for w in envs.values():
-        assert torch.equal(w.state, envs["staged"].state)
+        assert torch.equal(w.state, ref.state)
         w.close()
     with pytest.raises(ValueError):
         CatWorlds(cmap, 8, device=cuda_device).step_host(torch.zeros((8, 3), dtype=torch.uint8), mode="carrier-pigeon")
+
+
+def test_packed_records_on_a_ragged_shape(cuda_device):
+    """The packed record for a shape the <3, 90> instantiation does not cover (2 cops + 1 thief... with 37 rays: the
+    generic kernel, a type count that is not a multiple of 16)."""
+    cmap = pu.named_cmap("squarinth")
+    N = 130
+    kw = dict(device=cuda_device, seed=9, want_f32=False, want_shared=False, n_rays=37)
+    a_env, b_env = CatWorlds(cmap, N, **kw), CatWorlds(cmap, N, **kw)
+    a_env.reset(); b_env.reset()
+    g = torch.Generator().manual_seed(4)
+    for i in range(25):
+        a = torch.randint(0, 4, (N, 3), dtype=torch.uint8, generator=g)
+        a_env.step(a.to(cuda_device))
+        h = b_env.step_host(a, mode="zero_copy" if i % 2 else "staged", packed=True)
+        assert torch.equal(h["obs_type"], a_env.obs_type.cpu())
+        assert torch.equal(h["obs_dist"].contiguous().view(torch.int16), a_env.obs_dist.cpu().view(torch.int16))
+        assert torch.equal(h["reward"], a_env.reward.cpu()) and torch.equal(h["winner"], a_env.winner.cpu())
+    a_env.close(); b_env.close()
 
 
 def test_auto_reset_emits_terminal_reward_and_new_episode_observation(cuda_device):

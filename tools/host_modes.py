@@ -23,14 +23,15 @@ for name, N, free in cases:
     e1.record(); torch.cuda.synchronize()
     print(f"{name} x {N}: device-resident {e0.elapsed_time(e1) / 200 * 1e3:.1f} us/step; record {cw.record_bytes} B/world, {N * cw.record_bytes / 1e6:.2f} MB/step")
     modes = [("zero_copy", None), ("staged", None)] + [("pipelined", c) for c in (1, 2, 3, 4, 6, 8, 12, 16)]
-    for mode, ch in modes:
+    modes = [(m, c, True) for m, c in modes] + [("zero_copy", None, False), ("pipelined", 4, False)]
+    for mode, ch, packed in modes:
         for i in range(20):
-            cw.step_host(acts[i % 8], mode=mode, chunks=ch)
+            cw.step_host(acts[i % 8], mode=mode, chunks=ch, packed=packed)
         import time
         t0 = time.perf_counter()
         K = 300
         for i in range(K):
-            cw.step_host(acts[i % 8], mode=mode, chunks=ch)
+            cw.step_host(acts[i % 8], mode=mode, chunks=ch, packed=packed)
         dt = (time.perf_counter() - t0) / K
-        print(f"  {mode:10s} chunks={ch}: {dt * 1e6:7.1f} us/step  {N * cw.record_bytes / dt / 1e9:5.1f} GB/s D2H")
+        print(f"  {mode:10s} chunks={ch} {'packed' if packed else 'u8    '}: {dt * 1e6:7.1f} us/step  {cw.d2h_bytes(packed) / dt / 1e9:5.1f} GB/s D2H")
     cw.close()
