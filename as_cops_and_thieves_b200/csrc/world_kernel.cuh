@@ -1088,6 +1088,7 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
       const float rw = lane < A ? w.rew[lane] : 0.f;
       const uint32_t fl = (uint32_t)w.flg[0] | ((uint32_t)w.flg[1] << 8) | ((uint32_t)w.flg[2] << 16);
       const int nw = (nrays + 15) >> 4;
+      CAT_CHECK(LAY(r_off_type) + 16 * nw <= LAY(r_bytes) && LAY(rp_bytes) <= LAY(r_bytes) && LAY(r_off_type) + 4 * nw == LAY(rp_off_reward));
 #pragma unroll 1
       for (int i0 = 0; i0 < nw; i0 += 32) {
         const int i = i0 + lane;
@@ -1100,6 +1101,8 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
             const uint32_t c = (v[j] & 0x03030303u) | (((v[j] >> 2) & 0x01010101u) * 3u);
             pk |= ((c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu) << (8 * j);
           }
+          const int left = nrays - 16 * i;                 // the last word: bits beyond the world's rays stay zero
+          if (left < 16) pk &= (1u << (2 * left)) - 1u;
         }
         __syncwarp();
         if (i < nw) reinterpret_cast<uint32_t*>(w.rtype)[i] = pk;

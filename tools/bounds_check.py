@@ -49,6 +49,8 @@ for name, free, kw in cases + [("ragged", None, dict(n_rays=45)), ("ragged", Non
             cw.step(torch.randint(0, 4, (N, cw.A), dtype=torch.uint8, generator=g).cuda())
         cw.step_host(torch.randint(0, 4, (N, cw.A), dtype=torch.uint8, generator=g), mode="pipelined", chunks=3)
         cw.step_host(torch.randint(0, 4, (N, cw.A), dtype=torch.uint8, generator=g), mode="zero_copy")
+        cw.step_host(torch.randint(0, 4, (N, cw.A), dtype=torch.uint8, generator=g), mode="zero_copy", packed=False)
+        cw.step_host(torch.randint(0, 4, (N, cw.A), dtype=torch.uint8, generator=g), mode="staged", packed=False)
         torch.cuda.synchronize()
         L.cat_debug_stats(buf, 1)
         print(f"{name:12s} free={free} {kw} sensor={'lists' if ray_cell == 0 else 'rasteriser'}: {buf[6]} violations"
