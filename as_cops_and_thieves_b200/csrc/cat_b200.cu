@@ -499,8 +499,7 @@ static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, v
   const int rc = prepare(env, state_dev, io, mode, &k);
   if (rc != CAT_OK) return rc;
   DEVICE_SCOPE(env);
-  env->kernel<<<env->grid, env->threads, env->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(k);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(env->kernel, env->grid, env->threads, (size_t)env->smem_bytes, reinterpret_cast<cudaStream_t>(stream), k));
   return CAT_OK;
 }
 
@@ -543,8 +542,7 @@ int cat_env_step_host(CatEnv* env, void* state_dev, const uint8_t* host_actions,
     LaunchShape shp;
     if (!pick_launch_shape(env, n, &shp)) return fail(CAT_ERR_CUDA, "occupancy query failed");
     k.world_begin = w0; k.world_end = w1;
-    env->kernel<<<shp.grid, shp.threads, shp.smem, stream>>>(k);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(env->kernel, shp.grid, shp.threads, (size_t)shp.smem, stream, k));
     CUDA_TRY(cudaEventRecord(env->chunk_events[c], stream));
     CUDA_TRY(cudaStreamWaitEvent(env->copy_stream, env->chunk_events[c], 0));
     CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(records_host) + (size_t)w0 * stride, static_cast<const char*>(records_dev) + (size_t)w0 * stride,

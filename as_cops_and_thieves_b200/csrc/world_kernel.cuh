@@ -1519,6 +1519,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(k.blob_bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+        "l"(k.blob), "r"(k.blob_bytes), "r"(smem_u32(&mbar))
+        : "memory");
+  }
+  // Programmatic dependent launch (the host launches with programmatic stream serialisation): everything above — CTA
+  // scheduling, barrier set-up, the copy of the map, which no kernel ever writes — may run while the previous launch
+  // in the stream (the previous step) is still draining; nothing it wrote is touched before this wait returns.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // Prefetch this warp's first record while the map copy is in flight (with one world per warp, the usual case
   // at a few thousand worlds, both latencies would otherwise add up on the critical path).
   const long long first_world = k.world_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -1528,14 +1541,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     const float* g = k.state + (size_t)first_world * LAY(rec_words);
     if (lane < LAY(rec_words)) pf0 = g[lane];
     if (lane + 32 < LAY(rec_words)) pf1 = g[lane + 32];
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(k.blob_bytes)
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
-        "l"(k.blob), "r"(k.blob_bytes), "r"(smem_u32(&mbar))
-        : "memory");
   }
   {
     uint32_t done = 0;
