@@ -1510,6 +1510,7 @@ template <int TA, int TR>
 __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_constant__ KParams k) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int next_slot;   // the CTA's world queue (below)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // Stage the map once per CTA: one elected thread issues a TMA bulk copy (cp.async.bulk ->
@@ -1517,6 +1518,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    next_slot = (int)(blockDim.x >> 5);   // slots 0 .. warps-1 are the warps' first worlds
   }
   __syncthreads();
   if (tid == 0) {
@@ -1534,7 +1536,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // Prefetch this warp's first record while the map copy is in flight (with one world per warp, the usual case
   // at a few thousand worlds, both latencies would otherwise add up on the critical path).
-  const long long first_world = k.world_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const bool one_wave_launch = (long long)gridDim.x * (blockDim.x >> 5) >= k.world_end - k.world_begin;
+  const long long first_world = one_wave_launch ? k.world_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp
+                                                : k.world_begin + blockIdx.x + (long long)warp * gridDim.x;
   const bool prefetched = LAY(rec_words) <= 64 && k.mode != MODE_INIT && first_world < k.world_end;
   float pf0 = 0.f, pf1 = 0.f;
   if (prefetched) {
@@ -1586,18 +1590,26 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   for (int i = lane; i < (LAY(r_bytes) >> 2); i += 32) reinterpret_cast<uint32_t*>(w.rdist)[i] = 0u;
   __syncwarp();
   const int A = TA ? TA : k.A;
-  const int wpc = blockDim.x >> 5;   // warps per CTA: chosen per environment by the host (pick_launch_shape)
-  const long long stride = (long long)gridDim.x * wpc;
+  // Worlds to warps.  CTA c owns the worlds c, c + G, c + 2 G, ... of the launch (G = gridDim.x): every SM gets the same
+  // number of worlds to within one, whatever the world count — with contiguous blocks of `warps` worlds per CTA and round,
+  // 16384 worlds on 148 x 32 warps left 80 SMs with three rounds and 68 with four: the SMs were busy 77 % of the launch
+  // (ncu sm__cycles_active / elapsed, profiles/r2_notes.md).  Inside the CTA the warps draw their next world from a
+  // shared counter when they finish one (slot s = the CTA's s-th world), so a warp that met cheap worlds takes more of
+  // them and the CTA's last round is spread over all its warps' leftovers instead of pinned to the first few.
+  auto next_world_slot = [&]() {
+    int s_ = 0;
+    if (lane == 0) s_ = atomicAdd(&next_slot, 1);
+    return __shfl_sync(0xFFFFFFFFu, s_, 0);
+  };
+  // (a launch with a warp for every world keeps the contiguous numbering: neighbouring records stay in one CTA)
+  const int wpc = blockDim.x >> 5;
+  const bool one_wave = one_wave_launch;
 #pragma unroll 1
-  for (long long wbase = k.world_begin + (long long)blockIdx.x * wpc; wbase < k.world_end; wbase += stride) {
-#ifdef CAT_WORLD_SYNC
-    // (Round 1 re-aligned the CTA's warps here once per world for the instruction cache — the rasteriser's hot code
-    // was 38 KB.  The list walk's hot loop is ~3 KB and the barrier now costs more than it saves: 221 -> 207 us on
-    // agh-map x 16384 with 32-warp CTAs, profiles/r2_notes.md.  Kept as a build option.)
-    __syncthreads();
-#endif
-    const long long world = wbase + warp;
-    if (world >= k.world_end) continue;
+  for (int slot = warp;; slot = next_world_slot()) {
+    if (one_wave && slot >= wpc) break;
+    const long long world = one_wave ? k.world_begin + (long long)blockIdx.x * wpc + slot
+                                     : k.world_begin + blockIdx.x + (long long)slot * gridDim.x;
+    if (world >= k.world_end) break;
     float* grec = k.state + (size_t)world * LAY(rec_words);
     int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
 
