@@ -106,10 +106,11 @@ struct CatEnv {
 
 // the kernel instantiation an environment runs (fixed at creation): agents / rays as compile-time constants for the
 // shipped shape, the any-shape instantiation otherwise (CAT_GENERIC_KERNEL=1 at creation forces it: test knob)
-static WorldKernel pick_world_kernel(int A, int R) {
+static WorldKernel pick_world_kernel(int A, int R, bool lists) {
   const char* e = getenv("CAT_GENERIC_KERNEL");
   const bool generic = e && e[0] == '1';
-  return (A == 3 && R == 90 && !generic) ? cat_world_kernel<3, 90> : cat_world_kernel<0, 0>;
+  if (A == 3 && R == 90 && !generic) return lists ? cat_world_kernel<3, 90, true> : cat_world_kernel<3, 90, false>;
+  return cat_world_kernel<0, 0, false>;
 }
 
 static bool pick_launch_shape(CatEnv* env, int n_worlds, LaunchShape* out) {
@@ -362,7 +363,7 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   // The attribute belongs to the FUNCTION (per device), not to this environment: always raise it to the device
   // maximum, so creating an environment for a smaller map never lowers the cap of one that is still alive.
   cudaFuncAttributes fattr{};
-  env->kernel = pick_world_kernel(A, R);
+  env->kernel = pick_world_kernel(A, R, k.ray_slots != nullptr);
   CREATE_TRY(cudaFuncGetAttributes(&fattr, env->kernel), "cudaFuncGetAttributes");
   max_optin -= (int)fattr.sharedSizeBytes;      // the opt-in limit covers static + dynamic shared memory
   CREATE_TRY(cudaFuncSetAttribute(env->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin), "cudaFuncSetAttribute");

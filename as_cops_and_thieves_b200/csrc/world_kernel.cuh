@@ -767,11 +767,11 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
 // candidate lists (sweep_lists, lanes = rays) or, without lists, by rasterising the edges in view into a 1-D depth
 // buffer per agent (rasterise_agent, lanes = edges then (edge, ray) pairs).  Then, lanes = rays: the other agents'
 // circles and the alpha = 0 rules are merged in, and the hit point goes through the float16 chain.
-template <int TA, int TR>
+template <int TA, int TR, bool TL>
 __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world, bool staged,
                                               SlotStage& st) {
   const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane;
-  const bool lists = k.ray_slots != nullptr;
+  const bool lists = TL || k.ray_slots != nullptr;   // TL: an instantiation without the rasteriser
   if (lists && !staged) stage_ray_slots<TA, TR>(k, w, st);
   const float* pos = w.rec;
   const float* tc = w.rec + LAY(o_tc);
@@ -1505,8 +1505,9 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
 }
 
 // TA / TR: agents per world and rays per agent as compile-time constants (the 2 cops + 1 thief x 90 rays of every
-// shipped map: <3, 90>), or 0 = read them from the parameters (any other configuration: <0, 0>).
-template <int TA, int TR>
+// shipped map: <3, 90>), or 0 = read them from the parameters (any other configuration: <0, 0>).  TL: the environment
+// has ray lists (the default) — the instantiation carries no rasteriser code at all.
+template <int TA, int TR, bool TL>
 __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_constant__ KParams k) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -1640,7 +1641,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     bool captured = false, timeout = false;
     // the sensor sweep reads the PRE-step positions, which are known now: start fetching the rays' candidate slots
     bool staged = false;
-    if (do_step && k.ray_slots) { stage_ray_slots<TA, TR>(k, w, slot_stage); staged = true; }
+    if (do_step && (TL || k.ray_slots)) { stage_ray_slots<TA, TR>(k, w, slot_stage); staged = true; }
     if (do_step) {  // ---------------- base_env.py:354-383 ----------------
       const float* pos = w.rec;
       float* vel = w.rec + LAY(o_vel);
@@ -1690,7 +1691,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
       // is re-spawned in it emits the NEW episode's observation (C-10) and a terminal reward that does not depend
       // on what is seen, so its terminal sensor sweep would be thrown away: skip it.  With one world per warp the
       // launch lasts as long as its slowest warp, and a second sweep made every finishing world that warp.
-      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world<TA, TR>(k, m, w, world, staged, slot_stage);
+      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world<TA, TR, TL>(k, m, w, world, staged, slot_stage);
       bool again = false;
       if (do_step) {
         if (lane < A) w.rew[lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
