@@ -82,7 +82,8 @@ struct LaunchShape { int threads, smem, grid; };
 
 struct CatEnv {
   std::vector<std::pair<int, LaunchShape>> shape_cache;   // launch shape per world count (the chunked host path asks every step)
-  WorldKernel kernel = nullptr;
+  WorldKernel kernel = nullptr;        // every output the ABI offers
+  WorldKernel kernel_record = nullptr; // record output only (launches that ask for nothing else)
   int device = 0;
   int n_worlds = 0;
   unsigned char* blob_dev = nullptr;
@@ -106,11 +107,14 @@ struct CatEnv {
 
 // the kernel instantiation an environment runs (fixed at creation): agents / rays as compile-time constants for the
 // shipped shape, the any-shape instantiation otherwise (CAT_GENERIC_KERNEL=1 at creation forces it: test knob)
-static WorldKernel pick_world_kernel(int A, int R, bool lists) {
+static WorldKernel pick_world_kernel(int A, int R, bool lists, bool extras) {
   const char* e = getenv("CAT_GENERIC_KERNEL");
   const bool generic = e && e[0] == '1';
-  if (A == 3 && R == 90 && !generic) return lists ? cat_world_kernel<3, 90, true> : cat_world_kernel<3, 90, false>;
-  return cat_world_kernel<0, 0, false>;
+  if (A == 3 && R == 90 && !generic) {
+    if (lists) return extras ? cat_world_kernel<3, 90, true, true> : cat_world_kernel<3, 90, true, false>;
+    return cat_world_kernel<3, 90, false, true>;
+  }
+  return cat_world_kernel<0, 0, false, true>;
 }
 
 static bool pick_launch_shape(CatEnv* env, int n_worlds, LaunchShape* out) {
@@ -363,10 +367,13 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   // The attribute belongs to the FUNCTION (per device), not to this environment: always raise it to the device
   // maximum, so creating an environment for a smaller map never lowers the cap of one that is still alive.
   cudaFuncAttributes fattr{};
-  env->kernel = pick_world_kernel(A, R, k.ray_slots != nullptr);
+  env->kernel = pick_world_kernel(A, R, k.ray_slots != nullptr, true);
+  env->kernel_record = pick_world_kernel(A, R, k.ray_slots != nullptr, false);
   CREATE_TRY(cudaFuncGetAttributes(&fattr, env->kernel), "cudaFuncGetAttributes");
   max_optin -= (int)fattr.sharedSizeBytes;      // the opt-in limit covers static + dynamic shared memory
   CREATE_TRY(cudaFuncSetAttribute(env->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin), "cudaFuncSetAttribute");
+  if (env->kernel_record != env->kernel)
+    CREATE_TRY(cudaFuncSetAttribute(env->kernel_record, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin), "cudaFuncSetAttribute");
   env->blob_bytes = blob_bytes; env->max_optin = max_optin; env->n_sm = n_sm;
   LaunchShape shp;
   if (!pick_launch_shape(env, n_worlds, &shp)) { cat_env_destroy(env); return fail(CAT_ERR_CUDA, "occupancy query failed"); }
@@ -495,12 +502,19 @@ static int prepare(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, 
   return CAT_OK;
 }
 
+// the instantiation for this launch: the record-only one when the record is all it writes
+static WorldKernel kernel_for(const CatEnv* env, const KParams& k) {
+  const bool record_only = k.record && !k.shared_dist && !k.shared_type && !k.team_pos && !k.obs_f32 && !k.state_f32 &&
+                           !k.hit_point && !k.critic_f32 && !k.obs_bf16 && !k.critic_bf16;
+  return record_only ? env->kernel_record : env->kernel;
+}
+
 static int launch(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, void* stream) {
   KParams k;
   const int rc = prepare(env, state_dev, io, mode, &k);
   if (rc != CAT_OK) return rc;
   DEVICE_SCOPE(env);
-  CUDA_TRY(launch_pdl(env->kernel, env->grid, env->threads, (size_t)env->smem_bytes, reinterpret_cast<cudaStream_t>(stream), k));
+  CUDA_TRY(launch_pdl(kernel_for(env, k), env->grid, env->threads, (size_t)env->smem_bytes, reinterpret_cast<cudaStream_t>(stream), k));
   return CAT_OK;
 }
 
@@ -543,7 +557,7 @@ int cat_env_step_host(CatEnv* env, void* state_dev, const uint8_t* host_actions,
     LaunchShape shp;
     if (!pick_launch_shape(env, n, &shp)) return fail(CAT_ERR_CUDA, "occupancy query failed");
     k.world_begin = w0; k.world_end = w1;
-    CUDA_TRY(launch_pdl(env->kernel, shp.grid, shp.threads, (size_t)shp.smem, stream, k));
+    CUDA_TRY(launch_pdl(kernel_for(env, k), shp.grid, shp.threads, (size_t)shp.smem, stream, k));
     CUDA_TRY(cudaEventRecord(env->chunk_events[c], stream));
     CUDA_TRY(cudaStreamWaitEvent(env->copy_stream, env->chunk_events[c], 0));
     CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(records_host) + (size_t)w0 * stride, static_cast<const char*>(records_dev) + (size_t)w0 * stride,

@@ -767,7 +767,7 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
 // candidate lists (sweep_lists, lanes = rays) or, without lists, by rasterising the edges in view into a 1-D depth
 // buffer per agent (rasterise_agent, lanes = edges then (edge, ray) pairs).  Then, lanes = rays: the other agents'
 // circles and the alpha = 0 rules are merged in, and the hit point goes through the float16 chain.
-template <int TA, int TR, bool TL>
+template <int TA, int TR, bool TL, bool TX>
 __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m, const Warp& w, long long world, bool staged,
                                               SlotStage& st) {
   const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane;
@@ -909,7 +909,7 @@ __device__ __forceinline__ void observe_world(const KParams& k, const MapView& m
         CAT_CHECK(r < LAY(nrays) && (feat == kNoFeature || feat >= kAgentTag || (int)(feat >> 1) < k.n_edges));
         w.rdist[r] = dbits;
         w.rtype[r] = type;
-        if (k.hit_point) {
+        if (TX && k.hit_point) {
           float2* hp = reinterpret_cast<float2*>(k.hit_point) + (size_t)world * LAY(nrays) + r;
           *hp = make_float2(hx, hy);
         }
@@ -999,11 +999,11 @@ __device__ __noinline__ void write_flat_layouts(const KParams& k, const uint16_t
 // to this launch (a step); reset / observe launches leave the caller's reward / flag arrays alone, except in record
 // mode, where the whole record is one block (their staged values are then 0 / 0 / 0 / -1).
 template <int TA, int TR>
-__device__ __forceinline__ void write_observation(const KParams& k, const Warp& w, long long world, bool flags_too) {
+__device__ __forceinline__ void write_optional_outputs(const KParams& k, const Warp& w, long long world, bool flags_too) {
   const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane, nrays = A * R;
   const float* pos = w.rec;
   if (k.record) {
-    // (shipped last, below: the packed form rewrites the staged types in place)
+    // (shipped last, by write_record: the packed form rewrites the staged types in place)
   } else if (k.obs_vec) {
     // 16-byte aligned world blocks (mapped pinned host memory): one or two 512-byte warp stores per array
     if (k.obs_dist) {
@@ -1076,7 +1076,12 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
     }
   }
   if (k.obs_f32 || k.state_f32 || k.critic_f32 || k.obs_bf16 || k.critic_bf16) write_flat_layouts(k, w.rdist, w.rtype, pos, world);
-  if (k.record) {
+}
+
+template <int TA, int TR>
+__device__ __forceinline__ void write_record(const KParams& k, const Warp& w, long long world) {
+  const int A = TA ? TA : k.A, R = TR ? TR : k.R, lane = w.lane, nrays = A * R;
+  {
     // one record per world, staged contiguously: [f16 distance | u8 type | f32 reward | flags], 16-byte stores
     unsigned char* stage = reinterpret_cast<unsigned char*>(w.rdist);
     int n16 = LAY(r_bytes) >> 4;
@@ -1130,6 +1135,14 @@ __device__ __forceinline__ void write_observation(const KParams& k, const Warp& 
       __syncwarp();
     }
   }
+}
+
+// TX = false: the instantiation for launches that ask for the record and nothing else (the host picks it per launch) —
+// none of the optional outputs above is compiled in.
+template <int TA, int TR, bool TX>
+__device__ __forceinline__ void write_observation(const KParams& k, const Warp& w, long long world, bool flags_too) {
+  if (TX) write_optional_outputs<TA, TR>(k, w, world, flags_too);
+  if (TX ? k.record != nullptr : true) write_record<TA, TR>(k, w, world);
 }
 
 // cop.py:49-75 / thief.py:48-69 in fp32 from the f16 distance.
@@ -1506,8 +1519,9 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
 
 // TA / TR: agents per world and rays per agent as compile-time constants (the 2 cops + 1 thief x 90 rays of every
 // shipped map: <3, 90>), or 0 = read them from the parameters (any other configuration: <0, 0>).  TL: the environment
-// has ray lists (the default) — the instantiation carries no rasteriser code at all.
-template <int TA, int TR, bool TL>
+// has ray lists (the default) — the instantiation carries no rasteriser code at all.  TX = false: the launch wants the
+// output record only — none of the optional outputs (separate arrays, shared observations, fp32 / bf16 layouts, hit points).
+template <int TA, int TR, bool TL, bool TX>
 __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_constant__ KParams k) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -1691,7 +1705,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
       // is re-spawned in it emits the NEW episode's observation (C-10) and a terminal reward that does not depend
       // on what is seen, so its terminal sensor sweep would be thrown away: skip it.  With one world per warp the
       // launch lasts as long as its slowest warp, and a second sweep made every finishing world that warp.
-      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world<TA, TR, TL>(k, m, w, world, staged, slot_stage);
+      if (!(do_step && (captured || timeout) && k.auto_reset)) observe_world<TA, TR, TL, TX>(k, m, w, world, staged, slot_stage);
       bool again = false;
       if (do_step) {
         if (lane < A) w.rew[lane] = agent_reward(k, lane, w.minbits[lane], captured, timeout);
@@ -1707,7 +1721,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
         if (lane == 0) { w.flg[0] = 0; w.flg[1] = 0; w.flg[2] = 0xFF; }
       }
       __syncwarp();
-      if (!again) write_observation<TA, TR>(k, w, world, k.mode == MODE_STEP);
+      if (!again) write_observation<TA, TR, TX>(k, w, world, k.mode == MODE_STEP);
       __syncwarp();
       if (do_step) {
         physics_world<TA, TR>(k, m, w);  // base_env.py:392
