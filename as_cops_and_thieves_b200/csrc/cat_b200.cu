@@ -502,9 +502,9 @@ static int prepare(CatEnv* env, void* state_dev, const CatStepIO* io, int mode, 
   return CAT_OK;
 }
 
-// the instantiation for this launch: the record-only one when the record is all it writes
+// the instantiation for this launch: the record-only one for a step whose record is all it writes
 static WorldKernel kernel_for(const CatEnv* env, const KParams& k) {
-  const bool record_only = k.record && !k.shared_dist && !k.shared_type && !k.team_pos && !k.obs_f32 && !k.state_f32 &&
+  const bool record_only = k.mode == MODE_STEP && k.record && !k.shared_dist && !k.shared_type && !k.team_pos && !k.obs_f32 && !k.state_f32 &&
                            !k.hit_point && !k.critic_f32 && !k.obs_bf16 && !k.critic_bf16;
   return record_only ? env->kernel_record : env->kernel;
 }

@@ -1519,14 +1519,16 @@ __device__ __forceinline__ void reset_world(const KParams& k, const MapView& m, 
 
 // TA / TR: agents per world and rays per agent as compile-time constants (the 2 cops + 1 thief x 90 rays of every
 // shipped map: <3, 90>), or 0 = read them from the parameters (any other configuration: <0, 0>).  TL: the environment
-// has ray lists (the default) — the instantiation carries no rasteriser code at all.  TX = false: the launch wants the
-// output record only — none of the optional outputs (separate arrays, shared observations, fp32 / bf16 layouts, hit points).
+// has ray lists (the default) — the instantiation carries no rasteriser code at all.  TX = false: a STEP launch that wants the
+// output record only — none of the optional outputs (separate arrays, shared observations, fp32 / bf16 layouts, hit
+// points) and none of the init / reset / observe launch modes is compiled in.
 template <int TA, int TR, bool TL, bool TX>
 __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_constant__ KParams k) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ int next_slot;   // the CTA's world queue (below)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mode = TX ? k.mode : (int)MODE_STEP;   // the record-only instantiation serves step launches only (kernel_for)
 
   // Stage the map once per CTA: one elected thread issues a TMA bulk copy (cp.async.bulk ->
   // UBLKCP) that completes on an mbarrier; everyone else waits on the barrier's phase.
@@ -1554,7 +1556,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
   const bool one_wave_launch = (long long)gridDim.x * (blockDim.x >> 5) >= k.world_end - k.world_begin;
   const long long first_world = one_wave_launch ? k.world_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp
                                                 : k.world_begin + blockIdx.x + (long long)warp * gridDim.x;
-  const bool prefetched = LAY(rec_words) <= 64 && k.mode != MODE_INIT && first_world < k.world_end;
+  const bool prefetched = LAY(rec_words) <= 64 && mode != MODE_INIT && first_world < k.world_end;
   float pf0 = 0.f, pf1 = 0.f;
   if (prefetched) {
     const float* g = k.state + (size_t)first_world * LAY(rec_words);
@@ -1628,7 +1630,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     float* grec = k.state + (size_t)world * LAY(rec_words);
     int32_t* reci = reinterpret_cast<int32_t*>(w.rec);
 
-    if (k.mode == MODE_INIT) {  // fresh environment (entity.py:115,124): agents at map positions
+    if (mode == MODE_INIT) {  // fresh environment (entity.py:115,124): agents at map positions
 #pragma unroll 1
       for (int i = lane; i < LAY(rec_words); i += 32) {
         float v = 0.f;
@@ -1640,7 +1642,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
       }
       continue;
     }
-    if (k.mode == MODE_RESET && k.reset_mask && !k.reset_mask[world]) continue;
+    if (mode == MODE_RESET && k.reset_mask && !k.reset_mask[world]) continue;
 
     if (prefetched && world == first_world) {
       if (lane < LAY(rec_words)) w.rec[lane] = pf0;
@@ -1651,7 +1653,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
     }
     __syncwarp();
 
-    bool do_step = k.mode == MODE_STEP, do_reset = k.mode == MODE_RESET;
+    bool do_step = mode == MODE_STEP, do_reset = mode == MODE_RESET;
     bool captured = false, timeout = false;
     // the sensor sweep reads the PRE-step positions, which are known now: start fetching the rays' candidate slots
     bool staged = false;
@@ -1716,12 +1718,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
           w.flg[2] = (uint8_t)(done ? (captured ? 0 : 1) : -1);         // winner
         }
         again = done && k.auto_reset;  // emit the observation of the re-spawned state instead
-      } else if (k.mode != MODE_STEP) {
+      } else if (mode != MODE_STEP) {
         if (lane < A) w.rew[lane] = 0.f;
         if (lane == 0) { w.flg[0] = 0; w.flg[1] = 0; w.flg[2] = 0xFF; }
       }
       __syncwarp();
-      if (!again) write_observation<TA, TR, TX>(k, w, world, k.mode == MODE_STEP);
+      if (!again) write_observation<TA, TR, TX>(k, w, world, mode == MODE_STEP);
       __syncwarp();
       if (do_step) {
         physics_world<TA, TR>(k, m, w);  // base_env.py:392
@@ -1730,7 +1732,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cat_world_kernel(const __grid_
       }
       break;
     }
-    if (k.mode != MODE_OBSERVE) {
+    if (mode != MODE_OBSERVE) {
 #pragma unroll 1
       for (int i = lane; i < LAY(rec_words); i += 32) grec[i] = w.rec[i];
     }
