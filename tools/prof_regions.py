@@ -24,6 +24,12 @@ for key in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_i
     if key in rr[0]:
         i = rr[0].index(key)
         print(f"{key:70s} {rr[1][i]:10s} {rr[2][i]}")
+# the instantiation the report's kernel is: cat_world_kernel<3, 90, true, false> -> ILi3ELi90ELb1ELb0E
+kname = rr[2][rr[0].index("Kernel Name")] if "Kernel Name" in rr[0] else ""
+mt = re.search(r"cat_world_kernel<(\d+), (\d+), (true|false|0|1), (true|false|0|1)>", kname)
+INST = (f"ILi{mt.group(1)}ELi{mt.group(2)}ELb{int(mt.group(3) in ('true', '1'))}ELb{int(mt.group(4) in ('true', '1'))}E"
+        if mt else "cat_world_kernel")
+print("instantiation:", kname, INST)
 cur_func = cur_line = None
 addr2line = {}
 for l in open(tmp / "dis.txt"):
@@ -36,7 +42,7 @@ for l in open(tmp / "dis.txt"):
         cur_line = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
-    if m and cur_func and "cat_world_kernel" in cur_func:
+    if m and cur_func and "cat_world_kernel" in cur_func and INST in cur_func:
         addr2line[int(m.group(1), 16)] = cur_line
 rows = list(csv.reader(open(tmp / "src.csv")))
 for _i in range(2, len(rows)):          # several launches in one report: keep the first
