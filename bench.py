@@ -471,7 +471,7 @@ def measure_workload(torch, CatWorlds, name, K, W, rank, world_size, dev, dist, 
         "gpu_launches": n_steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                     "algorithmic_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP, "kernel": "cat_world_kernel<3, 90>",
+                     "algorithmic_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP, "kernel": "cat_world_kernel<3, 90, true, false>",
                      "instruction_throughput": issue,
                      "note": "ALU/latency-bound path (SURVEY.md §8d): the HBM fraction is reported as asked, not a target; "
                              "what bounds the kernel is instruction issue and dependent-instruction latency at 32 warps "
