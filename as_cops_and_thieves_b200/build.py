@@ -42,14 +42,28 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Build libcat_b200.so if it is missing or older than its sources.  Safe when several processes (one rank per GPU
+    under torchrun) get here at once: the check and the build run under a file lock, nvcc writes to a temporary name and
+    the finished library is renamed into place, so nobody ever loads a half-written file."""
     if up_to_date() and not force:
         return LIB
-    proc = subprocess.run(nvcc_cmd(), capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libcat_b200.so")
-    (PKG / "build_ptxas.log").write_text(proc.stdout + proc.stderr)
+    import fcntl
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if up_to_date() and not force:          # another process built it while we waited
+                return LIB
+            tmp = LIB.with_name(f".{LIB.name}.{os.getpid()}.tmp")
+            proc = subprocess.run(nvcc_cmd(tmp), capture_output=True, text=True)
+            if verbose or proc.returncode != 0:
+                sys.stderr.write(proc.stdout + proc.stderr)
+            if proc.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise RuntimeError("nvcc failed building libcat_b200.so")
+            os.replace(tmp, LIB)
+            (PKG / "build_ptxas.log").write_text(proc.stdout + proc.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
