@@ -78,9 +78,16 @@ static void build_ray_lists(const CatMapDesc* map, int R, double L, double rsum,
     br = std::max(br, map->hull_bb[4 * h + 2]); bt = std::max(bt, map->hull_bb[4 * h + 3]);
   }
   const double gx0 = bl - reach, gy0 = bb - reach, gw = br - bl + 2 * reach, gh = bt - bb + 2 * reach;
-  // automatic: about 16k cells (narrower strips = shorter lists = fewer edge tests per ray; measured on agh-map x 16384:
-  // 308 / 248 / 208 / 198 / 187 us per step at 48 / 32 / 19 / 16 / 12 units), not below 12 units
-  if (!(cell > 0.0)) cell = std::max(12.0, sqrt(gw * gh / 16384.0));
+  // automatic: about 64k cells, not below 6 units (narrower strips = shorter lists = fewer edge tests and fewer overflow
+  // links per ray).  Measured on agh-map x 16384, us per step: 308 / 248 / 208 / 198 / 187 at 48 / 32 / 19 / 16 / 12 units
+  // with the first list kernel; 137 / 129 / 124 / 121 / 120 at 13.6 / 10 / 8 / 6.8 / 6.3 units with the final one
+  // (33 / 58 / 88 / 120 / 136 MB of lists: HBM is not the scarce resource here, and the builder takes about a second).
+  if (!(cell > 0.0)) {
+    double target = 65536.0, min_cell = 6.0;
+    if (const char* e = getenv("CAT_RAY_LIST_CELLS")) { const double v = atof(e); if (v >= 64.0) target = v; }          // tuning knobs
+    if (const char* e = getenv("CAT_RAY_LIST_MIN_CELL")) { const double v = atof(e); if (v >= 1.0) min_cell = v; }
+    cell = std::max(min_cell, sqrt(gw * gh / target));
+  }
   const int nx = std::max(1, (int)ceil(gw / cell)), ny = std::max(1, (int)ceil(gh / cell));
   out->g.x0 = (float)gx0; out->g.y0 = (float)gy0; out->g.cell = (float)cell; out->g.inv_cell = (float)(1.0 / cell);
   out->g.nx = nx; out->g.ny = ny;

@@ -96,7 +96,7 @@ typedef struct {
   /* Sensor-sweep acceleration (never changes a result, tests/test_parity_gpu.py::test_candidate_lists_do_not_change_results):
    * the library builds, per cell of a uniform grid over the walls' reach and per ray index, the list of edges that
    * ray can touch from any origin in the cell, nearest first.  ray_list_cell = edge length of those cells in map
-   * units; 0 = choose automatically (about 16384 cells, not below 12 units); < 0 = no lists: every sweep rasterises
+   * units; 0 = choose automatically (about 65536 cells, not below 6 units: 60-120 MB of lists); < 0 = no lists: every sweep rasterises
    * the map's edges into the per-agent depth buffer (the slower, any-map path). */
   double ray_list_cell;
 } CatParams;

@@ -274,7 +274,7 @@ def test_ray_list_builder_matches_its_numpy_statement(name, free, cell):
     x0, y0, c, nx, ny = grid
     assert nx * ny * R == len(lib) and (cell == 0.0 or abs(c - cell) < 1e-6)
     if cell == 0.0:
-        assert 8000 <= nx * ny <= 20000 and c >= 12.0           # automatic: about 16k cells, not below 12 units
+        assert 30000 <= nx * ny <= 80000 and c >= 6.0           # automatic: about 64k cells, not below 6 units
         return
     tight = ray_lists(cmap, R, L, rsum, eps=0.5e-2, grid=grid, return_bounds=True)
     loose = ray_lists(cmap, R, L, rsum, eps=2e-2, grid=grid, return_bounds=True)
