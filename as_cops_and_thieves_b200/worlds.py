@@ -361,11 +361,6 @@ class CatWorlds:
             self.auto_mode_times = {m: sorted(v)[len(v) // 2] for m, v in st["t"].items()}
         return h
 
-    def _io_bare(self) -> CatStepIO:
-        if getattr(self, "_io_bare_cached", None) is None:
-            self._io_bare_cached = self._make_io(extras=False)
-        return self._io_bare_cached
-
     def synchronize(self) -> None:
         """Wait for the launches enqueued so far (needed before reading ``pinned_outputs`` tensors on the host)."""
         torch.cuda.current_stream(self.device).synchronize()
