@@ -1,3 +1,6 @@
+#!/bin/bash
+# Run on the GPU box (gpurun -- bash tools/capture_profiles.sh): the bench line, the ncu launch list and the ncu --set full
+# captures that tools/refresh_profiles.sh turns into the summaries under profiles/.  ncu runs only after the plain run exited 0.
 mkdir -p gpurun_out/r2f
 python bench.py --steps 60 --warmup 3 --no-extras > gpurun_out/r2f/bench_noextras.json 2> gpurun_out/r2f/bench_noextras.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2f/launches_bench.csv python bench.py --steps 40 --warmup 3 --no-extras > gpurun_out/r2f/ncu_launch.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Turn the raw ncu output of gpu_p.sh (gpurun_out/r2f/) into the tracked summaries under profiles/.
+# Turn the raw ncu output of tools/capture_profiles.sh (gpurun_out/r2f/) into the tracked summaries under profiles/.
 set -e
 D=gpurun_out/r2f
 python tools/summarize_profiles.py launches $D/launches_bench.csv profiles/r2_launches_bench_summary.txt "ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 : python bench.py --steps 40 --warmup 3 --no-extras   (agh-map-16384, round 2, final kernel)" > /dev/null

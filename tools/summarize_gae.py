@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """profiles/r2_gae_kernels.txt + gae_dram_bytes.json (+ the GAE entries of traffic.json) from the two ncu captures
-gpu_p.sh takes (gpurun_out/r2f/gae_T{256,1024}.ncu-rep)."""
+tools/capture_profiles.sh takes (gpurun_out/r2f/gae_T{256,1024}.ncu-rep)."""
 import importlib.util
 import json
 import sys
