@@ -81,3 +81,29 @@ def test_renderer_draws_walls_and_agents():
     assert tuple(img[350, 350]) == (0, 0, 255)         # cop blue
     assert tuple(img[450, 330]) == (255, 0, 0)         # thief red
     assert tuple(img[600, 400]) == (0, 0, 0)
+
+
+def test_packed_record_types_unpack_to_object_type_values():
+    """include/cat_b200.h CatRecordLayout, type_bits == 2: ray r of a world is bits 2 (r % 4) .. + 1 of byte r // 4,
+    codes wall 0 / cop 1 / thief 2 / empty 3 (= ObjectType EMPTY, 4).  The decoder of the host-facing path against a
+    plain numpy packing, on a ray count that is not a multiple of four."""
+    import numpy as np
+    import torch
+    from as_cops_and_thieves_b200.worlds import CatWorlds, HostRecords
+    rng = np.random.default_rng(0)
+    N, A, R = 5, 3, 37
+    types = rng.choice(np.array([0, 1, 2, 4], np.uint8), size=(N, A * R))
+    codes = np.where(types == 4, 3, types).astype(np.uint8)
+    padded = np.zeros((N, (A * R + 3) // 4 * 4), np.uint8)
+    padded[:, :A * R] = codes
+    q = padded.reshape(N, -1, 4)
+    packed = (q[..., 0] | (q[..., 1] << 2) | (q[..., 2] << 4) | (q[..., 3] << 6)).astype(np.uint8)
+    got = CatWorlds.unpack_types(torch.from_numpy(packed), A, R)
+    assert got.shape == (N, A, R) and got.dtype == torch.uint8
+    assert np.array_equal(got.numpy().reshape(N, -1), types)
+    h = HostRecords(obs_type_packed=torch.from_numpy(packed))
+    h.shape = (A, R)
+    assert np.array_equal(h["obs_type"].numpy().reshape(N, -1), types)      # decoded on request, not stored
+    assert "obs_type" not in h
+    with pytest.raises(KeyError):
+        h["no-such-view"]
