@@ -731,11 +731,14 @@ __device__ __forceinline__ void sweep_lists(const KParams& k, const MapView& m, 
       if (fin) {
         bool redo = false;
         if (!strict && bf != kNoFeature) {   // cpBBTree leaf rule on the winner
-          // the ray's centre at first touch lies on the thin ray: well inside the hull's box means the thin ray enters
-          // it — decided by 4 compares; only hits near the box's border (grazing rays) pay for the exact slab test
+          // a point of the thin ray well inside the hull's box means the thin ray enters it — decided by 4 compares; only
+          // grazing rays pay for the exact slab test.  The probe point lies rsum + 0.5 beyond the centre's position at
+          // first touch: at the touch the centre is still rsum away from the surface, i.e. OUTSIDE the box of a thin wall
+          // (the 3-unit walls of squarinth / lbirinth / grandbyrinth), and at up to 65 degrees of incidence the probe
+          // lands inside it.
           const float4 bb = m.hull_bb[m.edge_hull[bf >> 1]];
-          const float s = __uint_as_float(bs), px = fmaf(s, ux, ox), py = fmaf(s, uy, oy);
-          if (!(px > bb.x + 0.05f && px < bb.z - 0.05f && py > bb.y + 0.05f && py < bb.w - 0.05f)) {
+          const float sp = __uint_as_float(bs) + (rsum + 0.5f), px = fmaf(sp, ux, ox), py = fmaf(sp, uy, oy);
+          if (!(sp <= L && px > bb.x + 0.05f && px < bb.z - 0.05f && py > bb.y + 0.05f && py < bb.w - 0.05f)) {
             const float4 dv = m.dir[ci];
             redo = !thin_bb_hit(bb, ox, oy, dv.x == 0.f, dv.y == 0.f, dv.z * inv_L, dv.w * inv_L);
           }
