@@ -261,6 +261,16 @@ int cat_gae(const float* rewards, const uint8_t* dones, const float* values, con
  * the count and pass a zeroed CAT_GAE_STATS_DOUBLES buffer with the reduced sums in [0..1] (calls = 0 selects slot 0). */
 int cat_adv_normalize(float* advantages, int64_t n, const double* stats_dev, int64_t count, void* stream);
 
+/* Environment variables the library reads (tuning / test knobs; none is needed for normal use, results never depend on them):
+ *   CAT_GENERIC_KERNEL=1       cat_env_create: run the any-shape instantiation <0, 0> even for 3 agents x 90 rays (tests)
+ *   CAT_MAX_WARPS_PER_CTA=n    pick_launch_shape: cap the warps per CTA (2..32)
+ *   CAT_MAX_GRID=n             pick_launch_shape: cap the CTAs of a launch
+ *   CAT_RAY_LIST_CELLS=n       automatic list grid: target cell count (default 65536)
+ *   CAT_RAY_LIST_MIN_CELL=x    automatic list grid: smallest cell (default 6 units)
+ *   CAT_PDL=0                  launch without programmatic stream serialisation (read once per process)
+ *   CAT_GAE_TMA=0              cat_gae: use the register-pipelined kernel for every shape
+ * Python side: CAT_B200_LIB=path loads another build of this library (profiling / checked builds under variants/). */
+
 #ifdef __cplusplus
 }
 #endif
