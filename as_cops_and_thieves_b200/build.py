@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 SRC = PKG / "csrc" / "cat_b200.cu"
 LIB = PKG / "libcat_b200.so"
-DEPS = [SRC, *sorted((PKG / "csrc").glob("*.cuh")), ROOT / "include" / "cat_b200.h", ROOT / "include" / "cat_philox.h"]
+DEPS = [SRC, *sorted((PKG / "csrc").glob("*.cuh")), *sorted((PKG / "csrc").glob("*.h")), ROOT / "include" / "cat_b200.h", ROOT / "include" / "cat_philox.h"]
 
 
 def nvcc_path() -> str:
