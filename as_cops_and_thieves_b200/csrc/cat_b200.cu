@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <utility>
@@ -80,6 +81,30 @@ struct DeviceGuard {
 typedef void (*WorldKernel)(const KParams);
 struct LaunchShape { int threads, smem, grid; };
 
+// The (cell, ray) candidate lists depend on the map and the sensor parameters only: environments created on the same
+// device for the same map share ONE copy (reference-counted; built and uploaded by the first, freed with the last) — ten
+// environments on agh-map hold 120 MB of lists, not 1.2 GB, and creating the second one skips the second-long build.
+struct SharedRayLists {
+  std::vector<unsigned char> key;   // device, sensor parameters, grid rule and every map array the builder reads
+  uint4* slots_dev = nullptr;
+  uint32_t* ovf_dev = nullptr;
+  RayListGrid g{};
+  size_t slot_words = 0, ovf_words = 0;
+  int refs = 0;
+};
+static std::mutex g_ray_lists_mutex;
+static std::vector<SharedRayLists*> g_ray_lists;
+
+static void ray_lists_release(SharedRayLists* sh) {
+  if (!sh) return;
+  std::lock_guard<std::mutex> lock(g_ray_lists_mutex);
+  if (--sh->refs > 0) return;
+  g_ray_lists.erase(std::remove(g_ray_lists.begin(), g_ray_lists.end(), sh), g_ray_lists.end());
+  if (sh->slots_dev) cudaFree(sh->slots_dev);
+  if (sh->ovf_dev) cudaFree(sh->ovf_dev);
+  delete sh;
+}
+
 struct CatEnv {
   std::vector<std::pair<int, LaunchShape>> shape_cache;   // launch shape per world count (the chunked host path asks every step)
   WorldKernel kernel = nullptr;        // every output the ABI offers
@@ -89,8 +114,7 @@ struct CatEnv {
   unsigned char* blob_dev = nullptr;
   int32_t* view_off_dev = nullptr;
   uint16_t* view_edges_dev = nullptr;
-  uint4* ray_slots_dev = nullptr;
-  uint32_t* ray_ovf_dev = nullptr;
+  SharedRayLists* ray_lists = nullptr;   // shared with the other environments of this map on this device
   unsigned long long* overflow_dev = nullptr;
   CatRecordLayout rec{}, rec_packed{};
   KParams kp{};
@@ -318,17 +342,52 @@ int cat_env_create(const CatMapDesc* map, const CatParams* pr, int32_t n_worlds,
   // per-(cell, ray) candidate lists of the sensor sweep (ray_lists.h), built here from the map description
   CatEnvInfo& inf = env->info;
   if (!(pr->ray_list_cell < 0.0)) {
-    RayLists rl;
-    build_ray_lists(map, R, pr->ray_length, pr->wall_radius + pr->ray_radius, pr->ray_list_cell, &rl);
-    CREATE_TRY(cudaMalloc(&env->ray_slots_dev, rl.slots.size() * 4), "cudaMalloc(ray lists)");
-    CREATE_TRY(cudaMalloc(&env->ray_ovf_dev, rl.ovf.size() * 4), "cudaMalloc(ray lists)");
-    CREATE_TRY(cudaMemcpy(env->ray_slots_dev, rl.slots.data(), rl.slots.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(ray lists)");
-    CREATE_TRY(cudaMemcpy(env->ray_ovf_dev, rl.ovf.data(), rl.ovf.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(ray lists)");
-    k.ray_slots = env->ray_slots_dev; k.ray_ovf = env->ray_ovf_dev;
-    k.ray_slot_count = (unsigned)(rl.slots.size() / 4); k.ray_ovf_words = (unsigned)rl.ovf.size();
-    k.rg_x0 = rl.g.x0; k.rg_y0 = rl.g.y0; k.rg_inv_cell = rl.g.inv_cell; k.rg_nx = rl.g.nx; k.rg_ny = rl.g.ny;
-    inf.ray_list_cells = rl.g.nx * rl.g.ny; inf.ray_list_nx = rl.g.nx; inf.ray_list_ny = rl.g.ny; inf.ray_list_cell = rl.g.cell;
-    inf.ray_list_bytes = (int64_t)(rl.slots.size() + rl.ovf.size()) * 4;
+    const double rsum = pr->wall_radius + pr->ray_radius;
+    // key: everything build_ray_lists reads
+    std::vector<unsigned char> key;
+    auto put = [&key](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); key.insert(key.end(), b, b + n); };
+    const char* knob_cells = getenv("CAT_RAY_LIST_CELLS");
+    const char* knob_min = getenv("CAT_RAY_LIST_MIN_CELL");
+    const double head[6] = {(double)device, (double)R, pr->ray_length, rsum, pr->ray_list_cell,
+                            (knob_cells ? atof(knob_cells) : 0.0) * 4096.0 + (knob_min ? atof(knob_min) : 0.0)};
+    put(head, sizeof(head));
+    put(&H, sizeof(H)); put(&E, sizeof(E));
+    put(map->hull_off, sizeof(int32_t) * (H + 1));
+    put(map->vert, sizeof(double) * 2 * E);
+    put(map->normal, sizeof(double) * 2 * E);
+    put(map->hull_bb, sizeof(double) * 4 * H);
+    SharedRayLists* sh = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_ray_lists_mutex);
+      for (SharedRayLists* c : g_ray_lists)
+        if (c->key == key) { sh = c; break; }
+      if (!sh) {
+        RayLists rl;
+        build_ray_lists(map, R, pr->ray_length, rsum, pr->ray_list_cell, &rl);
+        sh = new SharedRayLists();
+        sh->key.swap(key);
+        sh->g = rl.g; sh->slot_words = rl.slots.size(); sh->ovf_words = rl.ovf.size();
+        cudaError_t e1 = cudaMalloc(&sh->slots_dev, rl.slots.size() * 4);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&sh->ovf_dev, rl.ovf.size() * 4) : e1;
+        if (e2 == cudaSuccess) e2 = cudaMemcpy(sh->slots_dev, rl.slots.data(), rl.slots.size() * 4, cudaMemcpyHostToDevice);
+        if (e2 == cudaSuccess) e2 = cudaMemcpy(sh->ovf_dev, rl.ovf.data(), rl.ovf.size() * 4, cudaMemcpyHostToDevice);
+        if (e2 != cudaSuccess) {
+          if (sh->slots_dev) cudaFree(sh->slots_dev);
+          if (sh->ovf_dev) cudaFree(sh->ovf_dev);
+          delete sh;
+          cat_env_destroy(env);
+          return fail(CAT_ERR_CUDA, std::string("ray lists: ") + cudaGetErrorString(e2));
+        }
+        g_ray_lists.push_back(sh);
+      }
+      ++sh->refs;
+    }
+    env->ray_lists = sh;
+    k.ray_slots = sh->slots_dev; k.ray_ovf = sh->ovf_dev;
+    k.ray_slot_count = (unsigned)(sh->slot_words / 4); k.ray_ovf_words = (unsigned)sh->ovf_words;
+    k.rg_x0 = sh->g.x0; k.rg_y0 = sh->g.y0; k.rg_inv_cell = sh->g.inv_cell; k.rg_nx = sh->g.nx; k.rg_ny = sh->g.ny;
+    inf.ray_list_cells = sh->g.nx * sh->g.ny; inf.ray_list_nx = sh->g.nx; inf.ray_list_ny = sh->g.ny; inf.ray_list_cell = sh->g.cell;
+    inf.ray_list_bytes = (int64_t)(sh->slot_words + sh->ovf_words) * 4;
   }
   k.n_worlds = n_worlds; k.gid0 = gid0;
   k.A = A; k.nc = map->n_cops; k.R = R;
@@ -395,8 +454,7 @@ int cat_env_destroy(CatEnv* env) {
   if (env->blob_dev) cudaFree(env->blob_dev);
   if (env->view_off_dev) cudaFree(env->view_off_dev);
   if (env->view_edges_dev) cudaFree(env->view_edges_dev);
-  if (env->ray_slots_dev) cudaFree(env->ray_slots_dev);
-  if (env->ray_ovf_dev) cudaFree(env->ray_ovf_dev);
+  ray_lists_release(env->ray_lists);
   if (env->overflow_dev) cudaFree(env->overflow_dev);
   for (cudaEvent_t e : env->chunk_events) cudaEventDestroy(e);
   if (env->copies_done) cudaEventDestroy(env->copies_done);
