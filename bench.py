@@ -464,7 +464,8 @@ def measure_workload(torch, CatWorlds, name, K, W, rank, world_size, dev, dist, 
                                     f"{cw.info.ray_list_cell:.1f} units, {cw.info.ray_list_bytes / 1e6:.1f} MB in HBM/L2"),
                    "launch": f"{cw.info.grid} CTAs x {cw.info.warps_per_cta} warps, {cw.info.smem_bytes_per_cta} B shared memory",
                    "l2": f"inputs larger than L2: the timed steps rotate over {len(sets)} independent sets of {n_local} worlds "
-                         f"({footprint * len(sets) / 1e6:.0f} MB of state + record buffers > 126 MB L2), one launch = one set; "
+                         f"({footprint * len(sets) / 1e6:.0f} MB of state + record buffers > 126 MB L2; the map's ray lists are read-only "
+                         f"constants shared by the sets, one copy per map and device as a single environment holds), one launch = one set; "
                          f"{blocks} block(s) of K steps, each between one CUDA-event pair, span {ms_total:.1f} ms",
                    "parallelism": f"worlds sharded over {world_size} GPU(s), no data-path collective"},
         "e2e": e2e,
